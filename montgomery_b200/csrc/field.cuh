@@ -1,0 +1,155 @@
+// Prime-field arithmetic on 32-bit limbs in Montgomery form, fully reduced to [0, p).
+//
+// Replaces the reference's runtime-generated Wasm field module (29-bit limbs in i64 locals):
+//   multiply / square      src/wasm/multiply-montgomery.ts:58-215
+//   add / subtract / ...   src/wasm/field-arithmetic.ts:32-176
+//   inverse                src/wasm/inverse.ts:191-218 (here: Fermat, a^(p-2))
+//   to/from Montgomery     src/field-msm.ts:179-185
+// Design differs on purpose: 32-bit limbs, CIOS with two accumulators ("even"/"odd" limb
+// alignment) so that every 32x32->64 product lands on an aligned register pair and ptxas emits
+// IMAD.WIDE.U32(.X) carry chains; values are kept canonical (< p) so equality is a limb compare.
+// All three base primes satisfy p = 1 (mod 2^32): the Montgomery quotient digit is m = -t0 and
+// the p[0]*m product is replaced by a carry (same shortcut as multiply-montgomery.ts:324-334).
+#pragma once
+#include "ptx.cuh"
+#include "constants_gen.cuh"
+
+namespace mgb {
+
+template <class P>
+struct Fe {
+  uint32_t v[P::N];
+};
+
+template <class P>
+struct Field {
+  static constexpr int N = P::N;
+  typedef Fe<P> fe;
+  static_assert(P::M0 == 0xffffffffu, "engine assumes p = 1 mod 2^32");
+  static_assert(N % 2 == 0, "even limb count");
+
+  MGB_DEV static fe zero() { fe r; _Pragma("unroll") for (int i = 0; i < N; i++) r.v[i] = 0; return r; }
+  MGB_DEV static fe one() { fe r; _Pragma("unroll") for (int i = 0; i < N; i++) r.v[i] = P::one(i); return r; }
+  MGB_DEV static fe modulus() { fe r; _Pragma("unroll") for (int i = 0; i < N; i++) r.v[i] = P::mod(i); return r; }
+
+  MGB_DEV static bool is_zero(const fe& a) {
+    uint32_t o = 0;
+    _Pragma("unroll") for (int i = 0; i < N; i++) o |= a.v[i];
+    return o == 0;
+  }
+  MGB_DEV static bool eq(const fe& a, const fe& b) {
+    uint32_t o = 0;
+    _Pragma("unroll") for (int i = 0; i < N; i++) o |= a.v[i] ^ b.v[i];
+    return o == 0;
+  }
+  MGB_DEV static fe select(bool c, const fe& a, const fe& b) {  // c ? a : b
+    fe r;
+    _Pragma("unroll") for (int i = 0; i < N; i++) r.v[i] = c ? a.v[i] : b.v[i];
+    return r;
+  }
+
+  // t (N limbs, < 2p) -> canonical
+  MGB_DEV static fe reduce_once(const uint32_t* t) {
+    uint32_t u[N];
+    u[0] = ptx::sub_cc(t[0], P::mod(0));
+    _Pragma("unroll") for (int i = 1; i < N; i++) u[i] = ptx::subc_cc(t[i], P::mod(i));
+    uint32_t borrow = ptx::subc(0, 0);
+    fe r;
+    _Pragma("unroll") for (int i = 0; i < N; i++) r.v[i] = borrow ? t[i] : u[i];
+    return r;
+  }
+
+  MGB_DEV static fe add(const fe& a, const fe& b) {
+    uint32_t t[N];
+    t[0] = ptx::add_cc(a.v[0], b.v[0]);
+    _Pragma("unroll") for (int i = 1; i < N - 1; i++) t[i] = ptx::addc_cc(a.v[i], b.v[i]);
+    t[N - 1] = ptx::addc(a.v[N - 1], b.v[N - 1]);  // 2p < 2^(32N): no carry out
+    return reduce_once(t);
+  }
+  MGB_DEV static fe dbl(const fe& a) { return add(a, a); }
+
+  MGB_DEV static fe sub(const fe& a, const fe& b) {
+    uint32_t t[N];
+    t[0] = ptx::sub_cc(a.v[0], b.v[0]);
+    _Pragma("unroll") for (int i = 1; i < N; i++) t[i] = ptx::subc_cc(a.v[i], b.v[i]);
+    uint32_t borrow = ptx::subc(0, 0);  // 0xffffffff if a < b
+    fe r;
+    r.v[0] = ptx::add_cc(t[0], P::mod(0) & borrow);
+    _Pragma("unroll") for (int i = 1; i < N - 1; i++) r.v[i] = ptx::addc_cc(t[i], P::mod(i) & borrow);
+    r.v[N - 1] = ptx::addc(t[N - 1], P::mod(N - 1) & borrow);
+    return r;
+  }
+  MGB_DEV static fe neg(const fe& a) { return sub(zero(), a); }
+
+  // Montgomery product a*b/R mod p, a, b < p.
+  // X/Y alternate as E (pairs on limbs 0,1|2,3|...) and O (pairs on limbs 1,2|3,4|...): t = E + O*2^32.
+  MGB_DEV static fe mul(const fe& fa, const fe& fb) {
+    const uint32_t* a = fa.v;
+    const uint32_t* b = fb.v;
+    uint32_t X[N], Y[N];
+    _Pragma("unroll") for (int i = 0; i < N; i++) {
+      uint32_t* E = (i & 1) ? Y : X;
+      uint32_t* O = (i & 1) ? X : Y;
+      const uint32_t bi = b[i];
+      if (i == 0) {
+        _Pragma("unroll") for (int j = 0; j < N; j += 2) { E[j] = ptx::mul_lo(a[j], bi); E[j + 1] = ptx::mul_hi(a[j], bi); }
+        _Pragma("unroll") for (int j = 0; j < N; j += 2) { O[j] = ptx::mul_lo(a[j + 1], bi); O[j + 1] = ptx::mul_hi(a[j + 1], bi); }
+      } else {
+        // O is last round's E: its limb 0 was cancelled, its limb 1 now has the weight of E[0];
+        // the carry of that add has the weight of O's (shifted) pair 0 and enters the chain.
+        E[0] = ptx::add_cc(E[0], O[1]);
+        _Pragma("unroll") for (int j = 0; j < N - 2; j += 2) {
+          O[j] = ptx::madc_lo_cc(a[j + 1], bi, O[j + 2]);
+          O[j + 1] = ptx::madc_hi_cc(a[j + 1], bi, O[j + 3]);
+        }
+        O[N - 2] = ptx::madc_lo_cc(a[N - 1], bi, 0);
+        O[N - 1] = ptx::madc_hi(a[N - 1], bi, 0);
+        _Pragma("unroll") for (int j = 0; j < N; j += 2) {
+          E[j] = (j == 0) ? ptx::mad_lo_cc(a[j], bi, E[j]) : ptx::madc_lo_cc(a[j], bi, E[j]);
+          E[j + 1] = ptx::madc_hi_cc(a[j], bi, E[j + 1]);
+        }
+        O[N - 1] = ptx::addc(O[N - 1], 0);
+      }
+      const uint32_t m = 0u - E[0];
+      _Pragma("unroll") for (int j = 0; j < N; j += 2) {
+        O[j] = (j == 0) ? ptx::mad_lo_cc(P::mod(j + 1), m, O[j]) : ptx::madc_lo_cc(P::mod(j + 1), m, O[j]);
+        O[j + 1] = ptx::madc_hi_cc(P::mod(j + 1), m, O[j + 1]);
+      }
+      // E pair 0 += p[0]*m with p[0] = 1: limb 0 becomes 0, carry (E[0] != 0) goes into limb 1
+      (void)ptx::add_cc(E[0], 0xffffffffu);
+      E[1] = ptx::addc_cc(E[1], 0);
+      _Pragma("unroll") for (int j = 2; j < N; j += 2) {
+        E[j] = ptx::madc_lo_cc(P::mod(j), m, E[j]);
+        E[j + 1] = ptx::madc_hi_cc(P::mod(j), m, E[j + 1]);
+      }
+      O[N - 1] = ptx::addc(O[N - 1], 0);
+    }
+    uint32_t* E = ((N - 1) & 1) ? Y : X;
+    uint32_t* O = ((N - 1) & 1) ? X : Y;
+    uint32_t t[N];
+    t[0] = ptx::add_cc(O[0], E[1]);
+    _Pragma("unroll") for (int j = 1; j < N - 1; j++) t[j] = ptx::addc_cc(O[j], E[j + 1]);
+    t[N - 1] = ptx::addc(O[N - 1], 0);
+    return reduce_once(t);
+  }
+  MGB_DEV static fe sqr(const fe& a) { return mul(a, a); }
+
+  MGB_DEV static fe to_mont(const fe& a) { fe r2; _Pragma("unroll") for (int i = 0; i < N; i++) r2.v[i] = P::r2(i); return mul(a, r2); }
+  MGB_DEV static fe from_mont(const fe& a) { fe o = zero(); o.v[0] = 1; return mul(a, o); }
+
+  // a^(p-2); a = 0 -> 0.  (Not inlined: one copy per kernel.)
+  MGB_NOINLINE_DEV static fe inv(const fe& a) {
+    fe r = one();
+    _Pragma("unroll 1") for (int k = N - 1; k >= 0; k--) {
+      uint32_t w = 0;
+      _Pragma("unroll") for (int kk = 0; kk < N; kk++) if (kk == k) w = P::pm2(kk);
+      _Pragma("unroll 1") for (int bit = 31; bit >= 0; bit--) {
+        r = sqr(r);
+        if ((w >> bit) & 1) r = mul(r, a);
+      }
+    }
+    return r;
+  }
+};
+
+}  // namespace mgb

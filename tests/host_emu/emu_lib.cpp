@@ -1,0 +1,79 @@
+// TEST-ONLY: compiles the engine's math headers (field.cuh, ec.cuh) for the host with an emulated
+// carry flag, so the formulas can be checked against the oracle without a GPU.  Not shipped, not
+// linked into the product library.
+#define MGB_HOST_EMU 1
+#include "../../montgomery_b200/csrc/ec.cuh"
+#include <cstring>
+using namespace mgb;
+
+template <class P> static Fe<P> ld(const uint32_t* p) { Fe<P> r; memcpy(r.v, p, sizeof(r.v)); return r; }
+template <class P> static void st(uint32_t* p, const Fe<P>& a) { memcpy(p, a.v, sizeof(a.v)); }
+
+template <class P> static void fe_op(int op, uint32_t* out, const uint32_t* a, const uint32_t* b) {
+  typedef Field<P> F;
+  Fe<P> x = ld<P>(a), y = ld<P>(b), r;
+  switch (op) {
+    case 0: r = F::mul(x, y); break;
+    case 1: r = F::add(x, y); break;
+    case 2: r = F::sub(x, y); break;
+    case 3: r = F::inv(x); break;
+    case 4: r = F::to_mont(x); break;
+    case 5: r = F::from_mont(x); break;
+    case 6: r = F::sqr(x); break;
+    case 7: r = F::neg(x); break;
+    default: r = F::zero();
+  }
+  st<P>(out, r);
+}
+
+// Weierstrass ops on Montgomery-form coordinates.  Affine = 2N limbs (+inf flag in x top bit), XYZZ = 4N limbs.
+template <class P> static void w_op(int op, uint32_t* out, const uint32_t* a, const uint32_t* b) {
+  typedef Weierstrass<P> W;
+  typedef Field<P> F;
+  constexpr int N = P::N;
+  auto lda = [&](const uint32_t* p) { typename W::affine r; r.x = ld<P>(p); r.y = ld<P>(p + N); return r; };
+  auto ldx = [&](const uint32_t* p) { typename W::acc r; r.X = ld<P>(p); r.Y = ld<P>(p + N); r.ZZ = ld<P>(p + 2 * N); r.ZZZ = ld<P>(p + 3 * N); return r; };
+  auto sta = [&](const typename W::affine& r) { st<P>(out, r.x); st<P>(out + N, r.y); };
+  auto stx = [&](const typename W::acc& r) { st<P>(out, r.X); st<P>(out + N, r.Y); st<P>(out + 2 * N, r.ZZ); st<P>(out + 3 * N, r.ZZZ); };
+  switch (op) {
+    case 0: {  // affine + affine through prepare / invert / finish
+      auto A = lda(a), B = lda(b);
+      Fe<P> den; int kind = W::add_prepare(A, B, den);
+      sta(W::add_finish(kind, A, B, F::inv(den)));
+      break;
+    }
+    case 1: stx(W::madd(ldx(a), lda(b))); break;
+    case 2: stx(W::add(ldx(a), ldx(b))); break;
+    case 3: stx(W::dbl(ldx(a))); break;
+    case 4: sta(W::to_affine(ldx(a))); break;
+    case 5: stx(W::from_affine(lda(a))); break;
+  }
+}
+
+template <class P, class C> static void te_op(int op, uint32_t* out, const uint32_t* a, const uint32_t* b) {
+  typedef TwistedEdwards<P, C> T;
+  constexpr int N = P::N;
+  auto lde = [&](const uint32_t* p) { typename T::acc r; r.X = ld<P>(p); r.Y = ld<P>(p + N); r.Z = ld<P>(p + 2 * N); r.T = ld<P>(p + 3 * N); return r; };
+  auto lda = [&](const uint32_t* p) { typename T::affine r; r.x = ld<P>(p); r.y = ld<P>(p + N); r.kt = ld<P>(p + 2 * N); return r; };
+  auto ste = [&](const typename T::acc& r) { st<P>(out, r.X); st<P>(out + N, r.Y); st<P>(out + 2 * N, r.Z); st<P>(out + 3 * N, r.T); };
+  switch (op) {
+    case 0: ste(T::add(lde(a), lde(b))); break;
+    case 1: ste(T::madd(lde(a), lda(b))); break;
+    case 2: ste(T::add_affine(lda(a), lda(b))); break;
+    case 3: ste(T::dbl(lde(a))); break;
+    case 4: { Fe<P> x, y; T::to_affine(lde(a), x, y); st<P>(out, x); st<P>(out + N, y); break; }
+  }
+}
+
+extern "C" {
+void emu_fe_op(int field, int op, uint32_t* out, const uint32_t* a, const uint32_t* b) {
+  if (field == 0) fe_op<Fp377>(op, out, a, b);
+  else if (field == 1) fe_op<Fr377>(op, out, a, b);
+  else fe_op<FpPallas>(op, out, a, b);
+}
+void emu_w_op(int curve, int op, uint32_t* out, const uint32_t* a, const uint32_t* b) {
+  if (curve == 0) w_op<Fp377>(op, out, a, b);
+  else w_op<FpPallas>(op, out, a, b);
+}
+void emu_te_op(int op, uint32_t* out, const uint32_t* a, const uint32_t* b) { te_op<Fr377, Ed377Consts>(op, out, a, b); }
+}
