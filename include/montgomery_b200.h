@@ -1,0 +1,132 @@
+/* montgomery_b200 -- C ABI of the B200-native MSM engine.
+ *
+ * This is the drop-in boundary for the MSM hot path of mitschabaude/montgomery.  The reference has
+ * no FFI: its seam is the TypeScript object built by `createMsm` / `createMsmBasic` and registered
+ * as `Parallel.msm / msmUnsafe` (src/msm-batched-affine.ts:45-51,585-599, src/msm-basic.ts:34-43,
+ * src/parallel.ts:135-145,251-259), plus the value-typed `compute_msm(points, scalars)` wrappers
+ * (scripts/zprize23/submission-bls377.ts:20-65, scripts/zprize23/submission.ts:19-35).  Each entry
+ * point below names the reference interface it replaces.  INTEGRATION.md shows the N-API / ctypes
+ * bindings that sit on top.
+ *
+ * Conventions: every function returns 0 on success and a negative MGB_E_* code on failure (never
+ * throws or aborts across the ABI); `mgb_last_error` gives the message.  The caller owns all host
+ * buffers; the context owns all device memory and its stream.  One in-flight call per context.
+ * Byte formats are the reference's (src/parallel.ts:97-133,209-249): scalar = 32 bytes little
+ * endian; Weierstrass point = x||y, each ceil(bits/8) bytes LE (2*48 for BLS12-377, 2*32 for
+ * Pallas); twisted-Edwards point = x||y, 2*32 bytes LE.  The result is the canonical affine point
+ * (coordinates in [0,p), LE) plus an is_zero flag (Weierstrass infinity -> x = y = 0, flag 1, as
+ * src/curve-affine.ts:369-371; twisted-Edwards neutral -> (0,1), flag 1).
+ */
+#ifndef MONTGOMERY_B200_H
+#define MONTGOMERY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mgb_ctx mgb_ctx;
+
+enum mgb_curve {
+  MGB_BLS12_377_G1 = 0,     /* src/concrete/bls12-377.params.ts, msm-batched-affine + GLV   */
+  MGB_PALLAS = 1,           /* src/concrete/pasta.params.ts, msm-batched-affine + GLV       */
+  MGB_ED_ON_BLS12_377 = 2   /* src/concrete/ed-on-bls12-377.params.ts, msm-basic, no GLV    */
+};
+
+enum mgb_error {
+  MGB_OK = 0,
+  MGB_E_INVALID = -1,   /* bad argument (null pointer, n > capacity, unknown curve, c out of range) */
+  MGB_E_CUDA = -2,      /* a CUDA runtime call failed; message has the CUDA error string             */
+  MGB_E_NOMEM = -3,     /* device memory exhausted (the reference's "memory overflow" error,
+                           src/wasm/memory-helpers.ts:225-236)                                         */
+  MGB_E_STATE = -4      /* msm called before points were set                                          */
+};
+
+/* Per-call options; mirrors `{c?, useSafeAdditions?}` of msm-batched-affine.ts:74-77 and
+ * `{c?}` of msm-basic.ts:35-41.  c = 0 picks the engine's window size.  `unsafe` is accepted for
+ * API parity with `msmUnsafe`; the engine's additions are always complete, so it changes nothing. */
+typedef struct mgb_opts {
+  int c;
+  int unsafe;
+  int verbose;
+} mgb_opts;
+
+/* Per-phase device times in milliseconds (CUDA events on the context's stream); the analogue of
+ * the `log` array returned by msm() (src/msm-common.ts:176-213) with the same phase boundaries. */
+typedef struct mgb_timing {
+  float h2d_scalars;        /* host->device copy of the scalars (0 for the device-resident entry)   */
+  float decompose_slice;    /* "prepare points & scalars" + "slice scalars & count buckets"          */
+  float sort;               /* "integrate bucket counts" + "sort points"                             */
+  float accumulate;         /* "bucket accumulation"                                                  */
+  float reduce;             /* "normalize bucket storage" + "bucket reduction"                        */
+  float final_sum;          /* "partition sum" + "final sum" + affine normalisation                   */
+  float total;              /* whole call on the device, first kernel to result available             */
+  int c, K, rounds;         /* window bits, number of windows, accumulation rounds                    */
+  uint32_t max_bucket;      /* largest bucket (maxBucketSize, msm-batched-affine.ts:208)             */
+  uint64_t n_pairs;         /* affine / mixed additions performed in the accumulation phase          */
+  uint32_t n_launches;      /* kernels launched by this call                                          */
+} mgb_timing;
+
+/* Replaces `Weierstrass.create(params)` / `TwistedEdwards.create(params)` + `startThreads()`
+ * (src/parallel.ts:40,179,291): builds the engine for one curve on one GPU.  `max_points` bounds n
+ * of later calls (the reference bounds it by its 4 GiB wasm memory, src/field-msm.ts:55-56). */
+int mgb_create(mgb_ctx** out, int curve, int device, size_t max_points);
+
+/* Replaces `Parallel.pointsFromBytes` (src/parallel.ts:97-116, :209-232): uploads n points given as
+ * x||y LE bytes and converts them to the device layout (Montgomery form).  `is_zero` is optional
+ * (NULL = no point at infinity, as in the reference's byte format); a non-zero byte marks point i
+ * as the neutral element (the reference's `isNonZero` flag, src/curve-affine.ts:20-52). */
+int mgb_set_points(mgb_ctx* ctx, const uint8_t* xy_le, const uint8_t* is_zero, size_t n);
+
+/* Replaces `Parallel.randomPointsFast(n)` (src/curve-random.ts:24-92): fills the context with n
+ * points a_i*G, a_i a seeded 64-bit value (splitmix64 of seed and i), built on the device from
+ * window tables of the generator.  Deterministic; used for benchmarks and closed-form checks. */
+int mgb_random_points(mgb_ctx* ctx, uint64_t seed, size_t n);
+
+/* Reads back points [first, first+n) as canonical x||y LE bytes (`Affine.toBigint`,
+ * src/curve-affine.ts:220-233); is_zero may be NULL. */
+int mgb_get_points(mgb_ctx* ctx, size_t first, size_t n, uint8_t* xy_le, uint8_t* is_zero);
+
+/* Replaces `Parallel.msm / msmUnsafe(scalarPtr, pointPtr, N)` followed by `Projective.toAffine` +
+ * `Affine.toBigint` (src/msm-batched-affine.ts:69-340, scripts/msm-weierstrass.ts:90-92), or
+ * `msmBasic` + `toAffine` for the twisted-Edwards curve (src/msm-basic.ts:45-164).  Scalars are n
+ * host values of 32 bytes LE, paired with the first n points of the context.  n = 0 gives the
+ * neutral element.  opts and timing may be NULL. */
+int mgb_msm(mgb_ctx* ctx, const uint8_t* scalars_le32, size_t n, const mgb_opts* opts,
+            uint8_t* out_xy_le, int* out_is_zero, mgb_timing* timing);
+
+/* Same with scalars already in device memory (device pointer), for kernel-only timing. */
+int mgb_msm_device(mgb_ctx* ctx, const void* d_scalars_le32, size_t n, const mgb_opts* opts,
+                   uint8_t* out_xy_le, int* out_is_zero, mgb_timing* timing);
+
+/* Multi-GPU path (replaces the SPMD thread split of src/threads/threads.ts:354-359): each rank
+ * runs the MSM on its shard and leaves the partial sum, un-normalised, in a caller-provided DEVICE
+ * buffer of mgb_partial_bytes() bytes (to be all-gathered over NCCL by the host layer);
+ * mgb_combine_partials adds `count` gathered partials (device buffer) and normalises. */
+size_t mgb_partial_bytes(const mgb_ctx* ctx);
+int mgb_msm_partial(mgb_ctx* ctx, const void* scalars, int scalars_on_device, size_t n,
+                    const mgb_opts* opts, void* d_partial_out, mgb_timing* timing);
+int mgb_combine_partials(mgb_ctx* ctx, const void* d_partials, int count,
+                         uint8_t* out_xy_le, int* out_is_zero);
+
+/* Test hooks for the field layer (the analogue of the Wasm exports checked by src/field.test.ts):
+ * applies op elementwise on the device to n elements given as canonical LE bytes in/out.
+ * field: 0 = BLS12-377 Fp, 1 = BLS12-377 Fr (= ed-on-377 base field), 2 = Pallas Fp.
+ * op: 0 mul, 1 add, 2 sub, 3 inverse (Fermat), 4 square, 5 inverse (binary gcd), 6 negate. */
+int mgb_field_op(int device, int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n);
+
+/* Integer-pipe microbenchmarks (roofline denominator).  mode: 0 = mad.lo.u32, 1 = mad.hi.u32,
+ * 2 = mad.wide.u32, 3 = mad.lo.cc/madc.hi.cc carry chain (IMAD.WIDE.U32.X), 4 = Fp377 Montgomery
+ * multiplications, 5 = Fr377 multiplications.  Returns operations per second (ops = instructions x 32
+ * lanes for modes 0-3, field multiplications for 4-5) in *ops_per_s and the kernel ms in *ms. */
+int mgb_microbench(int device, int mode, int blocks_per_sm, int threads, int iters, double* ops_per_s, float* ms);
+
+const char* mgb_last_error(const mgb_ctx* ctx);   /* ctx may be NULL: last error of a ctx-less call */
+void mgb_destroy(mgb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MONTGOMERY_B200_H */

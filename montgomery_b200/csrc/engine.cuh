@@ -1,0 +1,643 @@
+// MSM pipeline kernels (sm_100a).  One template per curve family policy; see DESIGN.md for the
+// data layout and the per-kernel rooflines.
+//
+// Pipeline (reference phases in brackets, src/msm-batched-affine.ts):
+//   k_digits      GLV split + signed c-bit digits + bucket histogram         [:350-421, :175-205]
+//   scan          exclusive scan of the histogram -> bucket offsets          [:423-447]
+//   k_scatter     counting-sort scatter of point references (not points)     [:456-502]
+//   k_plan/k_batch_add  log-depth in-place tree per bucket, batched-affine additions with a
+//                 block-wide Montgomery batch inversion over a shared-memory product tree [:243-283,
+//                 src/curve-affine.ts:376-522, src/wasm/inverse.ts:220-271]
+//   k_reduce_*    bucket running sums per window chunk, then segment combination [:556-583]
+//   k_final       Horner over windows + affine normalisation                 [:311-334, curve-projective.ts:335-349]
+#pragma once
+#include <cuda_runtime.h>
+#include "ec.cuh"
+
+namespace mgb {
+
+// ---------------------------------------------------------------- vector loads / stores
+template <class P>
+MGB_DEV Fe<P> ld_fe(const uint32_t* p) {
+  Fe<P> r;
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  _Pragma("unroll") for (int i = 0; i < P::N / 4; i++) {
+    uint4 t = q[i];
+    r.v[4 * i] = t.x; r.v[4 * i + 1] = t.y; r.v[4 * i + 2] = t.z; r.v[4 * i + 3] = t.w;
+  }
+  return r;
+}
+template <class P>
+MGB_DEV Fe<P> ldg_fe(const uint32_t* p) {  // read-only path (point table)
+  Fe<P> r;
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  _Pragma("unroll") for (int i = 0; i < P::N / 4; i++) {
+    uint4 t = __ldg(q + i);
+    r.v[4 * i] = t.x; r.v[4 * i + 1] = t.y; r.v[4 * i + 2] = t.z; r.v[4 * i + 3] = t.w;
+  }
+  return r;
+}
+template <class P>
+MGB_DEV void st_fe(uint32_t* p, const Fe<P>& a) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+  _Pragma("unroll") for (int i = 0; i < P::N / 4; i++) q[i] = make_uint4(a.v[4 * i], a.v[4 * i + 1], a.v[4 * i + 2], a.v[4 * i + 3]);
+}
+
+// reference bits of a sorted entry: point index | endo << 30 | negate << 31
+static constexpr uint32_t REF_NEG = 0x80000000u;
+static constexpr uint32_t REF_ENDO = 0x40000000u;
+static constexpr uint32_t REF_IDX = 0x3fffffffu;
+static constexpr uint32_t NO_BUCKET = 0xffffffffu;
+static constexpr uint32_t PAIR_RIGHT_RAW = 0x80000000u;
+
+// ---------------------------------------------------------------- curve policies
+template <class FP, class CC, class GL>
+struct WeierstrassPolicy {
+  typedef FP P;
+  typedef Field<FP> F;
+  typedef Weierstrass<FP> G;
+  typedef typename G::acc acc;
+  typedef typename G::affine vpoint;   // materialised bucket element
+  typedef GL Glv;
+  static constexpr int N = FP::N;
+  static constexpr bool USE_GLV = true;
+  static constexpr bool BATCH_AFFINE = true;
+  static constexpr int HALVES = 2;
+  static constexpr int MAG_LIMBS = 4;        // |k0|, |k1| < 2^128
+  static constexpr int MAG_BITS = 128;       // digits must cover MAG_BITS (incl. the final carry)
+  static constexpr int ENTRY_LIMBS = 3 * N;  // x | y | beta*x
+  static constexpr int V_LIMBS = 2 * N;
+  static constexpr int ACC_LIMBS = 4 * N;
+  static constexpr int COORD_BYTES = 4 * N;
+
+  MGB_DEV static vpoint load_raw(const uint32_t* table, uint32_t ref) {
+    const uint32_t* e = table + (size_t)(ref & REF_IDX) * ENTRY_LIMBS;
+    vpoint r;
+    r.x = ldg_fe<FP>(e + ((ref & REF_ENDO) ? 2 * N : 0));
+    r.y = ldg_fe<FP>(e + N);
+    if (ref & REF_NEG) r.y = F::neg(r.y);
+    return r;
+  }
+  MGB_DEV static vpoint load_v(const uint32_t* V, uint32_t slot) {
+    const uint32_t* e = V + (size_t)(slot >> 1) * V_LIMBS;
+    vpoint r; r.x = ld_fe<FP>(e); r.y = ld_fe<FP>(e + N); return r;
+  }
+  MGB_DEV static void store_v(uint32_t* V, uint32_t slot, const vpoint& p) {
+    uint32_t* e = V + (size_t)(slot >> 1) * V_LIMBS;
+    st_fe<FP>(e, p.x); st_fe<FP>(e + N, p.y);
+  }
+  MGB_DEV static acc acc_zero() { return G::acc_zero(); }
+  MGB_DEV static acc add(const acc& a, const acc& b) { return G::add(a, b); }
+  MGB_DEV static acc dbl(const acc& a) { return G::dbl(a); }
+  MGB_DEV static acc add_v(const acc& a, const vpoint& p) { return G::madd(a, p); }
+  MGB_DEV static acc add_raw(const acc& a, const vpoint& p) { return G::madd(a, p); }
+  MGB_DEV static acc ld_acc(const uint32_t* p) { acc r; r.X = ld_fe<FP>(p); r.Y = ld_fe<FP>(p + N); r.ZZ = ld_fe<FP>(p + 2 * N); r.ZZZ = ld_fe<FP>(p + 3 * N); return r; }
+  MGB_DEV static void st_acc(uint32_t* p, const acc& a) { st_fe<FP>(p, a.X); st_fe<FP>(p + N, a.Y); st_fe<FP>(p + 2 * N, a.ZZ); st_fe<FP>(p + 3 * N, a.ZZZ); }
+  MGB_DEV static acc generator() {
+    acc g; _Pragma("unroll") for (int i = 0; i < N; i++) { g.X.v[i] = CC::gx(i); g.Y.v[i] = CC::gy(i); }
+    g.ZZ = F::one(); g.ZZZ = F::one(); return g;
+  }
+  // x||y canonical bytes -> table entry
+  MGB_DEV static void make_entry(uint32_t* e, const Fe<FP>& x_plain, const Fe<FP>& y_plain, bool inf) {
+    Fe<FP> x = F::to_mont(x_plain), y = F::to_mont(y_plain);
+    Fe<FP> beta; _Pragma("unroll") for (int i = 0; i < N; i++) beta.v[i] = CC::beta(i);
+    Fe<FP> bx = F::mul(x, beta);
+    if (inf) { x = F::zero(); y = F::zero(); bx = F::zero(); x.v[N - 1] = G::INF_BIT; bx.v[N - 1] = G::INF_BIT; }
+    st_fe<FP>(e, x); st_fe<FP>(e + N, y); st_fe<FP>(e + 2 * N, bx);
+  }
+  MGB_DEV static void make_entry_from_acc(uint32_t* e, const acc& a) {
+    vpoint p = G::to_affine(a);
+    bool inf = G::is_inf(p);
+    make_entry(e, F::from_mont(p.x), F::from_mont(p.y), inf);
+  }
+  MGB_DEV static void entry_to_plain(const uint32_t* e, Fe<FP>& x, Fe<FP>& y, bool& inf) {
+    Fe<FP> xm = ld_fe<FP>(e);
+    inf = (xm.v[N - 1] & G::INF_BIT) != 0;
+    if (inf) { x = F::zero(); y = F::zero(); return; }
+    x = F::from_mont(xm); y = F::from_mont(ld_fe<FP>(e + N));
+  }
+  // final accumulator -> canonical plain coordinates
+  MGB_DEV static void acc_to_plain(const acc& a, Fe<FP>& x, Fe<FP>& y, bool& inf) {
+    vpoint p = G::to_affine(a);
+    inf = G::is_inf(p);
+    if (inf) { x = F::zero(); y = F::zero(); return; }
+    x = F::from_mont(p.x); y = F::from_mont(p.y);
+  }
+};
+
+template <class FP, class CC>
+struct TwistedEdwardsPolicy {
+  typedef FP P;
+  typedef Field<FP> F;
+  typedef TwistedEdwards<FP, CC> G;
+  typedef typename G::acc acc;
+  typedef typename G::acc vpoint;
+  typedef typename G::affine raw;
+  static constexpr int N = FP::N;
+  static constexpr bool USE_GLV = false;
+  static constexpr bool BATCH_AFFINE = false;
+  static constexpr int HALVES = 1;
+  static constexpr int MAG_LIMBS = 8;
+  static constexpr int MAG_BITS = CC::SCALAR_BITS + 1;
+  static constexpr int ENTRY_LIMBS = 3 * N;  // x | y | 2d*x*y
+  static constexpr int V_LIMBS = 4 * N;
+  static constexpr int ACC_LIMBS = 4 * N;
+  static constexpr int COORD_BYTES = 4 * N;
+
+  MGB_DEV static raw load_raw(const uint32_t* table, uint32_t ref) {
+    const uint32_t* e = table + (size_t)(ref & REF_IDX) * ENTRY_LIMBS;
+    raw r; r.x = ldg_fe<FP>(e); r.y = ldg_fe<FP>(e + N); r.kt = ldg_fe<FP>(e + 2 * N);
+    if (ref & REF_NEG) { r.x = F::neg(r.x); r.kt = F::neg(r.kt); }
+    return r;
+  }
+  MGB_DEV static vpoint load_v(const uint32_t* V, uint32_t slot) { return ld_acc(V + (size_t)(slot >> 1) * V_LIMBS); }
+  MGB_DEV static void store_v(uint32_t* V, uint32_t slot, const vpoint& p) { st_acc(V + (size_t)(slot >> 1) * V_LIMBS, p); }
+  MGB_DEV static acc acc_zero() { return G::acc_zero(); }
+  MGB_DEV static acc add(const acc& a, const acc& b) { return G::add(a, b); }
+  MGB_DEV static acc dbl(const acc& a) { return G::dbl(a); }
+  MGB_DEV static acc add_v(const acc& a, const vpoint& p) { return G::add(a, p); }
+  MGB_DEV static acc add_raw(const acc& a, const raw& p) { return G::madd(a, p); }
+  MGB_DEV static acc ld_acc(const uint32_t* p) { acc r; r.X = ld_fe<FP>(p); r.Y = ld_fe<FP>(p + N); r.Z = ld_fe<FP>(p + 2 * N); r.T = ld_fe<FP>(p + 3 * N); return r; }
+  MGB_DEV static void st_acc(uint32_t* p, const acc& a) { st_fe<FP>(p, a.X); st_fe<FP>(p + N, a.Y); st_fe<FP>(p + 2 * N, a.Z); st_fe<FP>(p + 3 * N, a.T); }
+  MGB_DEV static acc generator() {
+    raw g; _Pragma("unroll") for (int i = 0; i < N; i++) { g.x.v[i] = CC::gx(i); g.y.v[i] = CC::gy(i); }
+    return G::from_affine(g);
+  }
+  MGB_DEV static void make_entry(uint32_t* e, const Fe<FP>& x_plain, const Fe<FP>& y_plain, bool inf) {
+    Fe<FP> x = F::to_mont(x_plain), y = F::to_mont(y_plain);
+    if (inf) { x = F::zero(); y = F::one(); }
+    Fe<FP> kt = F::mul(F::mul(x, y), G::k2d());
+    st_fe<FP>(e, x); st_fe<FP>(e + N, y); st_fe<FP>(e + 2 * N, kt);
+  }
+  MGB_DEV static void make_entry_from_acc(uint32_t* e, const acc& a) {
+    Fe<FP> x, y; G::to_affine(a, x, y);
+    make_entry(e, F::from_mont(x), F::from_mont(y), false);
+  }
+  MGB_DEV static void entry_to_plain(const uint32_t* e, Fe<FP>& x, Fe<FP>& y, bool& inf) {
+    x = F::from_mont(ld_fe<FP>(e)); y = F::from_mont(ld_fe<FP>(e + N));
+    Fe<FP> o = F::zero(); o.v[0] = 1;
+    inf = F::is_zero(x) && F::eq(y, o);
+  }
+  MGB_DEV static void acc_to_plain(const acc& a, Fe<FP>& x, Fe<FP>& y, bool& inf) {
+    Fe<FP> xm, ym; G::to_affine(a, xm, ym);
+    x = F::from_mont(xm); y = F::from_mont(ym);
+    Fe<FP> o = F::zero(); o.v[0] = 1;
+    inf = F::is_zero(x) && F::eq(y, o);
+  }
+};
+
+typedef WeierstrassPolicy<Fp377, Bls12377Consts, Glv377> CurveBls377;
+typedef WeierstrassPolicy<FpPallas, PallasConsts, GlvPallas> CurvePallas;
+typedef TwistedEdwardsPolicy<Fr377, Ed377Consts> CurveEd377;
+
+// ---------------------------------------------------------------- small multi-limb helpers (scalar side)
+template <int NA, int NB>
+MGB_DEV void mulw(uint32_t* out, const uint32_t* a, const uint32_t* b) {  // out[NA+NB] = a*b
+  _Pragma("unroll") for (int i = 0; i < NA + NB; i++) out[i] = 0;
+  _Pragma("unroll") for (int i = 0; i < NA; i++) {
+    uint64_t carry = 0;
+    _Pragma("unroll") for (int j = 0; j < NB; j++) {
+      uint64_t t = (uint64_t)a[i] * b[j] + out[i + j] + carry;
+      out[i + j] = (uint32_t)t;
+      carry = t >> 32;
+    }
+    out[i + NB] = (uint32_t)carry;
+  }
+}
+template <int NACC, int NT>
+MGB_DEV void acc_addsub(uint32_t* acc, const uint32_t* t, bool subtract) {  // acc +-= t (two's complement, NACC limbs)
+  uint64_t c = subtract ? 1 : 0;
+  _Pragma("unroll") for (int i = 0; i < NACC; i++) {
+    uint32_t ti = (i < NT) ? t[i] : 0u;
+    if (subtract) ti = ~ti;
+    uint64_t s = (uint64_t)acc[i] + ti + c;
+    acc[i] = (uint32_t)s;
+    c = s >> 32;
+  }
+}
+
+// s (8 limbs) -> |k0|, |k1| (4 limbs each) and their signs, k0 + k1*lambda = s (mod q).
+// Lattice rounding as in the reference (src/wasm/glv.ts:77-80), constants from gen_constants.py.
+template <class GL>
+MGB_DEV void glv_decompose(const uint32_t* s, uint32_t* k0, uint32_t* k1, bool& neg0, bool& neg1) {
+  uint32_t g[9], prod[17], x0[5], x1[5];
+  _Pragma("unroll") for (int h = 0; h < 2; h++) {
+    _Pragma("unroll") for (int i = 0; i < 9; i++) g[i] = h ? GL::g1(i) : GL::g0(i);
+    mulw<9, 8>(prod, g, s);
+    // round: add 2^383, keep bits >= 384
+    uint64_t c = (uint64_t)prod[11] + 0x80000000u;
+    c >>= 32;
+    uint32_t* x = h ? x1 : x0;
+    _Pragma("unroll") for (int i = 0; i < 5; i++) { uint64_t t = (uint64_t)prod[12 + i] + c; x[i] = (uint32_t)t; c = t >> 32; }
+  }
+  uint32_t v[4], t[9], a0[10], a1[10];
+  _Pragma("unroll") for (int i = 0; i < 10; i++) { a0[i] = (i < 8) ? s[i] : 0u; a1[i] = 0u; }
+  // k0 = s - (SG0*S_V00) x0|v00| - (SG1*S_V01) x1|v01|
+  _Pragma("unroll") for (int i = 0; i < 4; i++) v[i] = GL::v00(i);
+  mulw<5, 4>(t, x0, v); acc_addsub<10, 9>(a0, t, GL::SG0 * GL::S_V00 > 0);
+  _Pragma("unroll") for (int i = 0; i < 4; i++) v[i] = GL::v01(i);
+  mulw<5, 4>(t, x1, v); acc_addsub<10, 9>(a0, t, GL::SG1 * GL::S_V01 > 0);
+  // k1 = - (SG0*S_V10) x0|v10| - (SG1*S_V11) x1|v11|
+  _Pragma("unroll") for (int i = 0; i < 4; i++) v[i] = GL::v10(i);
+  mulw<5, 4>(t, x0, v); acc_addsub<10, 9>(a1, t, GL::SG0 * GL::S_V10 > 0);
+  _Pragma("unroll") for (int i = 0; i < 4; i++) v[i] = GL::v11(i);
+  mulw<5, 4>(t, x1, v); acc_addsub<10, 9>(a1, t, GL::SG1 * GL::S_V11 > 0);
+  neg0 = (a0[9] >> 31) != 0;
+  neg1 = (a1[9] >> 31) != 0;
+  if (neg0) { _Pragma("unroll") for (int i = 0; i < 10; i++) a0[i] = ~a0[i]; uint32_t one1[1] = {1}; acc_addsub<10, 1>(a0, one1, false); }
+  if (neg1) { _Pragma("unroll") for (int i = 0; i < 10; i++) a1[i] = ~a1[i]; uint32_t one1[1] = {1}; acc_addsub<10, 1>(a1, one1, false); }
+  _Pragma("unroll") for (int i = 0; i < 4; i++) { k0[i] = a0[i]; k1[i] = a1[i]; }
+}
+
+struct MsmParams {
+  uint32_t n;          // number of (scalar, point) pairs
+  int c;               // window bits
+  int K;               // windows
+  uint32_t L;          // buckets per window = 2^(c-1)
+  uint32_t nbuckets;   // K*L
+  uint32_t nent;       // n * HALVES * K
+};
+
+// ---------------------------------------------------------------- k_digits
+// One thread per scalar.  Entry e = (h*K + w) of scalar i lives at [e*n + i] (coalesced).
+template <class CV>
+__global__ void __launch_bounds__(256) k_digits(MsmParams pr, const uint32_t* __restrict__ scalars,
+                                                uint32_t* __restrict__ ent_bucket, uint32_t* __restrict__ ent_rank,
+                                                uint32_t* __restrict__ counts) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pr.n) return;
+  uint32_t s[8];
+  {
+    const uint4* q = reinterpret_cast<const uint4*>(scalars + (size_t)i * 8);
+    uint4 a = q[0], b = q[1];
+    s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w; s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
+  }
+  constexpr int ML = CV::MAG_LIMBS;
+  uint32_t mag[CV::HALVES][ML + 1];
+  bool neg[CV::HALVES];
+  if constexpr (CV::USE_GLV) {
+    glv_decompose<typename CV::Glv>(s, mag[0], mag[1], neg[0], neg[1]);
+    mag[0][ML] = 0; mag[1][ML] = 0;
+  } else {
+    _Pragma("unroll") for (int k = 0; k < ML; k++) mag[0][k] = s[k];
+    mag[0][ML] = 0;
+    neg[0] = false;
+  }
+  const int c = pr.c;
+  const uint32_t L = pr.L, cmask = (1u << c) - 1;
+  _Pragma("unroll") for (int h = 0; h < CV::HALVES; h++) {
+    uint32_t carry = 0;
+    for (int w = 0; w < pr.K; w++) {
+      int bit = w * c;
+      int limb = bit >> 5, sh = bit & 31;
+      uint32_t lo = 0, hi = 0;
+      _Pragma("unroll") for (int k = 0; k <= ML; k++) { if (k == limb) lo = mag[h][k]; if (k == limb + 1) hi = mag[h][k]; }
+      uint32_t slice = (uint32_t)((((uint64_t)hi << 32) | lo) >> sh) & cmask;
+      uint32_t l = slice + carry;
+      bool dneg = false;
+      if (l > L) { l = 2 * L - l; carry = 1; dneg = true; } else carry = 0;
+      uint32_t e = (uint32_t)(h * pr.K + w);
+      size_t pos = (size_t)e * pr.n + i;
+      if (l == 0) { ent_bucket[pos] = NO_BUCKET; continue; }
+      uint32_t bucket = (uint32_t)w * L + (l - 1);
+      uint32_t rank = atomicAdd(&counts[bucket], 1u);
+      ent_bucket[pos] = bucket;
+      ent_rank[pos] = rank | ((dneg != neg[h]) ? REF_NEG : 0u);  // rank < 2^31
+    }
+  }
+}
+
+// ---------------------------------------------------------------- exclusive scan (uint32), 3 kernels
+static constexpr int SCAN_T = 1024;
+static constexpr int SCAN_ITEMS = 4;
+static constexpr int SCAN_TILE = SCAN_T * SCAN_ITEMS;
+
+MGB_DEV uint32_t block_excl_scan(uint32_t val, uint32_t* total_out, uint32_t* sm /* 32 words */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t x = val;
+  _Pragma("unroll") for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+  if (lane == 31) sm[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t w = (lane < (int)(blockDim.x >> 5)) ? sm[lane] : 0;
+    _Pragma("unroll") for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, w, d); if (lane >= d) w += y; }
+    sm[lane] = w;  // inclusive scan of warp totals
+  }
+  __syncthreads();
+  uint32_t base = wid ? sm[wid - 1] : 0;
+  *total_out = sm[(blockDim.x >> 5) - 1];
+  __syncthreads();
+  return base + x - val;
+}
+
+// in: counts[n]; out: offs[n] (exclusive, tile-local), tile_sums[tile]; also global max of counts
+static __global__ void __launch_bounds__(SCAN_T) k_scan_tiles(const uint32_t* __restrict__ counts, uint32_t* __restrict__ offs,
+                                                       uint32_t* __restrict__ tile_sums, uint32_t n, uint32_t* __restrict__ maxcount) {
+  __shared__ uint32_t sm[32];
+  uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS], sum = 0, mx = 0;
+  _Pragma("unroll") for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = (base + k < n) ? counts[base + k] : 0; sum += v[k]; mx = max(mx, v[k]); }
+  uint32_t total;
+  uint32_t ex = block_excl_scan(sum, &total, sm);
+  _Pragma("unroll") for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) offs[base + k] = ex; ex += v[k]; }
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  if ((threadIdx.x & 31) == 0 && mx) atomicMax(maxcount, mx);
+}
+// single block: exclusive scan of tile_sums[ntiles] in place, total -> *grand
+static __global__ void __launch_bounds__(SCAN_T) k_scan_sums(uint32_t* __restrict__ tile_sums, uint32_t ntiles, uint32_t* __restrict__ grand) {
+  __shared__ uint32_t sm[32];
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < ntiles; base += SCAN_T) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t v = (i < ntiles) ? tile_sums[i] : 0;
+    uint32_t total;
+    uint32_t ex = block_excl_scan(v, &total, sm);
+    if (i < ntiles) tile_sums[i] = carry + ex;
+    carry += total;
+  }
+  if (threadIdx.x == 0) *grand = carry;
+}
+static __global__ void __launch_bounds__(SCAN_T) k_scan_add(uint32_t* __restrict__ offs, const uint32_t* __restrict__ tile_sums,
+                                                     uint32_t n, const uint32_t* __restrict__ grand) {
+  uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  uint32_t add = tile_sums[blockIdx.x];
+  _Pragma("unroll") for (int k = 0; k < SCAN_ITEMS; k++) if (base + k < n) offs[base + k] += add;
+  if (blockIdx.x == 0 && threadIdx.x == 0) offs[n] = *grand;
+}
+
+// ---------------------------------------------------------------- k_scatter
+// refs[slot] = point reference, slot_bucket[slot] = bucket, slot = offs[bucket] + rank
+template <class CV>
+__global__ void __launch_bounds__(256) k_scatter(MsmParams pr, const uint32_t* __restrict__ ent_bucket, const uint32_t* __restrict__ ent_rank,
+                                                 const uint32_t* __restrict__ offs, uint32_t* __restrict__ refs, uint32_t* __restrict__ slot_bucket) {
+  size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= pr.nent) return;
+  uint32_t b = ent_bucket[pos];
+  if (b == NO_BUCKET) return;
+  uint32_t rk = ent_rank[pos];
+  uint32_t e = (uint32_t)(pos / pr.n), i = (uint32_t)(pos - (size_t)e * pr.n);
+  uint32_t ref = i | (rk & REF_NEG);
+  if (CV::HALVES == 2 && e >= (uint32_t)pr.K) ref |= REF_ENDO;
+  uint32_t slot = offs[b] + (rk & ~REF_NEG);
+  refs[slot] = ref;
+  slot_bucket[slot] = b;
+}
+
+// ---------------------------------------------------------------- k_plan
+// Round r of the in-place bucket tree (reference: msm-batched-affine.ts:243-263): the element at
+// local index j (multiple of 2^(r+1)) absorbs the element at j + 2^r if that is inside the bucket.
+// Emits the compact list of left slots (order irrelevant: pairs are independent).
+static __global__ void __launch_bounds__(256) k_plan(uint32_t nslots, int r, const uint32_t* __restrict__ slot_bucket,
+                                              const uint32_t* __restrict__ offs, uint32_t* __restrict__ pairs, uint32_t* __restrict__ npairs) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  bool active = false;
+  uint32_t entry = 0;
+  if (s < nslots) {
+    uint32_t b = slot_bucket[s];
+    uint32_t o = offs[b], n = offs[b + 1] - o, j = s - o;
+    uint32_t step = 1u << r;
+    if ((j & (2 * step - 1)) == 0 && j + step < n) {
+      active = true;
+      bool right_raw = (r == 0) || (j + step + 1 >= n);  // right operand was never a left operand in round 0
+      entry = s | (right_raw ? PAIR_RIGHT_RAW : 0u);
+    }
+  }
+  uint32_t m = __ballot_sync(0xffffffffu, active);
+  if (m) {
+    int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(npairs, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (active) pairs[base + __popc(m & ((1u << lane) - 1))] = entry;
+  }
+}
+
+// ---------------------------------------------------------------- k_batch_add (Weierstrass)
+// Persistent blocks; each tile is T*E independent affine additions sharing ONE field inversion:
+// per-thread prefix products (E elements, kept in local memory), a product tree over the T thread
+// totals in shared memory, one binary-gcd inversion by thread 0, tree down-sweep, per-thread
+// back-substitution.  6 multiplications per addition + 3/E for the tree.
+template <class CV, int T, int E>
+__global__ void __launch_bounds__(T) k_batch_add(const uint32_t* __restrict__ table, const uint32_t* __restrict__ refs,
+                                                 uint32_t* __restrict__ V, const uint32_t* __restrict__ pairs,
+                                                 const uint32_t* __restrict__ npairs_ptr, int r) {
+  typedef typename CV::P FP;
+  typedef typename CV::F F;
+  typedef typename CV::G G;
+  typedef Fe<FP> fe;
+  constexpr int N = CV::N;
+  extern __shared__ uint4 smem_raw[];
+  uint32_t* tree = reinterpret_cast<uint32_t*>(smem_raw);  // 2T field elements
+  const uint32_t npairs = *npairs_ptr;
+  const uint32_t ntiles = (npairs + T * E - 1) / (T * E);
+  const uint32_t step = 1u << r;
+  const int tid = threadIdx.x;
+
+  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    fe den[E], pre[E];
+    uint32_t kinds = 0;
+    fe run = F::one();
+    _Pragma("unroll 1") for (int e = 0; e < E; e++) {
+      uint32_t idx = tile * (T * E) + e * T + tid;
+      int kind = 5;
+      fe d = F::one();
+      if (idx < npairs) {
+        uint32_t ent = pairs[idx];
+        uint32_t s = ent & ~PAIR_RIGHT_RAW;
+        typename CV::vpoint A = (r == 0) ? CV::load_raw(table, refs[s]) : CV::load_v(V, s);
+        typename CV::vpoint B = (ent & PAIR_RIGHT_RAW) ? CV::load_raw(table, refs[s + step]) : CV::load_v(V, s + step);
+        kind = G::add_prepare(A, B, d);
+      }
+      kinds |= (uint32_t)kind << (3 * e);
+      pre[e] = run;
+      den[e] = d;
+      run = F::mul(run, d);
+    }
+    st_fe<FP>(tree + (size_t)(T + tid) * N, run);
+    __syncthreads();
+    for (int w = T / 2; w >= 1; w >>= 1) {
+      if (tid < w) {
+        int k = w + tid;
+        fe a = ld_fe<FP>(tree + (size_t)(2 * k) * N), b = ld_fe<FP>(tree + (size_t)(2 * k + 1) * N);
+        st_fe<FP>(tree + (size_t)k * N, F::mul(a, b));
+      }
+      __syncthreads();
+    }
+    if (tid == 0) st_fe<FP>(tree + N, F::inv_bgcd(ld_fe<FP>(tree + N)));
+    __syncthreads();
+    for (int w = 1; w < T; w <<= 1) {
+      if (tid < w) {
+        int k = w + tid;
+        fe ik = ld_fe<FP>(tree + (size_t)k * N);
+        fe a = ld_fe<FP>(tree + (size_t)(2 * k) * N), b = ld_fe<FP>(tree + (size_t)(2 * k + 1) * N);
+        st_fe<FP>(tree + (size_t)(2 * k) * N, F::mul(ik, b));
+        st_fe<FP>(tree + (size_t)(2 * k + 1) * N, F::mul(ik, a));
+      }
+      __syncthreads();
+    }
+    fe u = ld_fe<FP>(tree + (size_t)(T + tid) * N);  // inverse of this thread's total
+    __syncthreads();                                  // tree is reused by the next tile
+    _Pragma("unroll 1") for (int e = E - 1; e >= 0; e--) {
+      int kind = (kinds >> (3 * e)) & 7;
+      fe inv_den = F::mul(u, pre[e]);
+      u = F::mul(u, den[e]);
+      if (kind == 5) continue;
+      uint32_t idx = tile * (T * E) + e * T + tid;
+      uint32_t ent = pairs[idx];
+      uint32_t s = ent & ~PAIR_RIGHT_RAW;
+      typename CV::vpoint A = (r == 0) ? CV::load_raw(table, refs[s]) : CV::load_v(V, s);
+      typename CV::vpoint B = (ent & PAIR_RIGHT_RAW) ? CV::load_raw(table, refs[s + step]) : CV::load_v(V, s + step);
+      CV::store_v(V, s, G::add_finish(kind, A, B, inv_den));
+    }
+  }
+}
+
+// ---------------------------------------------------------------- k_pair_add (twisted Edwards: no inversion needed)
+template <class CV>
+__global__ void __launch_bounds__(256) k_pair_add(const uint32_t* __restrict__ table, const uint32_t* __restrict__ refs,
+                                                  uint32_t* __restrict__ V, const uint32_t* __restrict__ pairs,
+                                                  const uint32_t* __restrict__ npairs_ptr, int r) {
+  const uint32_t npairs = *npairs_ptr;
+  const uint32_t step = 1u << r;
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < npairs; idx += gridDim.x * blockDim.x) {
+    uint32_t ent = pairs[idx];
+    uint32_t s = ent & ~PAIR_RIGHT_RAW;
+    typename CV::acc res;
+    if (r == 0) {
+      res = CV::G::add_affine(CV::load_raw(table, refs[s]), CV::load_raw(table, refs[s + step]));
+    } else {
+      typename CV::acc A = CV::load_v(V, s);
+      if (ent & PAIR_RIGHT_RAW) res = CV::add_raw(A, CV::load_raw(table, refs[s + step]));
+      else res = CV::add_v(A, CV::load_v(V, s + step));
+    }
+    CV::store_v(V, s, res);
+  }
+}
+
+// ---------------------------------------------------------------- bucket reduction
+// Level 0: one thread per chunk of m = 2^mlog consecutive buckets of one window.  With t the
+// 0-based bucket position inside the window (digit l = t+1), the chunk yields
+//   U = sum_j B_j,   W = sum_j j*B_j   (j = local index),
+// by the running-sum walk of the reference (msm-batched-affine.ts:556-583).  `rounds` is the
+// number of accumulation rounds that were run: a bucket's elements at local indices multiple of
+// 2^rounds are still separate and are summed here.
+template <class CV>
+__global__ void __launch_bounds__(128) k_reduce_level0(MsmParams pr, int mlog, int rounds, const uint32_t* __restrict__ table,
+                                                       const uint32_t* __restrict__ refs, const uint32_t* __restrict__ V,
+                                                       const uint32_t* __restrict__ offs, uint32_t* __restrict__ outU, uint32_t* __restrict__ outW) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t nchunks = pr.nbuckets >> mlog;
+  if (g >= nchunks) return;
+  const uint32_t m = 1u << mlog;
+  typename CV::acc row = CV::acc_zero(), tri = CV::acc_zero();
+  const uint32_t stride = 1u << rounds;
+  for (int j = (int)m - 1; j >= 0; j--) {
+    uint32_t b = g * m + (uint32_t)j;
+    uint32_t o = offs[b], n = offs[b + 1] - o;
+    for (uint32_t q = 0; q < n; q += stride) {
+      // element at local index q is materialised iff it had a partner in round 0
+      if (rounds > 0 && q + 1 < n) row = CV::add_v(row, CV::load_v(V, o + q));
+      else row = CV::add_raw(row, CV::load_raw(table, refs[o + q]));
+    }
+    if (j > 0) tri = CV::add(tri, row);
+  }
+  CV::st_acc(outU + (size_t)g * CV::ACC_LIMBS, row);
+  CV::st_acc(outW + (size_t)g * CV::ACC_LIMBS, tri);
+}
+
+// Level >= 1: combine m consecutive segments (each covering 2^slog buckets) of one window:
+//   U = sum U_j,  W = sum W_j + 2^slog * sum_j j*U_j.
+// nseg_in segments per window in, ceil(nseg_in / m) out.
+template <class CV>
+__global__ void __launch_bounds__(128) k_reduce_combine(int K, uint32_t nseg_in, int mlog, int slog,
+                                                        const uint32_t* __restrict__ inU, const uint32_t* __restrict__ inW,
+                                                        uint32_t* __restrict__ outU, uint32_t* __restrict__ outW) {
+  const uint32_t m = 1u << mlog;
+  const uint32_t nseg_out = (nseg_in + m - 1) >> mlog;
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nseg_out * (uint32_t)K) return;
+  uint32_t w = g / nseg_out, go = g - w * nseg_out;
+  uint32_t first = go * m;
+  uint32_t cnt = min(m, nseg_in - first);
+  typename CV::acc row = CV::acc_zero(), tri = CV::acc_zero(), ws = CV::acc_zero();
+  for (int j = (int)cnt - 1; j >= 0; j--) {
+    size_t idx = (size_t)w * nseg_in + first + (uint32_t)j;
+    row = CV::add(row, CV::ld_acc(inU + idx * CV::ACC_LIMBS));
+    ws = CV::add(ws, CV::ld_acc(inW + idx * CV::ACC_LIMBS));
+    if (j > 0) tri = CV::add(tri, row);
+  }
+  for (int d = 0; d < slog; d++) tri = CV::dbl(tri);
+  CV::st_acc(outU + (size_t)g * CV::ACC_LIMBS, row);
+  CV::st_acc(outW + (size_t)g * CV::ACC_LIMBS, CV::add(ws, tri));
+}
+
+// Window sum S_w = W + U (digit = position + 1); result = sum_w 2^(c*w) S_w by Horner
+// (msm-batched-affine.ts:322-334).  One thread.  Writes the un-normalised accumulator.
+template <class CV>
+__global__ void k_final(int K, int c, const uint32_t* __restrict__ inU, const uint32_t* __restrict__ inW, uint32_t* __restrict__ out_acc) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  typename CV::acc res = CV::acc_zero();
+  for (int w = K - 1; w >= 0; w--) {
+    for (int d = 0; d < c; d++) res = CV::dbl(res);
+    typename CV::acc S = CV::add(CV::ld_acc(inU + (size_t)w * CV::ACC_LIMBS), CV::ld_acc(inW + (size_t)w * CV::ACC_LIMBS));
+    res = CV::add(res, S);
+  }
+  CV::st_acc(out_acc, res);
+}
+
+// sum `count` partial accumulators (multi-GPU combine) and/or normalise: out = canonical x||y + flag
+template <class CV>
+__global__ void k_normalize(const uint32_t* __restrict__ accs, int count, uint32_t* __restrict__ out_xy, uint32_t* __restrict__ out_flag) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  typename CV::acc res = CV::ld_acc(accs);
+  for (int i = 1; i < count; i++) res = CV::add(res, CV::ld_acc(accs + (size_t)i * CV::ACC_LIMBS));
+  Fe<typename CV::P> x, y;
+  bool inf;
+  CV::acc_to_plain(res, x, y, inf);
+  _Pragma("unroll") for (int i = 0; i < CV::N; i++) { out_xy[i] = x.v[i]; out_xy[CV::N + i] = y.v[i]; }
+  *out_flag = inf ? 1u : 0u;
+}
+
+// ---------------------------------------------------------------- point ingestion / generation
+template <class CV>
+__global__ void __launch_bounds__(128) k_set_points(uint32_t n, const uint32_t* __restrict__ xy, const uint8_t* __restrict__ is_zero, uint32_t* __restrict__ table) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fe<typename CV::P> x = ld_fe<typename CV::P>(xy + (size_t)i * 2 * CV::N), y = ld_fe<typename CV::P>(xy + (size_t)i * 2 * CV::N + CV::N);
+  CV::make_entry(table + (size_t)i * CV::ENTRY_LIMBS, x, y, is_zero ? is_zero[i] != 0 : false);
+}
+template <class CV>
+__global__ void __launch_bounds__(128) k_get_points(uint32_t first, uint32_t n, const uint32_t* __restrict__ table, uint32_t* __restrict__ xy, uint8_t* __restrict__ is_zero) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fe<typename CV::P> x, y;
+  bool inf;
+  CV::entry_to_plain(table + (size_t)(first + i) * CV::ENTRY_LIMBS, x, y, inf);
+  st_fe<typename CV::P>(xy + (size_t)i * 2 * CV::N, x);
+  st_fe<typename CV::P>(xy + (size_t)i * 2 * CV::N + CV::N, y);
+  if (is_zero) is_zero[i] = inf ? 1 : 0;
+}
+
+MGB_DEV uint64_t splitmix64(uint64_t seed, uint64_t i) {
+  uint64_t z = seed + (i + 1) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+// P_i = a_i * G, a_i = splitmix64(seed, i) | 1-if-zero  (known discrete logs: closed-form checks)
+template <class CV>
+__global__ void __launch_bounds__(128) k_random_points(uint32_t n, uint64_t seed, uint32_t* __restrict__ table) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t a = splitmix64(seed, i);
+  if (a == 0) a = 1;
+  typename CV::acc g = CV::generator(), res = CV::acc_zero();
+  for (int bit = 63; bit >= 0; bit--) {
+    res = CV::dbl(res);
+    if ((a >> bit) & 1) res = CV::add(res, g);
+  }
+  CV::make_entry_from_acc(table + (size_t)i * CV::ENTRY_LIMBS, res);
+}
+
+}  // namespace mgb

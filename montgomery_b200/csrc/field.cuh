@@ -83,7 +83,7 @@ struct Field {
 
   // Montgomery product a*b/R mod p, a, b < p.
   // X/Y alternate as E (pairs on limbs 0,1|2,3|...) and O (pairs on limbs 1,2|3,4|...): t = E + O*2^32.
-  MGB_DEV static fe mul(const fe& fa, const fe& fb) {
+  MGB_DEV static fe mul_inl(const fe& fa, const fe& fb) {
     const uint32_t* a = fa.v;
     const uint32_t* b = fb.v;
     uint32_t X[N], Y[N];
@@ -132,13 +132,74 @@ struct Field {
     t[N - 1] = ptx::addc(O[N - 1], 0);
     return reduce_once(t);
   }
+  // Out-of-line copy: one body per kernel keeps the instruction footprint inside the SM's
+  // instruction cache (an inlined multiplication is ~5 KB of SASS).
+  MGB_NOINLINE_DEV static fe mul(fe a, fe b) { return mul_inl(a, b); }  // by value: register ABI, no stack traffic
   MGB_DEV static fe sqr(const fe& a) { return mul(a, a); }
 
   MGB_DEV static fe to_mont(const fe& a) { fe r2; _Pragma("unroll") for (int i = 0; i < N; i++) r2.v[i] = P::r2(i); return mul(a, r2); }
   MGB_DEV static fe from_mont(const fe& a) { fe o = zero(); o.v[0] = 1; return mul(a, o); }
 
+  // Montgomery inverse a -> a^-1 (both in Montgomery form) by the plain binary extended Euclid on
+  // the stored integer aR (shifts and adds only, ALU pipe), then one multiplication by R^3.
+  // Variable time, meant to run on one lane per batch (reference: Kaliski almost-inverse plus
+  // corrections, src/wasm/inverse.ts:136-218).  a = 0 -> 0.
+  MGB_NOINLINE_DEV static fe inv_bgcd(fe a) {
+    if (is_zero(a)) return a;
+    uint32_t u[N], v[N], x1[N], x2[N];
+    _Pragma("unroll") for (int i = 0; i < N; i++) { u[i] = a.v[i]; v[i] = P::mod(i); x1[i] = 0; x2[i] = 0; }
+    x1[0] = 1;
+    while (true) {
+      uint32_t ou = u[0] ^ 1, ov = v[0] ^ 1;
+      _Pragma("unroll") for (int i = 1; i < N; i++) { ou |= u[i]; ov |= v[i]; }
+      if (ou == 0 || ov == 0) {
+        fe x;
+        _Pragma("unroll") for (int i = 0; i < N; i++) x.v[i] = (ou == 0) ? x1[i] : x2[i];
+        fe r3; _Pragma("unroll") for (int i = 0; i < N; i++) r3.v[i] = P::r3(i);
+        return mul(x, r3);
+      }
+      if ((u[0] & 1) == 0) { shr1(u); halve(x1); }
+      else if ((v[0] & 1) == 0) { shr1(v); halve(x2); }
+      else {
+        // both odd: subtract the smaller from the larger
+        uint32_t t[N];
+        t[0] = ptx::sub_cc(u[0], v[0]);
+        _Pragma("unroll") for (int i = 1; i < N; i++) t[i] = ptx::subc_cc(u[i], v[i]);
+        uint32_t borrow = ptx::subc(0, 0);
+        if (borrow == 0) {  // u >= v
+          _Pragma("unroll") for (int i = 0; i < N; i++) u[i] = t[i];
+          submod(x1, x2);
+        } else {
+          v[0] = ptx::sub_cc(v[0], u[0]);
+          _Pragma("unroll") for (int i = 1; i < N - 1; i++) v[i] = ptx::subc_cc(v[i], u[i]);
+          v[N - 1] = ptx::subc(v[N - 1], u[N - 1]);
+          submod(x2, x1);
+        }
+      }
+    }
+  }
+  MGB_DEV static void shr1(uint32_t* x) {
+    _Pragma("unroll") for (int i = 0; i < N - 1; i++) x[i] = (x[i] >> 1) | (x[i + 1] << 31);
+    x[N - 1] >>= 1;
+  }
+  MGB_DEV static void halve(uint32_t* x) {  // x/2 mod p for x < p
+    uint32_t msk = 0u - (x[0] & 1);
+    x[0] = ptx::add_cc(x[0], P::mod(0) & msk);
+    _Pragma("unroll") for (int i = 1; i < N - 1; i++) x[i] = ptx::addc_cc(x[i], P::mod(i) & msk);
+    x[N - 1] = ptx::addc(x[N - 1], P::mod(N - 1) & msk);
+    shr1(x);
+  }
+  MGB_DEV static void submod(uint32_t* x, const uint32_t* y) {  // x = x - y mod p
+    x[0] = ptx::sub_cc(x[0], y[0]);
+    _Pragma("unroll") for (int i = 1; i < N; i++) x[i] = ptx::subc_cc(x[i], y[i]);
+    uint32_t borrow = ptx::subc(0, 0);
+    x[0] = ptx::add_cc(x[0], P::mod(0) & borrow);
+    _Pragma("unroll") for (int i = 1; i < N - 1; i++) x[i] = ptx::addc_cc(x[i], P::mod(i) & borrow);
+    x[N - 1] = ptx::addc(x[N - 1], P::mod(N - 1) & borrow);
+  }
+
   // a^(p-2); a = 0 -> 0.  (Not inlined: one copy per kernel.)
-  MGB_NOINLINE_DEV static fe inv(const fe& a) {
+  MGB_NOINLINE_DEV static fe inv(fe a) {
     fe r = one();
     _Pragma("unroll 1") for (int k = N - 1; k >= 0; k--) {
       uint32_t w = 0;

@@ -1,0 +1,415 @@
+// Host orchestration + C ABI of the MSM engine (see include/montgomery_b200.h).
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "engine.cuh"
+#include "../../include/montgomery_b200.h"
+
+using namespace mgb;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+enum Ev { EV_START, EV_H2D, EV_DIGITS, EV_SORT, EV_ACC, EV_REDUCE, EV_FINAL, EV_COUNT };
+
+}  // namespace
+
+struct mgb_ctx {
+  int curve = 0, device = 0;
+  size_t max_points = 0, npoints = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[EV_COUNT] = {};
+  DevBuf table, scalars, ent_bucket, ent_rank, counts, offs, tile_sums, refs, slot_bucket, pairs, V, redU[2], redW[2], misc, acc_out, out_xy, stage;
+  uint32_t* h_pinned = nullptr;  // [0..31] out xy limbs + flag, [64..] misc readback
+  int sm_count = 148;
+  std::string err;
+};
+
+namespace {
+
+int fail(mgb_ctx* ctx, int code, const std::string& msg) {
+  g_last_error = msg;
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+#define CU(ctx, call)                                                                         \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(ctx, e_ == cudaErrorMemoryAllocation ? MGB_E_NOMEM : MGB_E_CUDA,            \
+                  std::string(#call) + ": " + cudaGetErrorString(e_));                        \
+  } while (0)
+
+int ensure(mgb_ctx* ctx, DevBuf& b, size_t bytes) {
+  if (b.cap >= bytes) return 0;
+  if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+  size_t want = bytes + bytes / 8 + 256;
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(ctx, MGB_E_NOMEM, std::string("device memory overflow: cudaMalloc(") + std::to_string(want) + ") " + cudaGetErrorString(e));
+  }
+  b.cap = want;
+  return 0;
+}
+#define ENS(ctx, buf, bytes) do { int r_ = ensure(ctx, buf, bytes); if (r_) return r_; } while (0)
+
+int default_window(int curve, size_t n) {
+  int lg = 0;
+  while (((size_t)1 << lg) < n) lg++;
+  int c = lg - 4;
+  (void)curve;
+  return std::max(5, std::min(c, 20));
+}
+
+inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+template <class CV>
+int set_points_impl(mgb_ctx* ctx, const uint8_t* xy, const uint8_t* is_zero, size_t n) {
+  const size_t pbytes = 2 * CV::COORD_BYTES;
+  ENS(ctx, ctx->stage, n * pbytes + n);
+  CU(ctx, cudaMemcpyAsync(ctx->stage.p, xy, n * pbytes, cudaMemcpyHostToDevice, ctx->stream));
+  uint8_t* dz = nullptr;
+  if (is_zero) {
+    dz = (uint8_t*)ctx->stage.p + n * pbytes;
+    CU(ctx, cudaMemcpyAsync(dz, is_zero, n, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  k_set_points<CV><<<cdiv(n, 128), 128, 0, ctx->stream>>>((uint32_t)n, (const uint32_t*)ctx->stage.p, dz, (uint32_t*)ctx->table.p);
+  CU(ctx, cudaGetLastError());
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->npoints = n;
+  return 0;
+}
+
+template <class CV>
+int random_points_impl(mgb_ctx* ctx, uint64_t seed, size_t n) {
+  k_random_points<CV><<<cdiv(n, 128), 128, 0, ctx->stream>>>((uint32_t)n, seed, (uint32_t*)ctx->table.p);
+  CU(ctx, cudaGetLastError());
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->npoints = n;
+  return 0;
+}
+
+template <class CV>
+int get_points_impl(mgb_ctx* ctx, size_t first, size_t n, uint8_t* xy, uint8_t* is_zero) {
+  const size_t pbytes = 2 * CV::COORD_BYTES;
+  ENS(ctx, ctx->stage, n * pbytes + n);
+  uint8_t* dz = (uint8_t*)ctx->stage.p + n * pbytes;
+  k_get_points<CV><<<cdiv(n, 128), 128, 0, ctx->stream>>>((uint32_t)first, (uint32_t)n, (const uint32_t*)ctx->table.p, (uint32_t*)ctx->stage.p, dz);
+  CU(ctx, cudaGetLastError());
+  CU(ctx, cudaMemcpyAsync(xy, ctx->stage.p, n * pbytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (is_zero) CU(ctx, cudaMemcpyAsync(is_zero, dz, n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// Runs the pipeline; leaves the un-normalised result accumulator in ctx->acc_out.
+template <class CV>
+int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const mgb_opts* opts, mgb_timing* tm) {
+  cudaStream_t st = ctx->stream;
+  uint32_t launches = 0;
+  int c = (opts && opts->c > 0) ? opts->c : default_window(ctx->curve, n);
+  if (c < 2 || c > 24) return fail(ctx, MGB_E_INVALID, "window size c must be in [2, 24]");
+  MsmParams pr;
+  pr.n = (uint32_t)n;
+  pr.c = c;
+  pr.K = (CV::MAG_BITS + c - 1) / c;
+  pr.L = 1u << (c - 1);
+  pr.nbuckets = (uint32_t)pr.K * pr.L;
+  pr.nent = (uint32_t)(n * CV::HALVES * pr.K);
+  if ((size_t)n * CV::HALVES * pr.K >= (1ull << 31)) return fail(ctx, MGB_E_INVALID, "n * windows exceeds 2^31 entries");
+  const int mlog0 = std::min(4, c - 1);
+  const uint32_t nchunks0 = pr.nbuckets >> mlog0;
+
+  ENS(ctx, ctx->acc_out, CV::ACC_LIMBS * 4);
+  CU(ctx, cudaEventRecord(ctx->ev[EV_START], st));
+  const uint32_t* d_scalars;
+  if (on_device) {
+    d_scalars = (const uint32_t*)scalars;
+  } else {
+    ENS(ctx, ctx->scalars, n * 32);
+    CU(ctx, cudaMemcpyAsync(ctx->scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, st));
+    d_scalars = (const uint32_t*)ctx->scalars.p;
+  }
+  CU(ctx, cudaEventRecord(ctx->ev[EV_H2D], st));
+
+  ENS(ctx, ctx->ent_bucket, (size_t)pr.nent * 4);
+  ENS(ctx, ctx->ent_rank, (size_t)pr.nent * 4);
+  ENS(ctx, ctx->counts, ((size_t)pr.nbuckets + 1) * 4);
+  ENS(ctx, ctx->offs, ((size_t)pr.nbuckets + 1) * 4);
+  const uint32_t ntiles = cdiv(pr.nbuckets, SCAN_TILE);
+  ENS(ctx, ctx->tile_sums, (size_t)ntiles * 4);
+  ENS(ctx, ctx->refs, (size_t)pr.nent * 4);
+  ENS(ctx, ctx->slot_bucket, (size_t)pr.nent * 4);
+  ENS(ctx, ctx->pairs, ((size_t)pr.nent / 2 + 1) * 4);
+  ENS(ctx, ctx->V, ((size_t)pr.nent / 2 + 1) * CV::V_LIMBS * 4);
+  ENS(ctx, ctx->redU[0], (size_t)nchunks0 * CV::ACC_LIMBS * 4);
+  ENS(ctx, ctx->redW[0], (size_t)nchunks0 * CV::ACC_LIMBS * 4);
+  ENS(ctx, ctx->redU[1], ((size_t)(nchunks0 >> 4) + pr.K) * CV::ACC_LIMBS * 4);
+  ENS(ctx, ctx->redW[1], ((size_t)(nchunks0 >> 4) + pr.K) * CV::ACC_LIMBS * 4);
+  ENS(ctx, ctx->misc, 128 * 4);
+  uint32_t* misc = (uint32_t*)ctx->misc.p;  // [0] grand total, [1] max bucket, [2 + r] pair count of round r
+  CU(ctx, cudaMemsetAsync(ctx->counts.p, 0, ((size_t)pr.nbuckets + 1) * 4, st));
+  CU(ctx, cudaMemsetAsync(misc, 0, 128 * 4, st));
+
+  // ---- digits + histogram
+  k_digits<CV><<<cdiv(n, 256), 256, 0, st>>>(pr, d_scalars, (uint32_t*)ctx->ent_bucket.p, (uint32_t*)ctx->ent_rank.p, (uint32_t*)ctx->counts.p);
+  launches++;
+  CU(ctx, cudaGetLastError());
+  CU(ctx, cudaEventRecord(ctx->ev[EV_DIGITS], st));
+
+  // ---- offsets + scatter of references
+  k_scan_tiles<<<ntiles, SCAN_T, 0, st>>>((const uint32_t*)ctx->counts.p, (uint32_t*)ctx->offs.p, (uint32_t*)ctx->tile_sums.p, pr.nbuckets, misc + 1);
+  k_scan_sums<<<1, SCAN_T, 0, st>>>((uint32_t*)ctx->tile_sums.p, ntiles, misc);
+  k_scan_add<<<ntiles, SCAN_T, 0, st>>>((uint32_t*)ctx->offs.p, (const uint32_t*)ctx->tile_sums.p, pr.nbuckets, misc);
+  k_scatter<CV><<<cdiv(pr.nent, 256), 256, 0, st>>>(pr, (const uint32_t*)ctx->ent_bucket.p, (const uint32_t*)ctx->ent_rank.p,
+                                                   (const uint32_t*)ctx->offs.p, (uint32_t*)ctx->refs.p, (uint32_t*)ctx->slot_bucket.p);
+  launches += 4;
+  CU(ctx, cudaGetLastError());
+  CU(ctx, cudaMemcpyAsync(ctx->h_pinned + 64, misc, 8, cudaMemcpyDeviceToHost, st));
+  CU(ctx, cudaEventRecord(ctx->ev[EV_SORT], st));
+  CU(ctx, cudaStreamSynchronize(st));
+  const uint32_t nslots = ctx->h_pinned[64], maxcount = ctx->h_pinned[65];
+
+  // ---- bucket accumulation rounds
+  int rounds = 0;
+  while ((1u << rounds) < maxcount) rounds++;
+  const int grid_persist = ctx->sm_count * 2;
+  for (int r = 0; r < rounds; r++) {
+    k_plan<<<cdiv(nslots, 256), 256, 0, st>>>(nslots, r, (const uint32_t*)ctx->slot_bucket.p, (const uint32_t*)ctx->offs.p,
+                                             (uint32_t*)ctx->pairs.p, misc + 2 + r);
+    if constexpr (CV::BATCH_AFFINE) {
+      constexpr int T = 256, E = 8;
+      k_batch_add<CV, T, E><<<grid_persist, T, 2 * T * CV::N * 4, st>>>((const uint32_t*)ctx->table.p, (const uint32_t*)ctx->refs.p,
+                                                                        (uint32_t*)ctx->V.p, (const uint32_t*)ctx->pairs.p, misc + 2 + r, r);
+    } else {
+      k_pair_add<CV><<<ctx->sm_count * 8, 256, 0, st>>>((const uint32_t*)ctx->table.p, (const uint32_t*)ctx->refs.p,
+                                                       (uint32_t*)ctx->V.p, (const uint32_t*)ctx->pairs.p, misc + 2 + r, r);
+    }
+    launches += 2;
+  }
+  CU(ctx, cudaGetLastError());
+  CU(ctx, cudaEventRecord(ctx->ev[EV_ACC], st));
+
+  // ---- bucket reduction
+  k_reduce_level0<CV><<<cdiv(nchunks0, 128), 128, 0, st>>>(pr, mlog0, rounds, (const uint32_t*)ctx->table.p, (const uint32_t*)ctx->refs.p,
+                                                          (const uint32_t*)ctx->V.p, (const uint32_t*)ctx->offs.p,
+                                                          (uint32_t*)ctx->redU[0].p, (uint32_t*)ctx->redW[0].p);
+  launches++;
+  uint32_t nseg = pr.L >> mlog0;
+  int slog = mlog0, cur = 0;
+  while (nseg > 1) {
+    const int mlog = 4;
+    uint32_t nout = (nseg + 15) >> 4;
+    k_reduce_combine<CV><<<cdiv((size_t)nout * pr.K, 128), 128, 0, st>>>(pr.K, nseg, mlog, slog, (const uint32_t*)ctx->redU[cur].p, (const uint32_t*)ctx->redW[cur].p,
+                                                                        (uint32_t*)ctx->redU[cur ^ 1].p, (uint32_t*)ctx->redW[cur ^ 1].p);
+    launches++;
+    nseg = nout;
+    slog += mlog;
+    cur ^= 1;
+  }
+  CU(ctx, cudaGetLastError());
+  CU(ctx, cudaEventRecord(ctx->ev[EV_REDUCE], st));
+  k_final<CV><<<1, 32, 0, st>>>(pr.K, pr.c, (const uint32_t*)ctx->redU[cur].p, (const uint32_t*)ctx->redW[cur].p, (uint32_t*)ctx->acc_out.p);
+  launches++;
+  CU(ctx, cudaGetLastError());
+  if (tm) {
+    tm->c = c; tm->K = pr.K; tm->rounds = rounds; tm->max_bucket = maxcount; tm->n_launches = launches;
+    tm->n_pairs = 0;  // filled after the final sync (needs the per-round counters)
+  }
+  return 0;
+}
+
+int finish_timing(mgb_ctx* ctx, mgb_timing* tm) {
+  if (!tm) return 0;
+  auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]); return ms; };
+  tm->h2d_scalars = el(EV_START, EV_H2D);
+  tm->decompose_slice = el(EV_H2D, EV_DIGITS);
+  tm->sort = el(EV_DIGITS, EV_SORT);
+  tm->accumulate = el(EV_SORT, EV_ACC);
+  tm->reduce = el(EV_ACC, EV_REDUCE);
+  tm->final_sum = el(EV_REDUCE, EV_FINAL);
+  tm->total = el(EV_START, EV_FINAL);
+  uint32_t h[64];
+  CU(ctx, cudaMemcpy(h, (uint32_t*)ctx->misc.p + 2, sizeof(h), cudaMemcpyDeviceToHost));
+  uint64_t s = 0;
+  for (int r = 0; r < tm->rounds && r < 64; r++) s += h[r];
+  tm->n_pairs = s;
+  return 0;
+}
+
+template <class CV>
+int normalize_out(mgb_ctx* ctx, const void* d_accs, int count, uint8_t* out_xy, int* out_is_zero) {
+  ENS(ctx, ctx->out_xy, 64 * 4);
+  uint32_t* d = (uint32_t*)ctx->out_xy.p;
+  k_normalize<CV><<<1, 32, 0, ctx->stream>>>((const uint32_t*)d_accs, count, d, d + 2 * CV::N);
+  CU(ctx, cudaGetLastError());
+  CU(ctx, cudaMemcpyAsync(ctx->h_pinned, d, (2 * CV::N + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaEventRecord(ctx->ev[EV_FINAL], ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  if (out_xy) memcpy(out_xy, ctx->h_pinned, 2 * CV::COORD_BYTES);
+  if (out_is_zero) *out_is_zero = (int)ctx->h_pinned[2 * CV::N];
+  return 0;
+}
+
+template <class CV>
+int msm_impl(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const mgb_opts* opts, uint8_t* out_xy, int* out_is_zero, mgb_timing* tm) {
+  if (tm) memset(tm, 0, sizeof(*tm));
+  if (n == 0) {  // neutral element without touching the device pipeline
+    memset(out_xy, 0, 2 * CV::COORD_BYTES);
+    if (!CV::BATCH_AFFINE) out_xy[CV::COORD_BYTES] = 1;  // twisted Edwards neutral (0, 1)
+    if (out_is_zero) *out_is_zero = 1;
+    return 0;
+  }
+  int r = msm_core<CV>(ctx, scalars, on_device, n, opts, tm);
+  if (r) return r;
+  r = normalize_out<CV>(ctx, ctx->acc_out.p, 1, out_xy, out_is_zero);
+  if (r) return r;
+  if (tm) tm->n_launches += 1;
+  return finish_timing(ctx, tm);
+}
+
+template <class CV>
+int msm_partial_impl(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const mgb_opts* opts, void* d_out, mgb_timing* tm) {
+  if (tm) memset(tm, 0, sizeof(*tm));
+  if (n == 0) return fail(ctx, MGB_E_INVALID, "mgb_msm_partial: n must be > 0 on every rank");
+  int r = msm_core<CV>(ctx, scalars, on_device, n, opts, tm);
+  if (r) return r;
+  CU(ctx, cudaMemcpyAsync(d_out, ctx->acc_out.p, CV::ACC_LIMBS * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(ctx, cudaEventRecord(ctx->ev[EV_FINAL], ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return finish_timing(ctx, tm);
+}
+
+#define DISPATCH(ctx, fn, ...)                                              \
+  switch ((ctx)->curve) {                                                   \
+    case MGB_BLS12_377_G1: return fn<CurveBls377>(__VA_ARGS__);             \
+    case MGB_PALLAS: return fn<CurvePallas>(__VA_ARGS__);                   \
+    case MGB_ED_ON_BLS12_377: return fn<CurveEd377>(__VA_ARGS__);           \
+    default: return fail(ctx, MGB_E_INVALID, "unknown curve");              \
+  }
+
+size_t entry_bytes(int curve) {
+  switch (curve) {
+    case MGB_BLS12_377_G1: return CurveBls377::ENTRY_LIMBS * 4;
+    case MGB_PALLAS: return CurvePallas::ENTRY_LIMBS * 4;
+    default: return CurveEd377::ENTRY_LIMBS * 4;
+  }
+}
+
+int msm_common(mgb_ctx* ctx, const void* scalars, bool dev, size_t n, const mgb_opts* opts, uint8_t* out_xy, int* out_is_zero, mgb_timing* tm) {
+  if (!ctx || !out_xy || (!scalars && n)) return fail(ctx, MGB_E_INVALID, "mgb_msm: NULL argument");
+  if (n > ctx->npoints) return fail(ctx, ctx->npoints ? MGB_E_INVALID : MGB_E_STATE, "mgb_msm: n exceeds the number of points set");
+  CU(ctx, cudaSetDevice(ctx->device));
+  DISPATCH(ctx, msm_impl, ctx, scalars, dev, n, opts, out_xy, out_is_zero, tm);
+}
+
+}  // namespace
+
+extern "C" {
+
+int mgb_create(mgb_ctx** out, int curve, int device, size_t max_points) {
+  if (!out) return fail(nullptr, MGB_E_INVALID, "mgb_create: out is NULL");
+  if (curve < 0 || curve > 2) return fail(nullptr, MGB_E_INVALID, "mgb_create: unknown curve");
+  if (max_points == 0 || max_points > (1ull << 28)) return fail(nullptr, MGB_E_INVALID, "mgb_create: max_points must be in [1, 2^28]");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail(nullptr, MGB_E_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(nullptr, MGB_E_INVALID, "mgb_create: bad device index");
+  mgb_ctx* ctx = new mgb_ctx();
+  ctx->curve = curve;
+  ctx->device = device;
+  ctx->max_points = max_points;
+  int rc = [&]() -> int {
+    CU(ctx, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(ctx, cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    CU(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < EV_COUNT; i++) CU(ctx, cudaEventCreate(&ctx->ev[i]));
+    CU(ctx, cudaMallocHost((void**)&ctx->h_pinned, 256 * 4));
+    return ensure(ctx, ctx->table, max_points * entry_bytes(curve));
+  }();
+  if (rc) { std::string m = ctx->err; mgb_destroy(ctx); return fail(nullptr, rc, m); }
+  *out = ctx;
+  return 0;
+}
+
+int mgb_set_points(mgb_ctx* ctx, const uint8_t* xy_le, const uint8_t* is_zero, size_t n) {
+  if (!ctx || (!xy_le && n)) return fail(ctx, MGB_E_INVALID, "mgb_set_points: NULL argument");
+  if (n > ctx->max_points) return fail(ctx, MGB_E_INVALID, "mgb_set_points: n exceeds max_points");
+  CU(ctx, cudaSetDevice(ctx->device));
+  if (n == 0) { ctx->npoints = 0; return 0; }
+  DISPATCH(ctx, set_points_impl, ctx, xy_le, is_zero, n);
+}
+
+int mgb_random_points(mgb_ctx* ctx, uint64_t seed, size_t n) {
+  if (!ctx) return fail(ctx, MGB_E_INVALID, "mgb_random_points: NULL ctx");
+  if (n > ctx->max_points) return fail(ctx, MGB_E_INVALID, "mgb_random_points: n exceeds max_points");
+  CU(ctx, cudaSetDevice(ctx->device));
+  if (n == 0) { ctx->npoints = 0; return 0; }
+  DISPATCH(ctx, random_points_impl, ctx, seed, n);
+}
+
+int mgb_get_points(mgb_ctx* ctx, size_t first, size_t n, uint8_t* xy_le, uint8_t* is_zero) {
+  if (!ctx || (!xy_le && n)) return fail(ctx, MGB_E_INVALID, "mgb_get_points: NULL argument");
+  if (first + n > ctx->npoints) return fail(ctx, MGB_E_INVALID, "mgb_get_points: range exceeds stored points");
+  CU(ctx, cudaSetDevice(ctx->device));
+  if (n == 0) return 0;
+  DISPATCH(ctx, get_points_impl, ctx, first, n, xy_le, is_zero);
+}
+
+int mgb_msm(mgb_ctx* ctx, const uint8_t* scalars_le32, size_t n, const mgb_opts* opts, uint8_t* out_xy_le, int* out_is_zero, mgb_timing* timing) {
+  return msm_common(ctx, scalars_le32, false, n, opts, out_xy_le, out_is_zero, timing);
+}
+int mgb_msm_device(mgb_ctx* ctx, const void* d_scalars_le32, size_t n, const mgb_opts* opts, uint8_t* out_xy_le, int* out_is_zero, mgb_timing* timing) {
+  return msm_common(ctx, d_scalars_le32, true, n, opts, out_xy_le, out_is_zero, timing);
+}
+
+size_t mgb_partial_bytes(const mgb_ctx* ctx) {
+  if (!ctx) return 0;
+  switch (ctx->curve) {
+    case MGB_BLS12_377_G1: return CurveBls377::ACC_LIMBS * 4;
+    case MGB_PALLAS: return CurvePallas::ACC_LIMBS * 4;
+    default: return CurveEd377::ACC_LIMBS * 4;
+  }
+}
+
+int mgb_msm_partial(mgb_ctx* ctx, const void* scalars, int scalars_on_device, size_t n, const mgb_opts* opts, void* d_partial_out, mgb_timing* timing) {
+  if (!ctx || !d_partial_out || !scalars) return fail(ctx, MGB_E_INVALID, "mgb_msm_partial: NULL argument");
+  if (n > ctx->npoints) return fail(ctx, ctx->npoints ? MGB_E_INVALID : MGB_E_STATE, "mgb_msm_partial: n exceeds the number of points set");
+  CU(ctx, cudaSetDevice(ctx->device));
+  DISPATCH(ctx, msm_partial_impl, ctx, scalars, scalars_on_device != 0, n, opts, d_partial_out, timing);
+}
+
+int mgb_combine_partials(mgb_ctx* ctx, const void* d_partials, int count, uint8_t* out_xy_le, int* out_is_zero) {
+  if (!ctx || !d_partials || !out_xy_le || count < 1) return fail(ctx, MGB_E_INVALID, "mgb_combine_partials: bad argument");
+  CU(ctx, cudaSetDevice(ctx->device));
+  DISPATCH(ctx, normalize_out, ctx, d_partials, count, out_xy_le, out_is_zero);
+}
+
+const char* mgb_last_error(const mgb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+void mgb_destroy(mgb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  DevBuf* bufs[] = {&ctx->table, &ctx->scalars, &ctx->ent_bucket, &ctx->ent_rank, &ctx->counts, &ctx->offs, &ctx->tile_sums, &ctx->refs,
+                    &ctx->slot_bucket, &ctx->pairs, &ctx->V, &ctx->redU[0], &ctx->redU[1], &ctx->redW[0], &ctx->redW[1], &ctx->misc,
+                    &ctx->acc_out, &ctx->out_xy, &ctx->stage};
+  for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  for (int i = 0; i < EV_COUNT; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+}  // extern "C"

@@ -1,0 +1,183 @@
+// Field-layer test hooks and integer-pipe microbenchmarks (see include/montgomery_b200.h).
+#include <cstdio>
+#include <string>
+#include "engine.cuh"
+#include "../../include/montgomery_b200.h"
+
+using namespace mgb;
+
+namespace {
+
+template <class P>
+__global__ void __launch_bounds__(128) k_field_op(int op, uint32_t n, const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, uint32_t* __restrict__ out) {
+  typedef Field<P> F;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fe<P> x = F::to_mont(ld_fe<P>(a + (size_t)i * P::N));
+  Fe<P> y = F::to_mont(ld_fe<P>(b + (size_t)i * P::N));
+  Fe<P> r;
+  switch (op) {
+    case 0: r = F::mul(x, y); break;
+    case 1: r = F::add(x, y); break;
+    case 2: r = F::sub(x, y); break;
+    case 3: r = F::inv(x); break;
+    case 4: r = F::sqr(x); break;
+    case 5: r = F::inv_bgcd(x); break;
+    case 6: r = F::neg(x); break;
+    default: r = F::zero();
+  }
+  st_fe<P>(out + (size_t)i * P::N, F::from_mont(r));
+}
+
+// ---- integer pipe microbenchmarks: 8 independent dependency chains per thread
+template <int MODE>
+__global__ void __launch_bounds__(1024) k_imad(uint32_t* out, uint32_t seed, int iters) {
+  uint32_t a = seed ^ threadIdx.x, b = seed * 2654435761u + blockIdx.x;
+  if (MODE <= 1) {
+    uint32_t x[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = a + k;
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int u = 0; u < 16; u++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          if (MODE == 0) asm volatile("mad.lo.u32 %0,%0,%1,%2;" : "+r"(x[k]) : "r"(a), "r"(b));
+          else asm volatile("mad.hi.u32 %0,%0,%1,%2;" : "+r"(x[k]) : "r"(a), "r"(b));
+        }
+      }
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s ^= x[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  } else if (MODE == 2) {
+    uint64_t x[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = a + k;
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int u = 0; u < 16; u++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) asm volatile("mad.wide.u32 %0,%1,%2,%0;" : "+l"(x[k]) : "r"(a), "r"(b));
+      }
+    }
+    uint64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s ^= x[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = (uint32_t)(s ^ (s >> 32));
+  } else {
+    // carry chain: 8 aligned pairs, one IMAD.WIDE.U32.X each, carry rippling through
+    uint32_t x[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = a + k;
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int u = 0; u < 16; u++) {
+        x[0] = ptx::mad_lo_cc(a, b, x[0]);
+        x[1] = ptx::madc_hi_cc(a, b, x[1]);
+#pragma unroll
+        for (int k = 2; k < 16; k += 2) {
+          x[k] = ptx::madc_lo_cc(a, b, x[k]);
+          x[k + 1] = ptx::madc_hi_cc(a, b, x[k + 1]);
+        }
+      }
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) s ^= x[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  }
+}
+
+template <class P, bool INL>
+__global__ void __launch_bounds__(1024) k_mulbench(uint32_t* out, uint32_t seed, int iters) {
+  typedef Field<P> F;
+  Fe<P> a = F::one(), b = F::one();
+  a.v[0] ^= (seed ^ threadIdx.x) & 0xffff;
+  b.v[1] ^= blockIdx.x & 0xffff;
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+    if (INL) { a = F::mul_inl(a, b); b = F::mul_inl(b, a); }
+    else { a = F::mul(a, b); b = F::mul(b, a); }
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < P::N; k++) s ^= a.v[k] ^ b.v[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+thread_local std::string g_err;
+#define CUT(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_err = std::string(#call) + ": " + cudaGetErrorString(e_); return MGB_E_CUDA; } } while (0)
+
+}  // namespace
+
+extern "C" {
+
+int mgb_field_op(int device, int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
+  if (!a || !b || !out || field < 0 || field > 2) return MGB_E_INVALID;
+  CUT(cudaSetDevice(device));
+  const int N = field == 0 ? 12 : 8;
+  size_t bytes = n * N * 4;
+  uint32_t *da, *db, *dout;
+  CUT(cudaMalloc(&da, bytes)); CUT(cudaMalloc(&db, bytes)); CUT(cudaMalloc(&dout, bytes));
+  CUT(cudaMemcpy(da, a, bytes, cudaMemcpyHostToDevice));
+  CUT(cudaMemcpy(db, b, bytes, cudaMemcpyHostToDevice));
+  unsigned grid = (unsigned)((n + 127) / 128);
+  if (field == 0) k_field_op<Fp377><<<grid, 128>>>(op, (uint32_t)n, da, db, dout);
+  else if (field == 1) k_field_op<Fr377><<<grid, 128>>>(op, (uint32_t)n, da, db, dout);
+  else k_field_op<FpPallas><<<grid, 128>>>(op, (uint32_t)n, da, db, dout);
+  CUT(cudaGetLastError());
+  CUT(cudaMemcpy(out, dout, bytes, cudaMemcpyDeviceToHost));
+  cudaFree(da); cudaFree(db); cudaFree(dout);
+  return 0;
+}
+
+int mgb_microbench(int device, int mode, int blocks_per_sm, int threads, int iters, double* ops_per_s, float* ms_out) {
+  if (!ops_per_s || threads < 32 || threads > 1024 || blocks_per_sm < 1 || iters < 1) return MGB_E_INVALID;
+  CUT(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUT(cudaGetDeviceProperties(&prop, device));
+  int grid = prop.multiProcessorCount * blocks_per_sm;
+  uint32_t* d;
+  CUT(cudaMalloc(&d, (size_t)grid * threads * 4));
+  cudaEvent_t e0, e1;
+  CUT(cudaEventCreate(&e0)); CUT(cudaEventCreate(&e1));
+  auto launch = [&](int it) {
+    switch (mode) {
+      case 0: k_imad<0><<<grid, threads>>>(d, 12345u, it); break;
+      case 1: k_imad<1><<<grid, threads>>>(d, 12345u, it); break;
+      case 2: k_imad<2><<<grid, threads>>>(d, 12345u, it); break;
+      case 3: k_imad<3><<<grid, threads>>>(d, 12345u, it); break;
+      case 4: k_mulbench<Fp377, false><<<grid, threads>>>(d, 12345u, it); break;
+      case 5: k_mulbench<Fr377, false><<<grid, threads>>>(d, 12345u, it); break;
+      case 6: k_mulbench<Fp377, true><<<grid, threads>>>(d, 12345u, it); break;
+      case 7: k_mulbench<Fr377, true><<<grid, threads>>>(d, 12345u, it); break;
+      default: break;
+    }
+  };
+  if (mode < 0 || mode > 7) return MGB_E_INVALID;
+  launch(iters / 8 + 1);  // warm-up
+  CUT(cudaDeviceSynchronize());
+  CUT(cudaEventRecord(e0));
+  launch(iters);
+  CUT(cudaEventRecord(e1));
+  CUT(cudaEventSynchronize(e1));
+  CUT(cudaGetLastError());
+  float ms = 0;
+  CUT(cudaEventElapsedTime(&ms, e0, e1));
+  double per_thread;
+  if (mode <= 2) per_thread = 16.0 * 8 * iters;        // instructions per thread
+  else if (mode == 3) per_thread = 16.0 * 8 * iters;   // wide MADs per thread
+  else per_thread = 2.0 * iters;                        // field multiplications per thread
+  *ops_per_s = per_thread * (double)grid * threads / (ms * 1e-3);
+  if (ms_out) *ms_out = ms;
+  cudaFree(d);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return 0;
+}
+
+}  // extern "C"

