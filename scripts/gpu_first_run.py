@@ -1,6 +1,6 @@
 """First GPU run: microbenchmarks + quick MSM timings -> gpurun_out/first_run.json"""
 import ctypes, json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import montgomery_b200 as m
 from montgomery_b200 import _native, inputs
