@@ -367,42 +367,10 @@ static __global__ void __launch_bounds__(SCAN_T) k_scan_add(uint32_t* __restrict
 }
 
 // ---------------------------------------------------------------- k_scatter
-// refs[slot] = point reference, slot_bucket[slot] = bucket, slot = offs[bucket] + rank
-template <class CV>
-__global__ void __launch_bounds__(256) k_scatter(MsmParams pr, const uint32_t* __restrict__ ent_bucket, const uint32_t* __restrict__ ent_rank,
-                                                 const uint32_t* __restrict__ offs, uint32_t* __restrict__ refs, uint32_t* __restrict__ slot_bucket) {
-  size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pos >= pr.nent) return;
-  uint32_t b = ent_bucket[pos];
-  if (b == NO_BUCKET) return;
-  uint32_t rk = ent_rank[pos];
-  uint32_t e = (uint32_t)(pos / pr.n), i = (uint32_t)(pos - (size_t)e * pr.n);
-  uint32_t ref = i | (rk & REF_NEG);
-  if (CV::HALVES == 2 && e >= (uint32_t)pr.K) ref |= REF_ENDO;
-  uint32_t slot = offs[b] + (rk & ~REF_NEG);
-  refs[slot] = ref;
-  slot_bucket[slot] = b;
-}
-
-// ---------------------------------------------------------------- k_plan
-// Round r of the in-place bucket tree (reference: msm-batched-affine.ts:243-263): the element at
-// local index j (multiple of 2^(r+1)) absorbs the element at j + 2^r if that is inside the bucket.
-// Emits the compact list of left slots (order irrelevant: pairs are independent).
-static __global__ void __launch_bounds__(256) k_plan(uint32_t nslots, int r, const uint32_t* __restrict__ slot_bucket,
-                                              const uint32_t* __restrict__ offs, uint32_t* __restrict__ pairs, uint32_t* __restrict__ npairs) {
-  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  bool active = false;
-  uint32_t entry = 0;
-  if (s < nslots) {
-    uint32_t b = slot_bucket[s];
-    uint32_t o = offs[b], n = offs[b + 1] - o, j = s - o;
-    uint32_t step = 1u << r;
-    if ((j & (2 * step - 1)) == 0 && j + step < n) {
-      active = true;
-      bool right_raw = (r == 0) || (j + step + 1 >= n);  // right operand was never a left operand in round 0
-      entry = s | (right_raw ? PAIR_RIGHT_RAW : 0u);
-    }
-  }
+// refs[slot] = point reference, slot_bucket[slot] = bucket, slot = offs[bucket] + rank.
+// Also emits the pair list of round 0 of the bucket tree: a slot with even rank whose right
+// neighbour is inside the bucket absorbs that neighbour (order of the list is irrelevant).
+MGB_DEV void emit_pair(bool active, uint32_t entry, uint32_t* __restrict__ pairs, uint32_t* __restrict__ npairs) {
   uint32_t m = __ballot_sync(0xffffffffu, active);
   if (m) {
     int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
@@ -413,15 +381,62 @@ static __global__ void __launch_bounds__(256) k_plan(uint32_t nslots, int r, con
   }
 }
 
+template <class CV>
+__global__ void __launch_bounds__(256) k_scatter(MsmParams pr, const uint32_t* __restrict__ ent_bucket, const uint32_t* __restrict__ ent_rank,
+                                                 const uint32_t* __restrict__ offs, uint32_t* __restrict__ refs, uint32_t* __restrict__ slot_bucket,
+                                                 uint32_t* __restrict__ pairs, uint32_t* __restrict__ npairs) {
+  size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool active = false;
+  uint32_t slot = 0;
+  if (pos < pr.nent) {
+    uint32_t b = ent_bucket[pos];
+    if (b != NO_BUCKET) {
+      uint32_t rk = ent_rank[pos];
+      uint32_t e = (uint32_t)(pos / pr.n), i = (uint32_t)(pos - (size_t)e * pr.n);
+      uint32_t ref = i | (rk & REF_NEG);
+      if (CV::HALVES == 2 && e >= (uint32_t)pr.K) ref |= REF_ENDO;
+      uint32_t o = offs[b], n = offs[b + 1] - o, j = rk & ~REF_NEG;
+      slot = o + j;
+      refs[slot] = ref;
+      slot_bucket[slot] = b;
+      active = ((j & 1) == 0) && (j + 1 < n);
+    }
+  }
+  emit_pair(active, slot | PAIR_RIGHT_RAW, pairs, npairs);
+}
+
+// After round r, the element at local index j (multiple of 2^(r+1)) is a left operand of round r+1
+// iff j is a multiple of 2^(r+2) and j + 2^(r+1) is inside the bucket (reference:
+// msm-batched-affine.ts:243-263).  Left operands of round r+1 are a subset of those of round r, so
+// each add kernel emits the next round's list itself.
+MGB_DEV void emit_next_round(bool valid, uint32_t s, int r, const uint32_t* __restrict__ slot_bucket, const uint32_t* __restrict__ offs,
+                             uint32_t* __restrict__ pairs_out, uint32_t* __restrict__ npairs_out) {
+  bool active = false;
+  uint32_t entry = 0;
+  if (valid) {
+    uint32_t b = slot_bucket[s];
+    uint32_t o = offs[b], n = offs[b + 1] - o, j = s - o;
+    uint32_t step = 2u << r;
+    if ((j & (2 * step - 1)) == 0 && j + step < n) {
+      active = true;
+      entry = s | ((j + step + 1 >= n) ? PAIR_RIGHT_RAW : 0u);  // right operand never had a partner: still a raw reference
+    }
+  }
+  emit_pair(active, entry, pairs_out, npairs_out);
+}
+
 // ---------------------------------------------------------------- k_batch_add (Weierstrass)
 // Persistent blocks; each tile is T*E independent affine additions sharing ONE field inversion:
 // per-thread prefix products (E elements, kept in local memory), a product tree over the T thread
-// totals in shared memory, one binary-gcd inversion by thread 0, tree down-sweep, per-thread
-// back-substitution.  6 multiplications per addition + 3/E for the tree.
-template <class CV, int T, int E>
-__global__ void __launch_bounds__(T) k_batch_add(const uint32_t* __restrict__ table, const uint32_t* __restrict__ refs,
-                                                 uint32_t* __restrict__ V, const uint32_t* __restrict__ pairs,
-                                                 const uint32_t* __restrict__ npairs_ptr, int r) {
+// totals in shared memory, one binary-gcd inversion by thread 0 (ALU pipe; the other resident
+// blocks keep the multiplier busy meanwhile), tree down-sweep, per-thread back-substitution.
+// 6 multiplications per addition + 3/E for the tree.  Emits the pair list of the next round.
+template <class CV, int T, int E, int MINB>
+__global__ void __launch_bounds__(T, MINB) k_batch_add(const uint32_t* __restrict__ table, const uint32_t* __restrict__ refs,
+                                                       uint32_t* __restrict__ V, const uint32_t* __restrict__ pairs,
+                                                       const uint32_t* __restrict__ npairs_ptr, int r,
+                                                       const uint32_t* __restrict__ slot_bucket, const uint32_t* __restrict__ offs,
+                                                       uint32_t* __restrict__ pairs_out, uint32_t* __restrict__ npairs_out) {
   typedef typename CV::P FP;
   typedef typename CV::F F;
   typedef typename CV::G G;
@@ -436,7 +451,8 @@ __global__ void __launch_bounds__(T) k_batch_add(const uint32_t* __restrict__ ta
 
   for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     fe den[E], pre[E];
-    uint32_t kinds = 0;
+    uint32_t kinds[(E + 7) / 8];
+    _Pragma("unroll") for (int k = 0; k < (E + 7) / 8; k++) kinds[k] = 0;
     fe run = F::one();
     _Pragma("unroll 1") for (int e = 0; e < E; e++) {
       uint32_t idx = tile * (T * E) + e * T + tid;
@@ -449,7 +465,7 @@ __global__ void __launch_bounds__(T) k_batch_add(const uint32_t* __restrict__ ta
         typename CV::vpoint B = (ent & PAIR_RIGHT_RAW) ? CV::load_raw(table, refs[s + step]) : CV::load_v(V, s + step);
         kind = G::add_prepare(A, B, d);
       }
-      kinds |= (uint32_t)kind << (3 * e);
+      _Pragma("unroll") for (int k = 0; k < (E + 7) / 8; k++) if (k == (e >> 3)) kinds[k] |= (uint32_t)kind << (4 * (e & 7));
       pre[e] = run;
       den[e] = d;
       run = F::mul(run, d);
@@ -479,16 +495,20 @@ __global__ void __launch_bounds__(T) k_batch_add(const uint32_t* __restrict__ ta
     fe u = ld_fe<FP>(tree + (size_t)(T + tid) * N);  // inverse of this thread's total
     __syncthreads();                                  // tree is reused by the next tile
     _Pragma("unroll 1") for (int e = E - 1; e >= 0; e--) {
-      int kind = (kinds >> (3 * e)) & 7;
+      int kind = 0;
+      _Pragma("unroll") for (int k = 0; k < (E + 7) / 8; k++) if (k == (e >> 3)) kind = (kinds[k] >> (4 * (e & 7))) & 15;
       fe inv_den = F::mul(u, pre[e]);
       u = F::mul(u, den[e]);
-      if (kind == 5) continue;
-      uint32_t idx = tile * (T * E) + e * T + tid;
-      uint32_t ent = pairs[idx];
-      uint32_t s = ent & ~PAIR_RIGHT_RAW;
-      typename CV::vpoint A = (r == 0) ? CV::load_raw(table, refs[s]) : CV::load_v(V, s);
-      typename CV::vpoint B = (ent & PAIR_RIGHT_RAW) ? CV::load_raw(table, refs[s + step]) : CV::load_v(V, s + step);
-      CV::store_v(V, s, G::add_finish(kind, A, B, inv_den));
+      uint32_t s = 0;
+      if (kind != 5) {
+        uint32_t idx = tile * (T * E) + e * T + tid;
+        uint32_t ent = pairs[idx];
+        s = ent & ~PAIR_RIGHT_RAW;
+        typename CV::vpoint A = (r == 0) ? CV::load_raw(table, refs[s]) : CV::load_v(V, s);
+        typename CV::vpoint B = (ent & PAIR_RIGHT_RAW) ? CV::load_raw(table, refs[s + step]) : CV::load_v(V, s + step);
+        CV::store_v(V, s, G::add_finish(kind, A, B, inv_den));
+      }
+      emit_next_round(kind != 5, s, r, slot_bucket, offs, pairs_out, npairs_out);
     }
   }
 }
@@ -497,21 +517,29 @@ __global__ void __launch_bounds__(T) k_batch_add(const uint32_t* __restrict__ ta
 template <class CV>
 __global__ void __launch_bounds__(256) k_pair_add(const uint32_t* __restrict__ table, const uint32_t* __restrict__ refs,
                                                   uint32_t* __restrict__ V, const uint32_t* __restrict__ pairs,
-                                                  const uint32_t* __restrict__ npairs_ptr, int r) {
+                                                  const uint32_t* __restrict__ npairs_ptr, int r,
+                                                  const uint32_t* __restrict__ slot_bucket, const uint32_t* __restrict__ offs,
+                                                  uint32_t* __restrict__ pairs_out, uint32_t* __restrict__ npairs_out) {
   const uint32_t npairs = *npairs_ptr;
   const uint32_t step = 1u << r;
-  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < npairs; idx += gridDim.x * blockDim.x) {
-    uint32_t ent = pairs[idx];
-    uint32_t s = ent & ~PAIR_RIGHT_RAW;
-    typename CV::acc res;
-    if (r == 0) {
-      res = CV::G::add_affine(CV::load_raw(table, refs[s]), CV::load_raw(table, refs[s + step]));
-    } else {
-      typename CV::acc A = CV::load_v(V, s);
-      if (ent & PAIR_RIGHT_RAW) res = CV::add_raw(A, CV::load_raw(table, refs[s + step]));
-      else res = CV::add_v(A, CV::load_v(V, s + step));
+  const uint32_t nround = (npairs + 31) & ~31u;   // whole warps iterate together (ballot in emit_next_round)
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nround; idx += gridDim.x * blockDim.x) {
+    uint32_t s = 0;
+    bool valid = idx < npairs;
+    if (valid) {
+      uint32_t ent = pairs[idx];
+      s = ent & ~PAIR_RIGHT_RAW;
+      typename CV::acc res;
+      if (r == 0) {
+        res = CV::G::add_affine(CV::load_raw(table, refs[s]), CV::load_raw(table, refs[s + step]));
+      } else {
+        typename CV::acc A = CV::load_v(V, s);
+        if (ent & PAIR_RIGHT_RAW) res = CV::add_raw(A, CV::load_raw(table, refs[s + step]));
+        else res = CV::add_v(A, CV::load_v(V, s + step));
+      }
+      CV::store_v(V, s, res);
     }
-    CV::store_v(V, s, res);
+    emit_next_round(valid, s, r, slot_bucket, offs, pairs_out, npairs_out);
   }
 }
 

@@ -27,7 +27,7 @@ struct mgb_ctx {
   size_t max_points = 0, npoints = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[EV_COUNT] = {};
-  DevBuf table, scalars, ent_bucket, ent_rank, counts, offs, tile_sums, refs, slot_bucket, pairs, V, redU[2], redW[2], misc, acc_out, out_xy, stage;
+  DevBuf table, scalars, ent_bucket, ent_rank, counts, offs, tile_sums, refs, slot_bucket, pairs, pairs2, V, redU[2], redW[2], misc, acc_out, out_xy, stage;
   uint32_t* h_pinned = nullptr;  // [0..31] out xy limbs + flag, [64..] misc readback
   int sm_count = 148;
   std::string err;
@@ -151,6 +151,7 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   ENS(ctx, ctx->refs, (size_t)pr.nent * 4);
   ENS(ctx, ctx->slot_bucket, (size_t)pr.nent * 4);
   ENS(ctx, ctx->pairs, ((size_t)pr.nent / 2 + 1) * 4);
+  ENS(ctx, ctx->pairs2, ((size_t)pr.nent / 4 + 1) * 4);
   ENS(ctx, ctx->V, ((size_t)pr.nent / 2 + 1) * CV::V_LIMBS * 4);
   ENS(ctx, ctx->redU[0], (size_t)nchunks0 * CV::ACC_LIMBS * 4);
   ENS(ctx, ctx->redW[0], (size_t)nchunks0 * CV::ACC_LIMBS * 4);
@@ -172,7 +173,8 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   k_scan_sums<<<1, SCAN_T, 0, st>>>((uint32_t*)ctx->tile_sums.p, ntiles, misc);
   k_scan_add<<<ntiles, SCAN_T, 0, st>>>((uint32_t*)ctx->offs.p, (const uint32_t*)ctx->tile_sums.p, pr.nbuckets, misc);
   k_scatter<CV><<<cdiv(pr.nent, 256), 256, 0, st>>>(pr, (const uint32_t*)ctx->ent_bucket.p, (const uint32_t*)ctx->ent_rank.p,
-                                                   (const uint32_t*)ctx->offs.p, (uint32_t*)ctx->refs.p, (uint32_t*)ctx->slot_bucket.p);
+                                                   (const uint32_t*)ctx->offs.p, (uint32_t*)ctx->refs.p, (uint32_t*)ctx->slot_bucket.p,
+                                                   (uint32_t*)ctx->pairs.p, misc + 2);
   launches += 4;
   CU(ctx, cudaGetLastError());
   CU(ctx, cudaMemcpyAsync(ctx->h_pinned + 64, misc, 8, cudaMemcpyDeviceToHost, st));
@@ -181,21 +183,30 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   const uint32_t nslots = ctx->h_pinned[64], maxcount = ctx->h_pinned[65];
 
   // ---- bucket accumulation rounds
-  int rounds = 0;
-  while ((1u << rounds) < maxcount) rounds++;
-  const int grid_persist = ctx->sm_count * 2;
+  // Full depth is ceil(log2(max bucket)); for the usual near-uniform digit distribution the last
+  // rounds hold a handful of pairs each and cost a full batch latency, so they are left to the
+  // reduction kernel (which sums whatever a bucket has left).  Skewed inputs run the full depth.
+  int r_full = 0;
+  while ((1u << r_full) < maxcount) r_full++;
+  const uint32_t nonempty_bound = std::min<uint32_t>(pr.nbuckets, std::max<uint32_t>(nslots, 1));
+  const uint32_t avg = (nslots + nonempty_bound - 1) / nonempty_bound;
+  int r_typ = 0;
+  while ((1u << r_typ) < avg) r_typ++;
+  int rounds = (r_full <= r_typ + 4) ? std::min(r_full, r_typ) : r_full;
+  if (opts && opts->verbose > 1) rounds = r_full;
   for (int r = 0; r < rounds; r++) {
-    k_plan<<<cdiv(nslots, 256), 256, 0, st>>>(nslots, r, (const uint32_t*)ctx->slot_bucket.p, (const uint32_t*)ctx->offs.p,
-                                             (uint32_t*)ctx->pairs.p, misc + 2 + r);
+    uint32_t* pin = (uint32_t*)((r & 1) ? ctx->pairs2.p : ctx->pairs.p);
+    uint32_t* pout = (uint32_t*)((r & 1) ? ctx->pairs.p : ctx->pairs2.p);
     if constexpr (CV::BATCH_AFFINE) {
-      constexpr int T = 256, E = 8;
-      k_batch_add<CV, T, E><<<grid_persist, T, 2 * T * CV::N * 4, st>>>((const uint32_t*)ctx->table.p, (const uint32_t*)ctx->refs.p,
-                                                                        (uint32_t*)ctx->V.p, (const uint32_t*)ctx->pairs.p, misc + 2 + r, r);
+      constexpr int T = 128, E = 16, MINB = 4;
+      k_batch_add<CV, T, E, MINB><<<ctx->sm_count * MINB, T, 2 * T * CV::N * 4, st>>>(
+          (const uint32_t*)ctx->table.p, (const uint32_t*)ctx->refs.p, (uint32_t*)ctx->V.p, pin, misc + 2 + r, r,
+          (const uint32_t*)ctx->slot_bucket.p, (const uint32_t*)ctx->offs.p, pout, misc + 3 + r);
     } else {
-      k_pair_add<CV><<<ctx->sm_count * 8, 256, 0, st>>>((const uint32_t*)ctx->table.p, (const uint32_t*)ctx->refs.p,
-                                                       (uint32_t*)ctx->V.p, (const uint32_t*)ctx->pairs.p, misc + 2 + r, r);
+      k_pair_add<CV><<<ctx->sm_count * 8, 256, 0, st>>>((const uint32_t*)ctx->table.p, (const uint32_t*)ctx->refs.p, (uint32_t*)ctx->V.p, pin,
+                                                       misc + 2 + r, r, (const uint32_t*)ctx->slot_bucket.p, (const uint32_t*)ctx->offs.p, pout, misc + 3 + r);
     }
-    launches += 2;
+    launches += 1;
   }
   CU(ctx, cudaGetLastError());
   CU(ctx, cudaEventRecord(ctx->ev[EV_ACC], st));
@@ -403,7 +414,7 @@ void mgb_destroy(mgb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   DevBuf* bufs[] = {&ctx->table, &ctx->scalars, &ctx->ent_bucket, &ctx->ent_rank, &ctx->counts, &ctx->offs, &ctx->tile_sums, &ctx->refs,
-                    &ctx->slot_bucket, &ctx->pairs, &ctx->V, &ctx->redU[0], &ctx->redU[1], &ctx->redW[0], &ctx->redW[1], &ctx->misc,
+                    &ctx->slot_bucket, &ctx->pairs, &ctx->pairs2, &ctx->V, &ctx->redU[0], &ctx->redU[1], &ctx->redW[0], &ctx->redW[1], &ctx->misc,
                     &ctx->acc_out, &ctx->out_xy, &ctx->stage};
   for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
