@@ -243,10 +243,10 @@ def run_b200(args):
     lib = _native.lib()
     ops = ctypes.c_double()
     msb = ctypes.c_float()
-    lib.mgb_microbench(local, 2, 2, 1024, 2000, ctypes.byref(ops), ctypes.byref(msb))    # mad.wide.u32, independent chains
+    lib.mgb_microbench(local, 3, 2, 1024, 2000, ctypes.byref(ops), ctypes.byref(msb))    # carry-chained IMAD.WIDE.U32.X = one full 32x32+64->64 MAD
     peak_mads = ops.value
-    lib.mgb_microbench(local, 3, 2, 1024, 2000, ctypes.byref(ops), ctypes.byref(msb))    # carry-chained IMAD.WIDE.U32.X
-    peak_carry = ops.value
+    lib.mgb_microbench(local, 0, 2, 1024, 2000, ctypes.byref(ops), ctypes.byref(msb))    # plain IMAD (mad.lo.u32) issue rate
+    peak_imad_lo = ops.value
     algo_mads = ALGO_FIELD_MULTS_PER_POINT * MADS_PER_FIELD_MULT * n        # per GPU per step (reference op counts)
     acc_ms = phases["accumulate"]
     achieved = algo_mads / (phases["total"] * 1e-3)
@@ -254,7 +254,8 @@ def run_b200(args):
         "bound": "imad", "achieved": achieved / 1e12, "peak": peak_mads / 1e12, "unit": "T 32x32->64 MAD/s",
         "frac": achieved / peak_mads, "traffic": None,
         "note": "integer-multiply roofline of BASELINE.md: algorithmic MADs (108.6 field mults/point x 288) / device time of the whole MSM "
-                "(CUDA events on the engine's stream) / measured mad.wide.u32 rate of this GPU; carry-chained IMAD.WIDE.X peak = %.2f T/s" % (peak_carry / 1e12),
+                "(CUDA events on the engine's stream) / measured rate of carry-chained IMAD.WIDE.U32.X (one full 32x32+64->64 MAD per lane) on this GPU; "
+                "plain IMAD (mad.lo) issues at %.2f T/s, i.e. a full MAD costs two IMAD slots, as SURVEY 8d assumed" % (peak_imad_lo / 1e12),
         "dominant_kernel": {"name": "k_batch_add", "phase_ms": acc_ms, "share_of_step": acc_ms / phases["total"],
                             "pairs_per_step": int(tm["n_pairs"]), "field_mults_per_s": 6.0 * tm["n_pairs"] / (acc_ms * 1e-3)},
     }

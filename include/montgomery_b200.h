@@ -117,10 +117,13 @@ int mgb_combine_partials(mgb_ctx* ctx, const void* d_partials, int count,
  * op: 0 mul, 1 add, 2 sub, 3 inverse (Fermat), 4 square, 5 inverse (binary gcd), 6 negate. */
 int mgb_field_op(int device, int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n);
 
-/* Integer-pipe microbenchmarks (roofline denominator).  mode: 0 = mad.lo.u32, 1 = mad.hi.u32,
- * 2 = mad.wide.u32, 3 = mad.lo.cc/madc.hi.cc carry chain (IMAD.WIDE.U32.X), 4 = Fp377 Montgomery
- * multiplications, 5 = Fr377 multiplications.  Returns operations per second (ops = instructions x 32
- * lanes for modes 0-3, field multiplications for 4-5) in *ops_per_s and the kernel ms in *ms. */
+/* Integer-pipe microbenchmarks (roofline denominator).  mode: 0 = mad.lo.u32 (IMAD), 1 = mad.hi.u32,
+ * 2 = mad.wide.u32 with 64-bit accumulate, 3 = mad.lo.cc/madc.hi.cc carry chain (IMAD.WIDE.U32.X:
+ * the full 32x32+64->64 multiply-accumulate the field multiplication is made of), 4/5 = Fp377 /
+ * Fr377 Montgomery multiplications through the out-of-line call, 6/7 = the same inlined.  All
+ * multiplicands change every iteration (a loop-invariant product would be hoisted by ptxas).
+ * Returns operations per second (lane operations for modes 0-3, field multiplications for 4-7) in
+ * *ops_per_s and the kernel time in *ms. */
 int mgb_microbench(int device, int mode, int blocks_per_sm, int threads, int iters, double* ops_per_s, float* ms);
 
 const char* mgb_last_error(const mgb_ctx* ctx);   /* ctx may be NULL: last error of a ctx-less call */

@@ -136,6 +136,15 @@ struct Weierstrass {
     }
     return 0;
   }
+  // Fast path of add_prepare from the x coordinates alone: returns false (den untouched) when an
+  // operand is infinity or xA == xB, in which case the caller falls back to add_prepare.
+  MGB_DEV static bool prepare_x(const fe& xa, const fe& xb, fe& den) {
+    if ((xa.v[N - 1] | xb.v[N - 1]) & INF_BIT) return false;
+    fe d = F::sub(xb, xa);
+    if (F::is_zero(d)) return false;
+    den = d;
+    return true;
+  }
   MGB_DEV static affine add_finish(int kind, const affine& A, const affine& B, const fe& inv_den) {
     if (kind == 2) return A;
     if (kind == 3) return B;

@@ -82,6 +82,11 @@ struct WeierstrassPolicy {
     const uint32_t* e = V + (size_t)(slot >> 1) * V_LIMBS;
     vpoint r; r.x = ld_fe<FP>(e); r.y = ld_fe<FP>(e + N); return r;
   }
+  // x coordinate only (carries the infinity flag): all the first pass of a batched addition needs
+  MGB_DEV static Fe<FP> load_raw_x(const uint32_t* table, uint32_t ref) {
+    return ldg_fe<FP>(table + (size_t)(ref & REF_IDX) * ENTRY_LIMBS + ((ref & REF_ENDO) ? 2 * N : 0));
+  }
+  MGB_DEV static Fe<FP> load_v_x(const uint32_t* V, uint32_t slot) { return ld_fe<FP>(V + (size_t)(slot >> 1) * V_LIMBS); }
   MGB_DEV static void store_v(uint32_t* V, uint32_t slot, const vpoint& p) {
     uint32_t* e = V + (size_t)(slot >> 1) * V_LIMBS;
     st_fe<FP>(e, p.x); st_fe<FP>(e + N, p.y);
@@ -426,89 +431,97 @@ MGB_DEV void emit_next_round(bool valid, uint32_t s, int r, const uint32_t* __re
 }
 
 // ---------------------------------------------------------------- k_batch_add (Weierstrass)
-// Persistent blocks; each tile is T*E independent affine additions sharing ONE field inversion:
-// per-thread prefix products (E elements, kept in local memory), a product tree over the T thread
-// totals in shared memory, one binary-gcd inversion by thread 0 (ALU pipe; the other resident
-// blocks keep the multiplier busy meanwhile), tree down-sweep, per-thread back-substitution.
-// 6 multiplications per addition + 3/E for the tree.  Emits the pair list of the next round.
-template <class CV, int T, int E, int MINB>
-__global__ void __launch_bounds__(T, MINB) k_batch_add(const uint32_t* __restrict__ table, const uint32_t* __restrict__ refs,
-                                                       uint32_t* __restrict__ V, const uint32_t* __restrict__ pairs,
-                                                       const uint32_t* __restrict__ npairs_ptr, int r,
-                                                       const uint32_t* __restrict__ slot_bucket, const uint32_t* __restrict__ offs,
-                                                       uint32_t* __restrict__ pairs_out, uint32_t* __restrict__ npairs_out) {
+// Batched-affine additions with one field inversion per WARP tile of 32*E independent additions
+// (reference: batchAddNew / batchAddUnsafeNew, src/curve-affine.ts:376-522, and the Montgomery
+// trick of src/wasm/inverse.ts:220-271).  Warps are fully independent (no block barrier):
+//   1. every lane walks E pairs, loading only the x coordinates, and keeps the running product of
+//      the denominators; the prefix products go to a per-thread local array (L1/L2 resident);
+//   2. warp-wide inclusive prefix and suffix products of the 32 lane totals by shuffles;
+//   3. lane 0 inverts the grand total with the binary-gcd inverse (ALU pipe; the other warps of the
+//      SM keep the multiplier pipe busy meanwhile);
+//   4. every lane gets the inverse of its own total (2 multiplications), then walks its pairs
+//      backwards: recompute the denominator, peel off its inverse, finish the addition, store.
+// 6 multiplications per addition + 13/E for the warp products.  Emits the next round's pair list.
+template <class P>
+MGB_DEV Fe<P> shfl_fe(const Fe<P>& a, int src) {
+  Fe<P> r;
+  _Pragma("unroll") for (int i = 0; i < P::N; i++) r.v[i] = __shfl_sync(0xffffffffu, a.v[i], src);
+  return r;
+}
+
+template <class CV, int E, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_batch_add(const uint32_t* __restrict__ table, const uint32_t* __restrict__ refs,
+                                                         uint32_t* __restrict__ V, const uint32_t* __restrict__ pairs,
+                                                         const uint32_t* __restrict__ npairs_ptr, int r,
+                                                         const uint32_t* __restrict__ slot_bucket, const uint32_t* __restrict__ offs,
+                                                         uint32_t* __restrict__ pairs_out, uint32_t* __restrict__ npairs_out) {
   typedef typename CV::P FP;
   typedef typename CV::F F;
   typedef typename CV::G G;
   typedef Fe<FP> fe;
-  constexpr int N = CV::N;
-  extern __shared__ uint4 smem_raw[];
-  uint32_t* tree = reinterpret_cast<uint32_t*>(smem_raw);  // 2T field elements
   const uint32_t npairs = *npairs_ptr;
-  const uint32_t ntiles = (npairs + T * E - 1) / (T * E);
+  constexpr uint32_t TILE = 32 * E;
+  const uint32_t ntiles = (npairs + TILE - 1) / TILE;
   const uint32_t step = 1u << r;
-  const int tid = threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
 
-  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    fe den[E], pre[E];
-    uint32_t kinds[(E + 7) / 8];
-    _Pragma("unroll") for (int k = 0; k < (E + 7) / 8; k++) kinds[k] = 0;
+  for (uint32_t tile = gwarp; tile < ntiles; tile += nwarps) {
+    fe pre[E];
     fe run = F::one();
     _Pragma("unroll 1") for (int e = 0; e < E; e++) {
-      uint32_t idx = tile * (T * E) + e * T + tid;
-      int kind = 5;
+      uint32_t idx = tile * TILE + e * 32 + lane;
       fe d = F::one();
       if (idx < npairs) {
         uint32_t ent = pairs[idx];
         uint32_t s = ent & ~PAIR_RIGHT_RAW;
-        typename CV::vpoint A = (r == 0) ? CV::load_raw(table, refs[s]) : CV::load_v(V, s);
-        typename CV::vpoint B = (ent & PAIR_RIGHT_RAW) ? CV::load_raw(table, refs[s + step]) : CV::load_v(V, s + step);
-        kind = G::add_prepare(A, B, d);
+        uint32_t ra = (r == 0) ? refs[s] : 0u, rb = (ent & PAIR_RIGHT_RAW) ? refs[s + step] : 0u;
+        fe xa = (r == 0) ? CV::load_raw_x(table, ra) : CV::load_v_x(V, s);
+        fe xb = (ent & PAIR_RIGHT_RAW) ? CV::load_raw_x(table, rb) : CV::load_v_x(V, s + step);
+        if (!G::prepare_x(xa, xb, d)) {  // rare: an operand is infinity or the x coordinates coincide
+          typename CV::vpoint A = (r == 0) ? CV::load_raw(table, ra) : CV::load_v(V, s);
+          typename CV::vpoint B = (ent & PAIR_RIGHT_RAW) ? CV::load_raw(table, rb) : CV::load_v(V, s + step);
+          (void)G::add_prepare(A, B, d);
+        }
       }
-      _Pragma("unroll") for (int k = 0; k < (E + 7) / 8; k++) if (k == (e >> 3)) kinds[k] |= (uint32_t)kind << (4 * (e & 7));
       pre[e] = run;
-      den[e] = d;
       run = F::mul(run, d);
     }
-    st_fe<FP>(tree + (size_t)(T + tid) * N, run);
-    __syncthreads();
-    for (int w = T / 2; w >= 1; w >>= 1) {
-      if (tid < w) {
-        int k = w + tid;
-        fe a = ld_fe<FP>(tree + (size_t)(2 * k) * N), b = ld_fe<FP>(tree + (size_t)(2 * k + 1) * N);
-        st_fe<FP>(tree + (size_t)k * N, F::mul(a, b));
-      }
-      __syncthreads();
+    // warp products: pfx = c_0..c_lane, sfx = c_lane..c_31
+    fe pfx = run, sfx = run;
+    _Pragma("unroll 1") for (int dlt = 1; dlt < 32; dlt <<= 1) {
+      fe up = shfl_fe<FP>(pfx, lane - dlt < 0 ? lane : lane - dlt);
+      fe dn = shfl_fe<FP>(sfx, lane + dlt > 31 ? lane : lane + dlt);
+      fe np = F::mul(pfx, up), ns = F::mul(sfx, dn);
+      if (lane >= dlt) pfx = np;
+      if (lane + dlt <= 31) sfx = ns;
     }
-    if (tid == 0) st_fe<FP>(tree + N, F::inv_bgcd(ld_fe<FP>(tree + N)));
-    __syncthreads();
-    for (int w = 1; w < T; w <<= 1) {
-      if (tid < w) {
-        int k = w + tid;
-        fe ik = ld_fe<FP>(tree + (size_t)k * N);
-        fe a = ld_fe<FP>(tree + (size_t)(2 * k) * N), b = ld_fe<FP>(tree + (size_t)(2 * k + 1) * N);
-        st_fe<FP>(tree + (size_t)(2 * k) * N, F::mul(ik, b));
-        st_fe<FP>(tree + (size_t)(2 * k + 1) * N, F::mul(ik, a));
-      }
-      __syncthreads();
-    }
-    fe u = ld_fe<FP>(tree + (size_t)(T + tid) * N);  // inverse of this thread's total
-    __syncthreads();                                  // tree is reused by the next tile
+    fe total = shfl_fe<FP>(pfx, 31);
+    fe inv = total;
+    if (lane == 0) inv = F::inv_bgcd(total);
+    inv = shfl_fe<FP>(inv, 0);
+    fe left = shfl_fe<FP>(pfx, lane == 0 ? 0 : lane - 1);
+    fe right = shfl_fe<FP>(sfx, lane == 31 ? 31 : lane + 1);
+    fe u = inv;                                   // -> 1 / (this lane's total)
+    if (lane > 0) u = F::mul(u, left);
+    if (lane < 31) u = F::mul(u, right);
     _Pragma("unroll 1") for (int e = E - 1; e >= 0; e--) {
-      int kind = 0;
-      _Pragma("unroll") for (int k = 0; k < (E + 7) / 8; k++) if (k == (e >> 3)) kind = (kinds[k] >> (4 * (e & 7))) & 15;
-      fe inv_den = F::mul(u, pre[e]);
-      u = F::mul(u, den[e]);
+      uint32_t idx = tile * TILE + e * 32 + lane;
       uint32_t s = 0;
-      if (kind != 5) {
-        uint32_t idx = tile * (T * E) + e * T + tid;
+      bool valid = idx < npairs;
+      fe inv_den = F::mul(u, pre[e]);
+      if (valid) {
         uint32_t ent = pairs[idx];
         s = ent & ~PAIR_RIGHT_RAW;
         typename CV::vpoint A = (r == 0) ? CV::load_raw(table, refs[s]) : CV::load_v(V, s);
         typename CV::vpoint B = (ent & PAIR_RIGHT_RAW) ? CV::load_raw(table, refs[s + step]) : CV::load_v(V, s + step);
+        fe d;
+        int kind = G::add_prepare(A, B, d);
+        u = F::mul(u, d);
         CV::store_v(V, s, G::add_finish(kind, A, B, inv_den));
       }
-      emit_next_round(kind != 5, s, r, slot_bucket, offs, pairs_out, npairs_out);
+      emit_next_round(valid, s, r, slot_bucket, offs, pairs_out, npairs_out);
     }
   }
 }

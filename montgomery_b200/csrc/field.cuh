@@ -16,6 +16,16 @@
 
 namespace mgb {
 
+// -p^-1 mod 2^32 (= 2^32 - 1 for every supported prime) as a RUNTIME value: if ptxas can see that the
+// Montgomery quotient digit is a plain negation it folds the sign into the modulus immediates and
+// splits every modulus product into IMAD.X + IMAD.HI.U32.X (6 issue cycles on the multiplier pipe)
+// instead of one IMAD.WIDE.U32.X (4 cycles) -- measured +24% on the whole multiplication.
+#ifdef MGB_HOST_EMU
+static const uint32_t c_mgb_minv = 0xffffffffu;
+#else
+static __device__ __constant__ uint32_t c_mgb_minv = 0xffffffffu;
+#endif
+
 template <class P>
 struct Fe {
   uint32_t v[P::N];
@@ -110,7 +120,7 @@ struct Field {
         }
         O[N - 1] = ptx::addc(O[N - 1], 0);
       }
-      const uint32_t m = 0u - E[0];
+      const uint32_t m = E[0] * c_mgb_minv;
       _Pragma("unroll") for (int j = 0; j < N; j += 2) {
         O[j] = (j == 0) ? ptx::mad_lo_cc(P::mod(j + 1), m, O[j]) : ptx::madc_lo_cc(P::mod(j + 1), m, O[j]);
         O[j + 1] = ptx::madc_hi_cc(P::mod(j + 1), m, O[j + 1]);

@@ -198,8 +198,8 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
     uint32_t* pin = (uint32_t*)((r & 1) ? ctx->pairs2.p : ctx->pairs.p);
     uint32_t* pout = (uint32_t*)((r & 1) ? ctx->pairs.p : ctx->pairs2.p);
     if constexpr (CV::BATCH_AFFINE) {
-      constexpr int T = 128, E = 16, MINB = 4;
-      k_batch_add<CV, T, E, MINB><<<ctx->sm_count * MINB, T, 2 * T * CV::N * 4, st>>>(
+      constexpr int E = 32, MINB = 4;
+      k_batch_add<CV, E, MINB><<<ctx->sm_count * MINB, 128, 0, st>>>(
           (const uint32_t*)ctx->table.p, (const uint32_t*)ctx->refs.p, (uint32_t*)ctx->V.p, pin, misc + 2 + r, r,
           (const uint32_t*)ctx->slot_bucket.p, (const uint32_t*)ctx->offs.p, pout, misc + 3 + r);
     } else {

@@ -53,6 +53,8 @@ __global__ void __launch_bounds__(1024) k_imad(uint32_t* out, uint32_t seed, int
     for (int k = 0; k < 8; k++) s ^= x[k];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
   } else if (MODE == 2) {
+    // 32x32+64->64 with the multiplicand taken from the accumulator itself, so ptxas cannot hoist
+    // the product out of the loop (a loop-invariant product turns into plain 64-bit adds).
     uint64_t x[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) x[k] = a + k;
@@ -61,7 +63,7 @@ __global__ void __launch_bounds__(1024) k_imad(uint32_t* out, uint32_t seed, int
 #pragma unroll
       for (int u = 0; u < 16; u++) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) asm volatile("mad.wide.u32 %0,%1,%2,%0;" : "+l"(x[k]) : "r"(a), "r"(b));
+        for (int k = 0; k < 8; k++) { uint32_t m = (uint32_t)x[k]; asm volatile("mad.wide.u32 %0,%1,%2,%0;" : "+l"(x[k]) : "r"(m), "r"(b)); }
       }
     }
     uint64_t s = 0;
@@ -69,7 +71,8 @@ __global__ void __launch_bounds__(1024) k_imad(uint32_t* out, uint32_t seed, int
     for (int k = 0; k < 8; k++) s ^= x[k];
     out[blockIdx.x * blockDim.x + threadIdx.x] = (uint32_t)(s ^ (s >> 32));
   } else {
-    // carry chain: 8 aligned pairs, one IMAD.WIDE.U32.X each, carry rippling through
+    // carry chain: 8 aligned pairs, one IMAD.WIDE.U32.X each, carry rippling through; the
+    // multiplicand of pair k is the (changing) low word of pair k+1
     uint32_t x[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) x[k] = a + k;
@@ -77,12 +80,12 @@ __global__ void __launch_bounds__(1024) k_imad(uint32_t* out, uint32_t seed, int
     for (int it = 0; it < iters; it++) {
 #pragma unroll
       for (int u = 0; u < 16; u++) {
-        x[0] = ptx::mad_lo_cc(a, b, x[0]);
-        x[1] = ptx::madc_hi_cc(a, b, x[1]);
+        x[0] = ptx::mad_lo_cc(x[2], b, x[0]);
+        x[1] = ptx::madc_hi_cc(x[2], b, x[1]);
 #pragma unroll
         for (int k = 2; k < 16; k += 2) {
-          x[k] = ptx::madc_lo_cc(a, b, x[k]);
-          x[k + 1] = ptx::madc_hi_cc(a, b, x[k + 1]);
+          x[k] = ptx::madc_lo_cc(x[(k + 2) & 15], b, x[k]);
+          x[k + 1] = ptx::madc_hi_cc(x[(k + 2) & 15], b, x[k + 1]);
         }
       }
     }
