@@ -114,7 +114,8 @@ int mgb_combine_partials(mgb_ctx* ctx, const void* d_partials, int count,
 /* Test hooks for the field layer (the analogue of the Wasm exports checked by src/field.test.ts):
  * applies op elementwise on the device to n elements given as canonical LE bytes in/out.
  * field: 0 = BLS12-377 Fp, 1 = BLS12-377 Fr (= ed-on-377 base field), 2 = Pallas Fp.
- * op: 0 mul, 1 add, 2 sub, 3 inverse (Fermat), 4 square, 5 inverse (binary gcd), 6 negate. */
+ * op: 0 mul, 1 add, 2 sub, 3 inverse (Fermat), 4 square, 5 inverse (binary gcd), 6 negate,
+ * 7 inverse (division steps, the one the MSM uses). */
 int mgb_field_op(int device, int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n);
 
 /* Integer-pipe microbenchmarks (roofline denominator).  mode: 0 = mad.lo.u32 (IMAD), 1 = mad.hi.u32,

@@ -114,7 +114,7 @@ struct Weierstrass {
   // x = X/ZZ, y = Y/ZZZ with one inversion: t = 1/ZZZ, 1/ZZ = t^2 * ZZ^2
   MGB_DEV static affine to_affine(const acc& p) {
     if (acc_is_zero(p)) return affine_inf();
-    fe t = F::inv_bgcd(p.ZZZ);
+    fe t = F::inv_divsteps(p.ZZZ);
     fe izz = F::mul(F::sqr(t), F::sqr(p.ZZ));
     affine r;
     r.x = F::mul(p.X, izz);
@@ -222,7 +222,7 @@ struct TwistedEdwards {
   }
   // -> canonical affine (x, y); Z != 0 for every point of the odd-order subgroup times cofactor 4 group
   MGB_DEV static void to_affine(const acc& p, fe& x, fe& y) {
-    fe zi = F::inv_bgcd(p.Z);
+    fe zi = F::inv_divsteps(p.Z);
     x = F::mul(p.X, zi);
     y = F::mul(p.Y, zi);
   }

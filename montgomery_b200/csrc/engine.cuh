@@ -437,7 +437,7 @@ MGB_DEV void emit_next_round(bool valid, uint32_t s, int r, const uint32_t* __re
 //   1. every lane walks E pairs, loading only the x coordinates, and keeps the running product of
 //      the denominators; the prefix products go to a per-thread local array (L1/L2 resident);
 //   2. warp-wide inclusive prefix and suffix products of the 32 lane totals by shuffles;
-//   3. lane 0 inverts the grand total with the binary-gcd inverse (ALU pipe; the other warps of the
+//   3. lane 0 inverts the grand total with the division-step inverse (the other warps of the
 //      SM keep the multiplier pipe busy meanwhile);
 //   4. every lane gets the inverse of its own total (2 multiplications), then walks its pairs
 //      backwards: recompute the denominator, peel off its inverse, finish the addition, store.
@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(128, MINB) k_batch_add(const uint32_t* __restr
     }
     fe total = shfl_fe<FP>(pfx, 31);
     fe inv = total;
-    if (lane == 0) inv = F::inv_bgcd(total);
+    if (lane == 0) inv = F::inv_divsteps(total);
     inv = shfl_fe<FP>(inv, 0);
     fe left = shfl_fe<FP>(pfx, lane == 0 ? 0 : lane - 1);
     fe right = shfl_fe<FP>(sfx, lane == 31 ? 31 : lane + 1);

@@ -9,6 +9,7 @@
 // headers with g++ to check formulas without a GPU).  Never part of the shipped library.
 #define MGB_DEV inline
 #define MGB_NOINLINE_DEV inline
+#define MGB_CTZ(x) __builtin_ctz(x)
 #ifndef __CUDACC__
 #define __host__
 #define __device__
@@ -37,6 +38,7 @@ inline uint32_t subc(uint32_t a, uint32_t b) { return sub3(a, b, CF, false); }
 #else
 #define MGB_DEV __device__ __forceinline__
 #define MGB_NOINLINE_DEV __device__ __noinline__
+#define MGB_CTZ(x) (__ffs((int)(x)) - 1)
 
 namespace mgb {
 namespace ptx {

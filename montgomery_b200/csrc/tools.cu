@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(128) k_field_op(int op, uint32_t n, const uint
     case 4: r = F::sqr(x); break;
     case 5: r = F::inv_bgcd(x); break;
     case 6: r = F::neg(x); break;
+    case 7: r = F::inv_divsteps(x); break;
     default: r = F::zero();
   }
   st_fe<P>(out + (size_t)i * P::N, F::from_mont(r));

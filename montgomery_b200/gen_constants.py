@@ -35,6 +35,12 @@ def field_struct(name, p, n):
     out += carr("r2", R * R % p, n)       # to-Montgomery multiplier
     out += carr("r3", R * R * R % p, n)   # fixes up the plain binary inverse: mont(x, r3) = x*R^2
     out += carr("pm2", p - 2, n)          # Fermat exponent
+    n30 = (p.bit_length() + 1 + 29) // 30 + (1 if (p.bit_length() + 1) % 30 == 0 else 0)
+    n30 = max(n30, (32 * n + 29) // 30)   # must also hold any packed 32n-bit value
+    assert p % (1 << 30) == 1             # modulus^-1 mod 2^30 = 1 (used by the divsteps inverse)
+    body = ",".join("0x%08x" % ((p >> (30 * i)) & 0x3FFFFFFF) for i in range(n30))
+    out += "  static constexpr int N30 = %d;  // signed 30-bit limbs of the divsteps inverse\n" % n30
+    out += ("  __host__ __device__ static constexpr int32_t mod30(int i) { constexpr int32_t t[%d] = {%s}; return t[i]; }\n" % (n30, body))
     out += "};\n\n"
     return out
 

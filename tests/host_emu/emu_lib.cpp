@@ -22,6 +22,7 @@ template <class P> static void fe_op(int op, uint32_t* out, const uint32_t* a, c
     case 6: r = F::sqr(x); break;
     case 7: r = F::neg(x); break;
     case 8: r = F::inv_bgcd(x); break;
+    case 9: r = F::inv_divsteps(x); break;
     default: r = F::zero();
   }
   st<P>(out, r);

@@ -40,3 +40,5 @@ def test_field_ops_gpu(fid):
     inv_exp = [pow(x, -1, p) if x else 0 for x in a[:512]]
     assert _run(lib, fid, 3, a[:512], b[:512], n) == inv_exp     # Fermat
     assert _run(lib, fid, 5, a[:512], b[:512], n) == inv_exp     # binary gcd
+    inv_all = [pow(x, -1, p) if x else 0 for x in a]
+    assert _run(lib, fid, 7, a, b, n) == inv_all                  # division steps (used by the MSM)

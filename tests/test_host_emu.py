@@ -52,13 +52,18 @@ def test_field_ops(emu, fid):
     for it in range(20):
         a = [1, 2, p - 1, R % p][it] if it < 4 else rnd.randrange(1, p)
         exp = pow(a * Ri, -1, p) * R % p
-        for op in (3, 8):  # Fermat and binary-gcd inverses (src/field.test.ts: inverse, batchInverse)
+        for op in (3, 8, 9):  # Fermat, binary-gcd and division-step inverses (src/field.test.ts: inverse)
             if op == 3 and it >= 6:
                 continue
             emu.emu_fe_op(fid, op, out, L([a], n), L([0], n))
             assert I(out, n, 1)[0] == exp
-    emu.emu_fe_op(fid, 8, out, L([0], n), L([0], n))
-    assert I(out, n, 1)[0] == 0
+    for it in range(400):   # the division-step inverse is the one on the hot path: more cases
+        a = rnd.randrange(1, p)
+        emu.emu_fe_op(fid, 9, out, L([a], n), L([0], n))
+        assert I(out, n, 1)[0] == pow(a * Ri, -1, p) * R % p
+    for op in (8, 9):
+        emu.emu_fe_op(fid, op, out, L([0], n), L([0], n))
+        assert I(out, n, 1)[0] == 0
 
 
 @pytest.mark.parametrize("cid,prm,n", [(0, BLS12_377, 12), (1, PALLAS, 8)], ids=["bls12-377", "pallas"])
