@@ -145,6 +145,8 @@ struct Weierstrass {
     den = d;
     return true;
   }
+  // INL = true inlines the three multiplications (hot batched-addition loop: no call marshalling)
+  template <bool INL = false>
   MGB_DEV static affine add_finish(int kind, const affine& A, const affine& B, const fe& inv_den) {
     if (kind == 2) return A;
     if (kind == 3) return B;
@@ -152,10 +154,12 @@ struct Weierstrass {
     fe num;
     if (kind == 1) { fe xx = F::sqr(A.x); num = F::add(F::dbl(xx), xx); }
     else num = F::sub(B.y, A.y);
-    fe m = F::mul(num, inv_den);
+    fe m = INL ? F::mul_inl(num, inv_den) : F::mul(num, inv_den);
     affine r;
-    r.x = F::sub(F::sub(F::sqr(m), A.x), B.x);   // kind 1: B == A, so this is m^2 - 2x
-    r.y = F::sub(F::mul(m, F::sub(A.x, r.x)), A.y);
+    fe mm = INL ? F::mul_inl(m, m) : F::sqr(m);
+    r.x = F::sub(F::sub(mm, A.x), B.x);   // kind 1: B == A, so this is m^2 - 2x
+    fe t = F::sub(A.x, r.x);
+    r.y = F::sub(INL ? F::mul_inl(m, t) : F::mul(m, t), A.y);
     return r;
   }
 };

@@ -48,7 +48,6 @@ static constexpr uint32_t REF_NEG = 0x80000000u;
 static constexpr uint32_t REF_ENDO = 0x40000000u;
 static constexpr uint32_t REF_IDX = 0x3fffffffu;
 static constexpr uint32_t NO_BUCKET = 0xffffffffu;
-static constexpr uint32_t PAIR_RIGHT_RAW = 0x80000000u;
 
 // ---------------------------------------------------------------- curve policies
 template <class FP, class CC, class GL>
@@ -70,32 +69,29 @@ struct WeierstrassPolicy {
   static constexpr int ACC_LIMBS = 4 * N;
   static constexpr int COORD_BYTES = 4 * N;
 
-  MGB_DEV static vpoint load_raw(const uint32_t* table, uint32_t ref) {
-    const uint32_t* e = table + (size_t)(ref & REF_IDX) * ENTRY_LIMBS;
+  // table entry -> the point a sorted slot stands for (endomorphism / negation applied)
+  MGB_DEV static vpoint load_entry(const uint32_t* table, uint32_t idx, bool endo, bool negate) {
+    const uint32_t* e = table + (size_t)idx * ENTRY_LIMBS;
     vpoint r;
-    r.x = ldg_fe<FP>(e + ((ref & REF_ENDO) ? 2 * N : 0));
+    r.x = ldg_fe<FP>(e + (endo ? 2 * N : 0));
     r.y = ldg_fe<FP>(e + N);
-    if (ref & REF_NEG) r.y = F::neg(r.y);
+    if (negate) r.y = F::neg(r.y);
     return r;
   }
   MGB_DEV static vpoint load_v(const uint32_t* V, uint32_t slot) {
-    const uint32_t* e = V + (size_t)(slot >> 1) * V_LIMBS;
+    const uint32_t* e = V + (size_t)slot * V_LIMBS;
     vpoint r; r.x = ld_fe<FP>(e); r.y = ld_fe<FP>(e + N); return r;
   }
   // x coordinate only (carries the infinity flag): all the first pass of a batched addition needs
-  MGB_DEV static Fe<FP> load_raw_x(const uint32_t* table, uint32_t ref) {
-    return ldg_fe<FP>(table + (size_t)(ref & REF_IDX) * ENTRY_LIMBS + ((ref & REF_ENDO) ? 2 * N : 0));
-  }
-  MGB_DEV static Fe<FP> load_v_x(const uint32_t* V, uint32_t slot) { return ld_fe<FP>(V + (size_t)(slot >> 1) * V_LIMBS); }
+  MGB_DEV static Fe<FP> load_v_x(const uint32_t* V, uint32_t slot) { return ld_fe<FP>(V + (size_t)slot * V_LIMBS); }
   MGB_DEV static void store_v(uint32_t* V, uint32_t slot, const vpoint& p) {
-    uint32_t* e = V + (size_t)(slot >> 1) * V_LIMBS;
+    uint32_t* e = V + (size_t)slot * V_LIMBS;
     st_fe<FP>(e, p.x); st_fe<FP>(e + N, p.y);
   }
   MGB_DEV static acc acc_zero() { return G::acc_zero(); }
   MGB_DEV static acc add(const acc& a, const acc& b) { return G::add(a, b); }
   MGB_DEV static acc dbl(const acc& a) { return G::dbl(a); }
   MGB_DEV static acc add_v(const acc& a, const vpoint& p) { return G::madd(a, p); }
-  MGB_DEV static acc add_raw(const acc& a, const vpoint& p) { return G::madd(a, p); }
   MGB_DEV static acc ld_acc(const uint32_t* p) { acc r; r.X = ld_fe<FP>(p); r.Y = ld_fe<FP>(p + N); r.ZZ = ld_fe<FP>(p + 2 * N); r.ZZZ = ld_fe<FP>(p + 3 * N); return r; }
   MGB_DEV static void st_acc(uint32_t* p, const acc& a) { st_fe<FP>(p, a.X); st_fe<FP>(p + N, a.Y); st_fe<FP>(p + 2 * N, a.ZZ); st_fe<FP>(p + 3 * N, a.ZZZ); }
   MGB_DEV static acc generator() {
@@ -137,42 +133,40 @@ struct TwistedEdwardsPolicy {
   typedef TwistedEdwards<FP, CC> G;
   typedef typename G::acc acc;
   typedef typename G::acc vpoint;
-  typedef typename G::affine raw;
   static constexpr int N = FP::N;
   static constexpr bool USE_GLV = false;
   static constexpr bool BATCH_AFFINE = false;
   static constexpr int HALVES = 1;
   static constexpr int MAG_LIMBS = 8;
   static constexpr int MAG_BITS = CC::SCALAR_BITS + 1;
-  static constexpr int ENTRY_LIMBS = 3 * N;  // x | y | 2d*x*y
+  static constexpr int ENTRY_LIMBS = 3 * N;  // x | y | t = x*y
   static constexpr int V_LIMBS = 4 * N;
   static constexpr int ACC_LIMBS = 4 * N;
   static constexpr int COORD_BYTES = 4 * N;
 
-  MGB_DEV static raw load_raw(const uint32_t* table, uint32_t ref) {
-    const uint32_t* e = table + (size_t)(ref & REF_IDX) * ENTRY_LIMBS;
-    raw r; r.x = ldg_fe<FP>(e); r.y = ldg_fe<FP>(e + N); r.kt = ldg_fe<FP>(e + 2 * N);
-    if (ref & REF_NEG) { r.x = F::neg(r.x); r.kt = F::neg(r.kt); }
+  // table entry (x, y, t = x*y) -> extended point with Z = 1 (negation: -x, -t)
+  MGB_DEV static vpoint load_entry(const uint32_t* table, uint32_t idx, bool /*endo*/, bool negate) {
+    const uint32_t* e = table + (size_t)idx * ENTRY_LIMBS;
+    vpoint r; r.X = ldg_fe<FP>(e); r.Y = ldg_fe<FP>(e + N); r.Z = F::one(); r.T = ldg_fe<FP>(e + 2 * N);
+    if (negate) { r.X = F::neg(r.X); r.T = F::neg(r.T); }
     return r;
   }
-  MGB_DEV static vpoint load_v(const uint32_t* V, uint32_t slot) { return ld_acc(V + (size_t)(slot >> 1) * V_LIMBS); }
-  MGB_DEV static void store_v(uint32_t* V, uint32_t slot, const vpoint& p) { st_acc(V + (size_t)(slot >> 1) * V_LIMBS, p); }
+  MGB_DEV static vpoint load_v(const uint32_t* V, uint32_t slot) { return ld_acc(V + (size_t)slot * V_LIMBS); }
+  MGB_DEV static void store_v(uint32_t* V, uint32_t slot, const vpoint& p) { st_acc(V + (size_t)slot * V_LIMBS, p); }
   MGB_DEV static acc acc_zero() { return G::acc_zero(); }
   MGB_DEV static acc add(const acc& a, const acc& b) { return G::add(a, b); }
   MGB_DEV static acc dbl(const acc& a) { return G::dbl(a); }
   MGB_DEV static acc add_v(const acc& a, const vpoint& p) { return G::add(a, p); }
-  MGB_DEV static acc add_raw(const acc& a, const raw& p) { return G::madd(a, p); }
   MGB_DEV static acc ld_acc(const uint32_t* p) { acc r; r.X = ld_fe<FP>(p); r.Y = ld_fe<FP>(p + N); r.Z = ld_fe<FP>(p + 2 * N); r.T = ld_fe<FP>(p + 3 * N); return r; }
   MGB_DEV static void st_acc(uint32_t* p, const acc& a) { st_fe<FP>(p, a.X); st_fe<FP>(p + N, a.Y); st_fe<FP>(p + 2 * N, a.Z); st_fe<FP>(p + 3 * N, a.T); }
   MGB_DEV static acc generator() {
-    raw g; _Pragma("unroll") for (int i = 0; i < N; i++) { g.x.v[i] = CC::gx(i); g.y.v[i] = CC::gy(i); }
+    typename G::affine g; _Pragma("unroll") for (int i = 0; i < N; i++) { g.x.v[i] = CC::gx(i); g.y.v[i] = CC::gy(i); }
     return G::from_affine(g);
   }
   MGB_DEV static void make_entry(uint32_t* e, const Fe<FP>& x_plain, const Fe<FP>& y_plain, bool inf) {
     Fe<FP> x = F::to_mont(x_plain), y = F::to_mont(y_plain);
     if (inf) { x = F::zero(); y = F::one(); }
-    Fe<FP> kt = F::mul(F::mul(x, y), G::k2d());
-    st_fe<FP>(e, x); st_fe<FP>(e + N, y); st_fe<FP>(e + 2 * N, kt);
+    st_fe<FP>(e, x); st_fe<FP>(e + N, y); st_fe<FP>(e + 2 * N, F::mul(x, y));
   }
   MGB_DEV static void make_entry_from_acc(uint32_t* e, const acc& a) {
     Fe<FP> x, y; G::to_affine(a, x, y);
@@ -372,62 +366,60 @@ static __global__ void __launch_bounds__(SCAN_T) k_scan_add(uint32_t* __restrict
 }
 
 // ---------------------------------------------------------------- k_scatter
-// refs[slot] = point reference, slot_bucket[slot] = bucket, slot = offs[bucket] + rank.
-// Also emits the pair list of round 0 of the bucket tree: a slot with even rank whose right
-// neighbour is inside the bucket absorbs that neighbour (order of the list is irrelevant).
-MGB_DEV void emit_pair(bool active, uint32_t entry, uint32_t* __restrict__ pairs, uint32_t* __restrict__ npairs) {
+// Counting-sort scatter that MATERIALISES the points in bucket order, like the reference's
+// sortPoints (msm-batched-affine.ts:456-502): V[slot] = the point entry (endomorphism / negation
+// applied), slot = offs[bucket] + rank.  Consecutive threads read consecutive table entries
+// (coalesced); the 96-byte writes are scattered.  All later stages then address V by slot only.
+//
+// The in-place bucket tree (msm-batched-affine.ts:243-263): in round r the element at local index j
+// (multiple of 2^(r+1)) absorbs the element at j + 2^r if that is inside the bucket of size n.  The
+// rounds in which a slot is a left operand are r = 0 .. life-1 with
+//     life = min(ctz(j), floor(log2(n - j - 1)) + 1)        (0 if j is the last element),
+// so each pair-list entry carries (slot, life) and no bucket lookup is needed later.
+struct PairEnt {
+  uint32_t slot;
+  uint32_t life;
+};
+
+MGB_DEV void emit_pair(bool active, PairEnt ent, PairEnt* __restrict__ pairs, uint32_t* __restrict__ npairs) {
   uint32_t m = __ballot_sync(0xffffffffu, active);
   if (m) {
     int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
     uint32_t base = 0;
     if (lane == leader) base = atomicAdd(npairs, (uint32_t)__popc(m));
     base = __shfl_sync(0xffffffffu, base, leader);
-    if (active) pairs[base + __popc(m & ((1u << lane) - 1))] = entry;
+    if (active) pairs[base + __popc(m & ((1u << lane) - 1))] = ent;
   }
 }
 
 template <class CV>
 __global__ void __launch_bounds__(256) k_scatter(MsmParams pr, const uint32_t* __restrict__ ent_bucket, const uint32_t* __restrict__ ent_rank,
-                                                 const uint32_t* __restrict__ offs, uint32_t* __restrict__ refs, uint32_t* __restrict__ slot_bucket,
-                                                 uint32_t* __restrict__ pairs, uint32_t* __restrict__ npairs) {
+                                                 const uint32_t* __restrict__ offs, const uint32_t* __restrict__ table, uint32_t* __restrict__ V,
+                                                 PairEnt* __restrict__ pairs, uint32_t* __restrict__ npairs) {
   size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool active = false;
-  uint32_t slot = 0;
+  PairEnt ent = {0u, 0u};
   if (pos < pr.nent) {
     uint32_t b = ent_bucket[pos];
     if (b != NO_BUCKET) {
       uint32_t rk = ent_rank[pos];
       uint32_t e = (uint32_t)(pos / pr.n), i = (uint32_t)(pos - (size_t)e * pr.n);
-      uint32_t ref = i | (rk & REF_NEG);
-      if (CV::HALVES == 2 && e >= (uint32_t)pr.K) ref |= REF_ENDO;
+      const bool endo = (CV::HALVES == 2) && e >= (uint32_t)pr.K;
       uint32_t o = offs[b], n = offs[b + 1] - o, j = rk & ~REF_NEG;
-      slot = o + j;
-      refs[slot] = ref;
-      slot_bucket[slot] = b;
-      active = ((j & 1) == 0) && (j + 1 < n);
+      uint32_t slot = o + j;
+      CV::store_v(V, slot, CV::load_entry(table, i, endo, (rk & REF_NEG) != 0));
+      uint32_t rest = n - j - 1;                          // elements after this one
+      uint32_t life = 0;
+      if (rest) {
+        life = 32 - __clz(rest);                          // floor(log2(rest)) + 1
+        if (j) life = min(life, (uint32_t)(__ffs(j) - 1));
+      }
+      ent.slot = slot;
+      ent.life = life;
+      active = life > 0;
     }
   }
-  emit_pair(active, slot | PAIR_RIGHT_RAW, pairs, npairs);
-}
-
-// After round r, the element at local index j (multiple of 2^(r+1)) is a left operand of round r+1
-// iff j is a multiple of 2^(r+2) and j + 2^(r+1) is inside the bucket (reference:
-// msm-batched-affine.ts:243-263).  Left operands of round r+1 are a subset of those of round r, so
-// each add kernel emits the next round's list itself.
-MGB_DEV void emit_next_round(bool valid, uint32_t s, int r, const uint32_t* __restrict__ slot_bucket, const uint32_t* __restrict__ offs,
-                             uint32_t* __restrict__ pairs_out, uint32_t* __restrict__ npairs_out) {
-  bool active = false;
-  uint32_t entry = 0;
-  if (valid) {
-    uint32_t b = slot_bucket[s];
-    uint32_t o = offs[b], n = offs[b + 1] - o, j = s - o;
-    uint32_t step = 2u << r;
-    if ((j & (2 * step - 1)) == 0 && j + step < n) {
-      active = true;
-      entry = s | ((j + step + 1 >= n) ? PAIR_RIGHT_RAW : 0u);  // right operand never had a partner: still a raw reference
-    }
-  }
-  emit_pair(active, entry, pairs_out, npairs_out);
+  emit_pair(active, ent, pairs, npairs);
 }
 
 // ---------------------------------------------------------------- k_batch_add (Weierstrass)
@@ -449,12 +441,17 @@ MGB_DEV Fe<P> shfl_fe(const Fe<P>& a, int src) {
   return r;
 }
 
-template <class CV, int E, int MINB>
-__global__ void __launch_bounds__(128, MINB) k_batch_add(const uint32_t* __restrict__ table, const uint32_t* __restrict__ refs,
-                                                         uint32_t* __restrict__ V, const uint32_t* __restrict__ pairs,
+template <class CV>
+MGB_DEV void prefetch_point(const uint32_t* V, uint32_t slot) {
+  const char* p = reinterpret_cast<const char*>(V + (size_t)slot * CV::V_LIMBS);
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p + CV::V_LIMBS * 4 - 4));
+}
+
+template <class CV, int E, int MINB, bool INL>
+__global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ V, const PairEnt* __restrict__ pairs,
                                                          const uint32_t* __restrict__ npairs_ptr, int r,
-                                                         const uint32_t* __restrict__ slot_bucket, const uint32_t* __restrict__ offs,
-                                                         uint32_t* __restrict__ pairs_out, uint32_t* __restrict__ npairs_out) {
+                                                         PairEnt* __restrict__ pairs_out, uint32_t* __restrict__ npairs_out) {
   typedef typename CV::P FP;
   typedef typename CV::F F;
   typedef typename CV::G G;
@@ -470,23 +467,28 @@ __global__ void __launch_bounds__(128, MINB) k_batch_add(const uint32_t* __restr
   for (uint32_t tile = gwarp; tile < ntiles; tile += nwarps) {
     fe pre[E];
     fe run = F::one();
+    // software pipeline: slot indices two pairs ahead, x coordinates one pair ahead, so the loads of
+    // pair e+1 are in flight during the multiplication of pair e
+    const uint32_t base = tile * TILE + lane;
+    uint32_t s1 = (base < npairs) ? pairs[base].slot : NO_BUCKET;
+    uint32_t s2 = (base + 32 < npairs) ? pairs[base + 32].slot : NO_BUCKET;
+    fe xa_n = F::zero(), xb_n = F::zero();
+    if (s1 != NO_BUCKET) { xa_n = CV::load_v_x(V, s1); xb_n = CV::load_v_x(V, s1 + step); }
     _Pragma("unroll 1") for (int e = 0; e < E; e++) {
-      uint32_t idx = tile * TILE + e * 32 + lane;
+      const uint32_t s = s1;
+      const fe xa = xa_n, xb = xb_n;
+      s1 = s2;
+      s2 = (e + 2 < E && base + (e + 2) * 32 < npairs) ? pairs[base + (e + 2) * 32].slot : NO_BUCKET;
+      if (s1 != NO_BUCKET) { xa_n = CV::load_v_x(V, s1); xb_n = CV::load_v_x(V, s1 + step); }
       fe d = F::one();
-      if (idx < npairs) {
-        uint32_t ent = pairs[idx];
-        uint32_t s = ent & ~PAIR_RIGHT_RAW;
-        uint32_t ra = (r == 0) ? refs[s] : 0u, rb = (ent & PAIR_RIGHT_RAW) ? refs[s + step] : 0u;
-        fe xa = (r == 0) ? CV::load_raw_x(table, ra) : CV::load_v_x(V, s);
-        fe xb = (ent & PAIR_RIGHT_RAW) ? CV::load_raw_x(table, rb) : CV::load_v_x(V, s + step);
+      if (s != NO_BUCKET) {
         if (!G::prepare_x(xa, xb, d)) {  // rare: an operand is infinity or the x coordinates coincide
-          typename CV::vpoint A = (r == 0) ? CV::load_raw(table, ra) : CV::load_v(V, s);
-          typename CV::vpoint B = (ent & PAIR_RIGHT_RAW) ? CV::load_raw(table, rb) : CV::load_v(V, s + step);
+          typename CV::vpoint A = CV::load_v(V, s), B = CV::load_v(V, s + step);
           (void)G::add_prepare(A, B, d);
         }
       }
       pre[e] = run;
-      run = F::mul(run, d);
+      run = INL ? F::mul_inl(run, d) : F::mul(run, d);
     }
     // warp products: pfx = c_0..c_lane, sfx = c_lane..c_31
     fe pfx = run, sfx = run;
@@ -506,53 +508,46 @@ __global__ void __launch_bounds__(128, MINB) k_batch_add(const uint32_t* __restr
     fe u = inv;                                   // -> 1 / (this lane's total)
     if (lane > 0) u = F::mul(u, left);
     if (lane < 31) u = F::mul(u, right);
+    PairEnt nxt = {NO_BUCKET, 0u};
+    if (base + (E - 1) * 32 < npairs) nxt = pairs[base + (E - 1) * 32];
     _Pragma("unroll 1") for (int e = E - 1; e >= 0; e--) {
-      uint32_t idx = tile * TILE + e * 32 + lane;
-      uint32_t s = 0;
-      bool valid = idx < npairs;
-      fe inv_den = F::mul(u, pre[e]);
+      const PairEnt ent = nxt;
+      const bool valid = ent.slot != NO_BUCKET;
+      nxt.slot = NO_BUCKET;
+      if (e > 0 && base + (e - 1) * 32 < npairs) {
+        nxt = pairs[base + (e - 1) * 32];
+        prefetch_point<CV>(V, nxt.slot);           // next pair's operands -> L1 while this pair is computed
+        prefetch_point<CV>(V, nxt.slot + step);
+      }
+      fe inv_den = INL ? F::mul_inl(u, pre[e]) : F::mul(u, pre[e]);
       if (valid) {
-        uint32_t ent = pairs[idx];
-        s = ent & ~PAIR_RIGHT_RAW;
-        typename CV::vpoint A = (r == 0) ? CV::load_raw(table, refs[s]) : CV::load_v(V, s);
-        typename CV::vpoint B = (ent & PAIR_RIGHT_RAW) ? CV::load_raw(table, refs[s + step]) : CV::load_v(V, s + step);
+        typename CV::vpoint A = CV::load_v(V, ent.slot), B = CV::load_v(V, ent.slot + step);
         fe d;
         int kind = G::add_prepare(A, B, d);
-        u = F::mul(u, d);
-        CV::store_v(V, s, G::add_finish(kind, A, B, inv_den));
+        u = INL ? F::mul_inl(u, d) : F::mul(u, d);
+        CV::store_v(V, ent.slot, G::template add_finish<INL>(kind, A, B, inv_den));
       }
-      emit_next_round(valid, s, r, slot_bucket, offs, pairs_out, npairs_out);
+      emit_pair(valid && (uint32_t)(r + 1) < ent.life, ent, pairs_out, npairs_out);
     }
   }
 }
 
 // ---------------------------------------------------------------- k_pair_add (twisted Edwards: no inversion needed)
 template <class CV>
-__global__ void __launch_bounds__(256) k_pair_add(const uint32_t* __restrict__ table, const uint32_t* __restrict__ refs,
-                                                  uint32_t* __restrict__ V, const uint32_t* __restrict__ pairs,
+__global__ void __launch_bounds__(256) k_pair_add(uint32_t* __restrict__ V, const PairEnt* __restrict__ pairs,
                                                   const uint32_t* __restrict__ npairs_ptr, int r,
-                                                  const uint32_t* __restrict__ slot_bucket, const uint32_t* __restrict__ offs,
-                                                  uint32_t* __restrict__ pairs_out, uint32_t* __restrict__ npairs_out) {
+                                                  PairEnt* __restrict__ pairs_out, uint32_t* __restrict__ npairs_out) {
   const uint32_t npairs = *npairs_ptr;
   const uint32_t step = 1u << r;
-  const uint32_t nround = (npairs + 31) & ~31u;   // whole warps iterate together (ballot in emit_next_round)
+  const uint32_t nround = (npairs + 31) & ~31u;   // whole warps iterate together (ballot in emit_pair)
   for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nround; idx += gridDim.x * blockDim.x) {
-    uint32_t s = 0;
-    bool valid = idx < npairs;
+    const bool valid = idx < npairs;
+    PairEnt ent = {0u, 0u};
     if (valid) {
-      uint32_t ent = pairs[idx];
-      s = ent & ~PAIR_RIGHT_RAW;
-      typename CV::acc res;
-      if (r == 0) {
-        res = CV::G::add_affine(CV::load_raw(table, refs[s]), CV::load_raw(table, refs[s + step]));
-      } else {
-        typename CV::acc A = CV::load_v(V, s);
-        if (ent & PAIR_RIGHT_RAW) res = CV::add_raw(A, CV::load_raw(table, refs[s + step]));
-        else res = CV::add_v(A, CV::load_v(V, s + step));
-      }
-      CV::store_v(V, s, res);
+      ent = pairs[idx];
+      CV::store_v(V, ent.slot, CV::add(CV::load_v(V, ent.slot), CV::load_v(V, ent.slot + step)));
     }
-    emit_next_round(valid, s, r, slot_bucket, offs, pairs_out, npairs_out);
+    emit_pair(valid && (uint32_t)(r + 1) < ent.life, ent, pairs_out, npairs_out);
   }
 }
 
@@ -564,8 +559,7 @@ __global__ void __launch_bounds__(256) k_pair_add(const uint32_t* __restrict__ t
 // number of accumulation rounds that were run: a bucket's elements at local indices multiple of
 // 2^rounds are still separate and are summed here.
 template <class CV>
-__global__ void __launch_bounds__(128) k_reduce_level0(MsmParams pr, int mlog, int rounds, const uint32_t* __restrict__ table,
-                                                       const uint32_t* __restrict__ refs, const uint32_t* __restrict__ V,
+__global__ void __launch_bounds__(128) k_reduce_level0(MsmParams pr, int mlog, int rounds, const uint32_t* __restrict__ V,
                                                        const uint32_t* __restrict__ offs, uint32_t* __restrict__ outU, uint32_t* __restrict__ outW) {
   uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t nchunks = pr.nbuckets >> mlog;
@@ -576,11 +570,7 @@ __global__ void __launch_bounds__(128) k_reduce_level0(MsmParams pr, int mlog, i
   for (int j = (int)m - 1; j >= 0; j--) {
     uint32_t b = g * m + (uint32_t)j;
     uint32_t o = offs[b], n = offs[b + 1] - o;
-    for (uint32_t q = 0; q < n; q += stride) {
-      // element at local index q is materialised iff it had a partner in round 0
-      if (rounds > 0 && q + 1 < n) row = CV::add_v(row, CV::load_v(V, o + q));
-      else row = CV::add_raw(row, CV::load_raw(table, refs[o + q]));
-    }
+    for (uint32_t q = 0; q < n; q += stride) row = CV::add_v(row, CV::load_v(V, o + q));
     if (j > 0) tri = CV::add(tri, row);
   }
   CV::st_acc(outU + (size_t)g * CV::ACC_LIMBS, row);

@@ -27,7 +27,7 @@ struct mgb_ctx {
   size_t max_points = 0, npoints = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[EV_COUNT] = {};
-  DevBuf table, scalars, ent_bucket, ent_rank, counts, offs, tile_sums, refs, slot_bucket, pairs, pairs2, V, redU[2], redW[2], misc, acc_out, out_xy, stage;
+  DevBuf table, scalars, ent_bucket, ent_rank, counts, offs, tile_sums, pairs, pairs2, V, redU[2], redW[2], misc, acc_out, out_xy, stage;
   uint32_t* h_pinned = nullptr;  // [0..31] out xy limbs + flag, [64..] misc readback
   int sm_count = 148;
   std::string err;
@@ -148,11 +148,9 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   ENS(ctx, ctx->offs, ((size_t)pr.nbuckets + 1) * 4);
   const uint32_t ntiles = cdiv(pr.nbuckets, SCAN_TILE);
   ENS(ctx, ctx->tile_sums, (size_t)ntiles * 4);
-  ENS(ctx, ctx->refs, (size_t)pr.nent * 4);
-  ENS(ctx, ctx->slot_bucket, (size_t)pr.nent * 4);
-  ENS(ctx, ctx->pairs, ((size_t)pr.nent / 2 + 1) * 4);
-  ENS(ctx, ctx->pairs2, ((size_t)pr.nent / 4 + 1) * 4);
-  ENS(ctx, ctx->V, ((size_t)pr.nent / 2 + 1) * CV::V_LIMBS * 4);
+  ENS(ctx, ctx->pairs, ((size_t)pr.nent / 2 + 1) * sizeof(PairEnt));
+  ENS(ctx, ctx->pairs2, ((size_t)pr.nent / 4 + 1) * sizeof(PairEnt));
+  ENS(ctx, ctx->V, ((size_t)pr.nent + 1) * CV::V_LIMBS * 4);
   ENS(ctx, ctx->redU[0], (size_t)nchunks0 * CV::ACC_LIMBS * 4);
   ENS(ctx, ctx->redW[0], (size_t)nchunks0 * CV::ACC_LIMBS * 4);
   ENS(ctx, ctx->redU[1], ((size_t)(nchunks0 >> 4) + pr.K) * CV::ACC_LIMBS * 4);
@@ -173,8 +171,8 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   k_scan_sums<<<1, SCAN_T, 0, st>>>((uint32_t*)ctx->tile_sums.p, ntiles, misc);
   k_scan_add<<<ntiles, SCAN_T, 0, st>>>((uint32_t*)ctx->offs.p, (const uint32_t*)ctx->tile_sums.p, pr.nbuckets, misc);
   k_scatter<CV><<<cdiv(pr.nent, 256), 256, 0, st>>>(pr, (const uint32_t*)ctx->ent_bucket.p, (const uint32_t*)ctx->ent_rank.p,
-                                                   (const uint32_t*)ctx->offs.p, (uint32_t*)ctx->refs.p, (uint32_t*)ctx->slot_bucket.p,
-                                                   (uint32_t*)ctx->pairs.p, misc + 2);
+                                                   (const uint32_t*)ctx->offs.p, (const uint32_t*)ctx->table.p, (uint32_t*)ctx->V.p,
+                                                   (PairEnt*)ctx->pairs.p, misc + 2);
   launches += 4;
   CU(ctx, cudaGetLastError());
   CU(ctx, cudaMemcpyAsync(ctx->h_pinned + 64, misc, 8, cudaMemcpyDeviceToHost, st));
@@ -195,16 +193,14 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   int rounds = (r_full <= r_typ + 4) ? std::min(r_full, r_typ) : r_full;
   if (opts && opts->verbose > 1) rounds = r_full;
   for (int r = 0; r < rounds; r++) {
-    uint32_t* pin = (uint32_t*)((r & 1) ? ctx->pairs2.p : ctx->pairs.p);
-    uint32_t* pout = (uint32_t*)((r & 1) ? ctx->pairs.p : ctx->pairs2.p);
+    PairEnt* pin = (PairEnt*)((r & 1) ? ctx->pairs2.p : ctx->pairs.p);
+    PairEnt* pout = (PairEnt*)((r & 1) ? ctx->pairs.p : ctx->pairs2.p);
     if constexpr (CV::BATCH_AFFINE) {
       constexpr int E = 32, MINB = 4;
-      k_batch_add<CV, E, MINB><<<ctx->sm_count * MINB, 128, 0, st>>>(
-          (const uint32_t*)ctx->table.p, (const uint32_t*)ctx->refs.p, (uint32_t*)ctx->V.p, pin, misc + 2 + r, r,
-          (const uint32_t*)ctx->slot_bucket.p, (const uint32_t*)ctx->offs.p, pout, misc + 3 + r);
+      constexpr bool INL = true;
+      k_batch_add<CV, E, MINB, INL><<<ctx->sm_count * MINB, 128, 0, st>>>((uint32_t*)ctx->V.p, pin, misc + 2 + r, r, pout, misc + 3 + r);
     } else {
-      k_pair_add<CV><<<ctx->sm_count * 8, 256, 0, st>>>((const uint32_t*)ctx->table.p, (const uint32_t*)ctx->refs.p, (uint32_t*)ctx->V.p, pin,
-                                                       misc + 2 + r, r, (const uint32_t*)ctx->slot_bucket.p, (const uint32_t*)ctx->offs.p, pout, misc + 3 + r);
+      k_pair_add<CV><<<ctx->sm_count * 8, 256, 0, st>>>((uint32_t*)ctx->V.p, pin, misc + 2 + r, r, pout, misc + 3 + r);
     }
     launches += 1;
   }
@@ -212,8 +208,7 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   CU(ctx, cudaEventRecord(ctx->ev[EV_ACC], st));
 
   // ---- bucket reduction
-  k_reduce_level0<CV><<<cdiv(nchunks0, 128), 128, 0, st>>>(pr, mlog0, rounds, (const uint32_t*)ctx->table.p, (const uint32_t*)ctx->refs.p,
-                                                          (const uint32_t*)ctx->V.p, (const uint32_t*)ctx->offs.p,
+  k_reduce_level0<CV><<<cdiv(nchunks0, 128), 128, 0, st>>>(pr, mlog0, rounds, (const uint32_t*)ctx->V.p, (const uint32_t*)ctx->offs.p,
                                                           (uint32_t*)ctx->redU[0].p, (uint32_t*)ctx->redW[0].p);
   launches++;
   uint32_t nseg = pr.L >> mlog0;
@@ -413,8 +408,7 @@ const char* mgb_last_error(const mgb_ctx* ctx) { return ctx ? ctx->err.c_str() :
 void mgb_destroy(mgb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  DevBuf* bufs[] = {&ctx->table, &ctx->scalars, &ctx->ent_bucket, &ctx->ent_rank, &ctx->counts, &ctx->offs, &ctx->tile_sums, &ctx->refs,
-                    &ctx->slot_bucket, &ctx->pairs, &ctx->pairs2, &ctx->V, &ctx->redU[0], &ctx->redU[1], &ctx->redW[0], &ctx->redW[1], &ctx->misc,
+  DevBuf* bufs[] = {&ctx->table, &ctx->scalars, &ctx->ent_bucket, &ctx->ent_rank, &ctx->counts, &ctx->offs, &ctx->tile_sums, &ctx->pairs, &ctx->pairs2, &ctx->V, &ctx->redU[0], &ctx->redU[1], &ctx->redW[0], &ctx->redW[1], &ctx->misc,
                     &ctx->acc_out, &ctx->out_xy, &ctx->stage};
   for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
