@@ -552,67 +552,115 @@ __global__ void __launch_bounds__(256) k_pair_add(uint32_t* __restrict__ V, cons
 }
 
 // ---------------------------------------------------------------- bucket reduction
-// Level 0: one thread per chunk of m = 2^mlog consecutive buckets of one window.  With t the
-// 0-based bucket position inside the window (digit l = t+1), the chunk yields
-//   U = sum_j B_j,   W = sum_j j*B_j   (j = local index),
-// by the running-sum walk of the reference (msm-batched-affine.ts:556-583).  `rounds` is the
-// number of accumulation rounds that were run: a bucket's elements at local indices multiple of
-// 2^rounds are still separate and are summed here.
+// Window sum S_w = sum_{l=1..L} l * B_l (reference: reduceBucketsColumnProjective, the running sum
+// "triangle += row; row += B_l", msm-batched-affine.ts:556-583 -- 2L sequential additions per
+// chunk).  A sequential walk is latency-bound on a GPU, so the weight is split into D digits of
+// at most 5 bits instead:  idx = l - 1 = sum_d v_d * 2^(sh_d),  hence
+//     S_w = sum_d 2^(sh_d) * ( sum_v v * G[w][d][v] ) + sum_l B_l,
+//     G[w][d][v] = sum of the buckets of window w whose digit d equals v
+// -- D plain sums per bucket, done as chunked partial sums plus a log-depth tree, then one warp
+// per (w, d) forms sum_v v*G_v with a shuffle suffix scan (the "warp-shuffle running sum").
+struct ReduceGeom {
+  int D;            // digits
+  int width[6];     // bits per digit
+  int shift[6];     // bit position of each digit
+  int NP;           // partial sums per group (power of two)
+  int CH;           // buckets per partial sum
+};
+
 template <class CV>
-__global__ void __launch_bounds__(128) k_reduce_level0(MsmParams pr, int mlog, int rounds, const uint32_t* __restrict__ V,
-                                                       const uint32_t* __restrict__ offs, uint32_t* __restrict__ outU, uint32_t* __restrict__ outW) {
-  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t nchunks = pr.nbuckets >> mlog;
-  if (g >= nchunks) return;
-  const uint32_t m = 1u << mlog;
-  typename CV::acc row = CV::acc_zero(), tri = CV::acc_zero();
-  const uint32_t stride = 1u << rounds;
-  for (int j = (int)m - 1; j >= 0; j--) {
-    uint32_t b = g * m + (uint32_t)j;
-    uint32_t o = offs[b], n = offs[b + 1] - o;
-    for (uint32_t q = 0; q < n; q += stride) row = CV::add_v(row, CV::load_v(V, o + q));
-    if (j > 0) tri = CV::add(tri, row);
+__global__ void __launch_bounds__(128) k_group_partial(MsmParams pr, ReduceGeom gm, int rounds, const uint32_t* __restrict__ V,
+                                                       const uint32_t* __restrict__ offs, uint32_t* __restrict__ P) {
+  // thread -> (window w, digit d, value v, chunk ch)
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t total = (uint32_t)pr.K * gm.D * 32 * gm.NP;
+  if (t >= total) return;
+  uint32_t ch = t % gm.NP, g = t / gm.NP;
+  uint32_t v = g & 31, wd = g >> 5;
+  uint32_t d = wd % gm.D, w = wd / gm.D;
+  typename CV::acc acc = CV::acc_zero();
+  const int wdt = gm.width[d], sh = gm.shift[d];
+  const uint32_t gsize = pr.L >> wdt;                  // members of the group
+  if (v < (1u << wdt)) {
+    const uint32_t stride = 1u << rounds;
+    for (int k = 0; k < gm.CH; k++) {
+      uint32_t m = ch * gm.CH + k;
+      if (m >= gsize) break;
+      uint32_t low = m & ((1u << sh) - 1), high = m >> sh;
+      uint32_t idx = (high << (sh + wdt)) | (v << sh) | low;
+      uint32_t b = w * pr.L + idx;
+      uint32_t o = offs[b], n = offs[b + 1] - o;
+      for (uint32_t q = 0; q < n; q += stride) acc = CV::add_v(acc, CV::load_v(V, o + q));
+    }
   }
-  CV::st_acc(outU + (size_t)g * CV::ACC_LIMBS, row);
-  CV::st_acc(outW + (size_t)g * CV::ACC_LIMBS, tri);
+  CV::st_acc(P + (size_t)t * CV::ACC_LIMBS, acc);
 }
 
-// Level >= 1: combine m consecutive segments (each covering 2^slog buckets) of one window:
-//   U = sum U_j,  W = sum W_j + 2^slog * sum_j j*U_j.
-// nseg_in segments per window in, ceil(nseg_in / m) out.
+// one tree level: P[g][i] += P[g][i + half] for i < half
 template <class CV>
-__global__ void __launch_bounds__(128) k_reduce_combine(int K, uint32_t nseg_in, int mlog, int slog,
-                                                        const uint32_t* __restrict__ inU, const uint32_t* __restrict__ inW,
-                                                        uint32_t* __restrict__ outU, uint32_t* __restrict__ outW) {
-  const uint32_t m = 1u << mlog;
-  const uint32_t nseg_out = (nseg_in + m - 1) >> mlog;
-  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= nseg_out * (uint32_t)K) return;
-  uint32_t w = g / nseg_out, go = g - w * nseg_out;
-  uint32_t first = go * m;
-  uint32_t cnt = min(m, nseg_in - first);
-  typename CV::acc row = CV::acc_zero(), tri = CV::acc_zero(), ws = CV::acc_zero();
-  for (int j = (int)cnt - 1; j >= 0; j--) {
-    size_t idx = (size_t)w * nseg_in + first + (uint32_t)j;
-    row = CV::add(row, CV::ld_acc(inU + idx * CV::ACC_LIMBS));
-    ws = CV::add(ws, CV::ld_acc(inW + idx * CV::ACC_LIMBS));
-    if (j > 0) tri = CV::add(tri, row);
-  }
-  for (int d = 0; d < slog; d++) tri = CV::dbl(tri);
-  CV::st_acc(outU + (size_t)g * CV::ACC_LIMBS, row);
-  CV::st_acc(outW + (size_t)g * CV::ACC_LIMBS, CV::add(ws, tri));
+__global__ void __launch_bounds__(128) k_tree_round(uint32_t ngroups, int NP, int half, uint32_t* __restrict__ P) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ngroups * (uint32_t)half) return;
+  uint32_t i = t % half, g = t / half;
+  uint32_t* a = P + ((size_t)g * NP + i) * CV::ACC_LIMBS;
+  CV::st_acc(a, CV::add(CV::ld_acc(a), CV::ld_acc(a + (size_t)half * CV::ACC_LIMBS)));
 }
 
-// Window sum S_w = W + U (digit = position + 1); result = sum_w 2^(c*w) S_w by Horner
-// (msm-batched-affine.ts:322-334).  One thread.  Writes the un-normalised accumulator.
 template <class CV>
-__global__ void k_final(int K, int c, const uint32_t* __restrict__ inU, const uint32_t* __restrict__ inW, uint32_t* __restrict__ out_acc) {
+MGB_DEV typename CV::acc shfl_acc(const typename CV::acc& a, int src) {
+  typename CV::acc r;
+  const uint32_t* pa = reinterpret_cast<const uint32_t*>(&a);
+  uint32_t* pr = reinterpret_cast<uint32_t*>(&r);
+  _Pragma("unroll") for (int i = 0; i < CV::ACC_LIMBS; i++) pr[i] = __shfl_sync(0xffffffffu, pa[i], src);
+  return r;
+}
+
+// block = one window, warp d = one digit: X_d = sum_v v * G_v by an inclusive suffix scan over the
+// lanes (S_v = sum_{v' >= v} G_v', X = sum_{v >= 1} S_v), then thread 0 assembles
+// S_w = sum_d 2^(sh_d) X_d + sum_l B_l.
+template <class CV>
+__global__ void __launch_bounds__(192) k_window_sums(MsmParams pr, ReduceGeom gm, const uint32_t* __restrict__ P, uint32_t* __restrict__ Sw) {
+  __shared__ uint32_t sm[7 * CV::ACC_LIMBS];
+  const int lane = threadIdx.x & 31, d = threadIdx.x >> 5, w = blockIdx.x;
+  if (d < gm.D) {
+    typename CV::acc G = CV::acc_zero();
+    if (lane < (1 << gm.width[d])) G = CV::ld_acc(P + ((size_t)((w * gm.D + d) * 32 + lane) * gm.NP) * CV::ACC_LIMBS);
+    typename CV::acc S = G;
+    _Pragma("unroll 1") for (int dl = 1; dl < 32; dl <<= 1) {
+      typename CV::acc o = shfl_acc<CV>(S, lane + dl > 31 ? lane : lane + dl);
+      if (lane + dl <= 31) S = CV::add(S, o);
+    }
+    typename CV::acc tot = shfl_acc<CV>(S, 0);       // sum of all buckets of the window
+    typename CV::acc X = (lane >= 1) ? S : CV::acc_zero();
+    _Pragma("unroll 1") for (int dl = 16; dl >= 1; dl >>= 1) {
+      typename CV::acc o = shfl_acc<CV>(X, lane + dl > 31 ? lane : lane + dl);
+      if (lane < dl) X = CV::add(X, o);
+    }
+    if (lane == 0) {
+      CV::st_acc(sm + d * CV::ACC_LIMBS, X);
+      if (d == 0) CV::st_acc(sm + 6 * CV::ACC_LIMBS, tot);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    typename CV::acc acc = CV::ld_acc(sm + (gm.D - 1) * CV::ACC_LIMBS);
+    for (int dd = gm.D - 2; dd >= 0; dd--) {
+      for (int k = 0; k < gm.width[dd]; k++) acc = CV::dbl(acc);
+      acc = CV::add(acc, CV::ld_acc(sm + dd * CV::ACC_LIMBS));
+    }
+    acc = CV::add(acc, CV::ld_acc(sm + 6 * CV::ACC_LIMBS));
+    CV::st_acc(Sw + (size_t)w * CV::ACC_LIMBS, acc);
+  }
+}
+
+// result = sum_w 2^(c*w) S_w by Horner (msm-batched-affine.ts:322-334).  One thread.
+template <class CV>
+__global__ void k_final(int K, int c, const uint32_t* __restrict__ Sw, uint32_t* __restrict__ out_acc) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  typename CV::acc res = CV::acc_zero();
-  for (int w = K - 1; w >= 0; w--) {
+  typename CV::acc res = CV::ld_acc(Sw + (size_t)(K - 1) * CV::ACC_LIMBS);
+  for (int w = K - 2; w >= 0; w--) {
     for (int d = 0; d < c; d++) res = CV::dbl(res);
-    typename CV::acc S = CV::add(CV::ld_acc(inU + (size_t)w * CV::ACC_LIMBS), CV::ld_acc(inW + (size_t)w * CV::ACC_LIMBS));
-    res = CV::add(res, S);
+    res = CV::add(res, CV::ld_acc(Sw + (size_t)w * CV::ACC_LIMBS));
   }
   CV::st_acc(out_acc, res);
 }

@@ -63,12 +63,25 @@ int ensure(mgb_ctx* ctx, DevBuf& b, size_t bytes) {
 }
 #define ENS(ctx, buf, bytes) do { int r_ = ensure(ctx, buf, bytes); if (r_) return r_; } while (0)
 
-int default_window(int curve, size_t n) {
+// Window size: about log2(n) - 4 (average bucket of ~64 half-scalars for GLV), moved to the nearest c
+// whose top window is not nearly empty: with signed digits the top window holds mag_bits - (K-1)c
+// bits, and if that is much smaller than c its few buckets collect 2^(c - top) times the average
+// load and force extra accumulation rounds (the CPU analogue is handled by splitBuckets' top-window
+// weighting, src/msm-common.ts:89-96).  The reference's own table (msm-common.ts:25-41) is tuned
+// for 16 CPU threads and is not used here.
+int default_window(int mag_bits, size_t n) {
   int lg = 0;
   while (((size_t)1 << lg) < n) lg++;
-  int c = lg - 4;
-  (void)curve;
-  return std::max(5, std::min(c, 20));
+  const int c0 = std::max(5, std::min(lg - 4, 22));
+  static const int order[] = {0, -1, 1, -2, 2, -3, 3};
+  for (int off : order) {
+    int c = c0 + off;
+    if (c < 4 || c > 23) continue;
+    int K = (mag_bits + c - 1) / c;
+    int top = mag_bits - (K - 1) * c;
+    if (top >= c - 2) return c;
+  }
+  return c0;
 }
 
 inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
@@ -117,7 +130,7 @@ template <class CV>
 int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const mgb_opts* opts, mgb_timing* tm) {
   cudaStream_t st = ctx->stream;
   uint32_t launches = 0;
-  int c = (opts && opts->c > 0) ? opts->c : default_window(ctx->curve, n);
+  int c = (opts && opts->c > 0) ? opts->c : default_window(CV::MAG_BITS, n);
   if (c < 2 || c > 24) return fail(ctx, MGB_E_INVALID, "window size c must be in [2, 24]");
   MsmParams pr;
   pr.n = (uint32_t)n;
@@ -127,9 +140,25 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   pr.nbuckets = (uint32_t)pr.K * pr.L;
   pr.nent = (uint32_t)(n * CV::HALVES * pr.K);
   if ((size_t)n * CV::HALVES * pr.K >= (1ull << 31)) return fail(ctx, MGB_E_INVALID, "n * windows exceeds 2^31 entries");
-  const int mlog0 = std::min(4, c - 1);
-  const uint32_t nchunks0 = pr.nbuckets >> mlog0;
-
+  // geometry of the bucket reduction: c-1 index bits in D digits of <= 5 bits
+  ReduceGeom gm;
+  {
+    const int nb = c - 1;
+    gm.D = std::max(1, (nb + 4) / 5);
+    int pos = 0, minw = 32;
+    for (int d = 0; d < 6; d++) { gm.width[d] = 0; gm.shift[d] = 0; }
+    for (int d = 0; d < gm.D; d++) {
+      gm.width[d] = nb / gm.D + (d < nb % gm.D ? 1 : 0);
+      gm.shift[d] = pos;
+      pos += gm.width[d];
+      minw = std::min(minw, gm.width[d]);
+    }
+    const uint32_t gmax = pr.L >> minw;        // largest group
+    gm.CH = 8;
+    gm.NP = 1;
+    while ((uint32_t)gm.NP * gm.CH < gmax) gm.NP <<= 1;
+  }
+  const uint32_t ngroups = (uint32_t)pr.K * gm.D * 32;
   ENS(ctx, ctx->acc_out, CV::ACC_LIMBS * 4);
   CU(ctx, cudaEventRecord(ctx->ev[EV_START], st));
   const uint32_t* d_scalars;
@@ -151,10 +180,8 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   ENS(ctx, ctx->pairs, ((size_t)pr.nent / 2 + 1) * sizeof(PairEnt));
   ENS(ctx, ctx->pairs2, ((size_t)pr.nent / 4 + 1) * sizeof(PairEnt));
   ENS(ctx, ctx->V, ((size_t)pr.nent + 1) * CV::V_LIMBS * 4);
-  ENS(ctx, ctx->redU[0], (size_t)nchunks0 * CV::ACC_LIMBS * 4);
-  ENS(ctx, ctx->redW[0], (size_t)nchunks0 * CV::ACC_LIMBS * 4);
-  ENS(ctx, ctx->redU[1], ((size_t)(nchunks0 >> 4) + pr.K) * CV::ACC_LIMBS * 4);
-  ENS(ctx, ctx->redW[1], ((size_t)(nchunks0 >> 4) + pr.K) * CV::ACC_LIMBS * 4);
+  ENS(ctx, ctx->redU[0], (size_t)ngroups * gm.NP * CV::ACC_LIMBS * 4);
+  ENS(ctx, ctx->redW[0], (size_t)pr.K * CV::ACC_LIMBS * 4);
   ENS(ctx, ctx->misc, 128 * 4);
   uint32_t* misc = (uint32_t*)ctx->misc.p;  // [0] grand total, [1] max bucket, [2 + r] pair count of round r
   CU(ctx, cudaMemsetAsync(ctx->counts.p, 0, ((size_t)pr.nbuckets + 1) * 4, st));
@@ -207,25 +234,19 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   CU(ctx, cudaGetLastError());
   CU(ctx, cudaEventRecord(ctx->ev[EV_ACC], st));
 
-  // ---- bucket reduction
-  k_reduce_level0<CV><<<cdiv(nchunks0, 128), 128, 0, st>>>(pr, mlog0, rounds, (const uint32_t*)ctx->V.p, (const uint32_t*)ctx->offs.p,
-                                                          (uint32_t*)ctx->redU[0].p, (uint32_t*)ctx->redW[0].p);
+  // ---- bucket reduction (digit-decomposed weights, see engine.cuh)
+  k_group_partial<CV><<<cdiv(ngroups * gm.NP, 128), 128, 0, st>>>(pr, gm, rounds, (const uint32_t*)ctx->V.p, (const uint32_t*)ctx->offs.p,
+                                                                  (uint32_t*)ctx->redU[0].p);
   launches++;
-  uint32_t nseg = pr.L >> mlog0;
-  int slog = mlog0, cur = 0;
-  while (nseg > 1) {
-    const int mlog = 4;
-    uint32_t nout = (nseg + 15) >> 4;
-    k_reduce_combine<CV><<<cdiv((size_t)nout * pr.K, 128), 128, 0, st>>>(pr.K, nseg, mlog, slog, (const uint32_t*)ctx->redU[cur].p, (const uint32_t*)ctx->redW[cur].p,
-                                                                        (uint32_t*)ctx->redU[cur ^ 1].p, (uint32_t*)ctx->redW[cur ^ 1].p);
+  for (int half = gm.NP / 2; half >= 1; half >>= 1) {
+    k_tree_round<CV><<<cdiv((size_t)ngroups * half, 128), 128, 0, st>>>(ngroups, gm.NP, half, (uint32_t*)ctx->redU[0].p);
     launches++;
-    nseg = nout;
-    slog += mlog;
-    cur ^= 1;
   }
+  k_window_sums<CV><<<pr.K, 192, 0, st>>>(pr, gm, (const uint32_t*)ctx->redU[0].p, (uint32_t*)ctx->redW[0].p);
+  launches++;
   CU(ctx, cudaGetLastError());
   CU(ctx, cudaEventRecord(ctx->ev[EV_REDUCE], st));
-  k_final<CV><<<1, 32, 0, st>>>(pr.K, pr.c, (const uint32_t*)ctx->redU[cur].p, (const uint32_t*)ctx->redW[cur].p, (uint32_t*)ctx->acc_out.p);
+  k_final<CV><<<1, 32, 0, st>>>(pr.K, pr.c, (const uint32_t*)ctx->redW[0].p, (uint32_t*)ctx->acc_out.p);
   launches++;
   CU(ctx, cudaGetLastError());
   if (tm) {
