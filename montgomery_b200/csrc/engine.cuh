@@ -50,7 +50,7 @@ static constexpr uint32_t REF_IDX = 0x3fffffffu;
 static constexpr uint32_t NO_BUCKET = 0xffffffffu;
 
 // ---------------------------------------------------------------- curve policies
-template <class FP, class CC, class GL>
+template <class FP, class CC, class GL, int MAGB>
 struct WeierstrassPolicy {
   typedef FP P;
   typedef Field<FP> F;
@@ -63,7 +63,7 @@ struct WeierstrassPolicy {
   static constexpr bool BATCH_AFFINE = true;
   static constexpr int HALVES = 2;
   static constexpr int MAG_LIMBS = 4;        // |k0|, |k1| < 2^128
-  static constexpr int MAG_BITS = 128;       // digits must cover MAG_BITS (incl. the final carry)
+  static constexpr int MAG_BITS = MAGB;      // bound on |k0|, |k1| in bits, plus one for the final carry
   static constexpr int ENTRY_LIMBS = 3 * N;  // x | y | beta*x
   static constexpr int V_LIMBS = 2 * N;
   static constexpr int ACC_LIMBS = 4 * N;
@@ -185,8 +185,8 @@ struct TwistedEdwardsPolicy {
   }
 };
 
-typedef WeierstrassPolicy<Fp377, Bls12377Consts, Glv377> CurveBls377;
-typedef WeierstrassPolicy<FpPallas, PallasConsts, GlvPallas> CurvePallas;
+typedef WeierstrassPolicy<Fp377, Bls12377Consts, Glv377, 127> CurveBls377;     // |k| < 2^126 (gen_constants.py self-check; reference maxBits = 126)
+typedef WeierstrassPolicy<FpPallas, PallasConsts, GlvPallas, 128> CurvePallas;  // |k| < 2^127
 typedef TwistedEdwardsPolicy<Fr377, Ed377Consts> CurveEd377;
 
 // ---------------------------------------------------------------- small multi-limb helpers (scalar side)
@@ -255,6 +255,7 @@ struct MsmParams {
   uint32_t L;          // buckets per window = 2^(c-1)
   uint32_t nbuckets;   // K*L
   uint32_t nent;       // n * HALVES * K
+  int top_sub;         // the top window's digit has few bits: its buckets are split 2^top_sub ways (by point index)
 };
 
 // ---------------------------------------------------------------- k_digits
@@ -299,6 +300,11 @@ __global__ void __launch_bounds__(256) k_digits(MsmParams pr, const uint32_t* __
       size_t pos = (size_t)e * pr.n + i;
       if (l == 0) { ent_bucket[pos] = NO_BUCKET; continue; }
       uint32_t bucket = (uint32_t)w * L + (l - 1);
+      if (w == pr.K - 1 && pr.top_sub) {
+        // sparse top window: spread each digit over 2^top_sub buckets of equal weight
+        if (l > (L >> pr.top_sub)) { atomicOr(&counts[pr.nbuckets], 1u); l = L >> pr.top_sub; }  // cannot happen for |k| < 2^(MAG_BITS-1)
+        bucket = (uint32_t)w * L + (((l - 1) << pr.top_sub) | ((2 * i + h) & ((1u << pr.top_sub) - 1)));
+      }
       uint32_t rank = atomicAdd(&counts[bucket], 1u);
       ent_bucket[pos] = bucket;
       ent_rank[pos] = rank | ((dneg != neg[h]) ? REF_NEG : 0u);  // rank < 2^31
@@ -448,16 +454,18 @@ MGB_DEV void prefetch_point(const uint32_t* V, uint32_t slot) {
   asm volatile("prefetch.global.L1 [%0];" ::"l"(p + CV::V_LIMBS * 4 - 4));
 }
 
-template <class CV, int E, int MINB, bool INL>
+template <class CV, int EMAX, int MINB, bool INL>
 __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ V, const PairEnt* __restrict__ pairs,
-                                                         const uint32_t* __restrict__ npairs_ptr, int r,
+                                                         const uint32_t* __restrict__ npairs_ptr, int r, int E,
                                                          PairEnt* __restrict__ pairs_out, uint32_t* __restrict__ npairs_out) {
   typedef typename CV::P FP;
   typedef typename CV::F F;
   typedef typename CV::G G;
   typedef Fe<FP> fe;
   const uint32_t npairs = *npairs_ptr;
-  constexpr uint32_t TILE = 32 * E;
+  // E (<= EMAX) pairs per lane: large tiles amortise the inversion, small ones keep every warp busy
+  // in the late rounds that have few pairs
+  const uint32_t TILE = 32u * (uint32_t)E;
   const uint32_t ntiles = (npairs + TILE - 1) / TILE;
   const uint32_t step = 1u << r;
   const int lane = threadIdx.x & 31;
@@ -465,7 +473,7 @@ __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ 
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
 
   for (uint32_t tile = gwarp; tile < ntiles; tile += nwarps) {
-    fe pre[E];
+    fe pre[EMAX];
     fe run = F::one();
     // software pipeline: slot indices two pairs ahead, x coordinates one pair ahead, so the loads of
     // pair e+1 are in flight during the multiplication of pair e
@@ -579,12 +587,19 @@ __global__ void __launch_bounds__(128) k_group_partial(MsmParams pr, ReduceGeom 
   uint32_t v = g & 31, wd = g >> 5;
   uint32_t d = wd % gm.D, w = wd / gm.D;
   typename CV::acc acc = CV::acc_zero();
-  const int wdt = gm.width[d], sh = gm.shift[d];
+  // digit d of the weight index idx = (bucket >> sub): bits [shift + sub, ...) of the bucket number
+  const int sub = (w == (uint32_t)pr.K - 1) ? pr.top_sub : 0;
+  const int nb = pr.c - 1;
+  const int sh = min(gm.shift[d] + sub, nb);
+  const int wdt = min(gm.width[d], nb - sh);
   const uint32_t gsize = pr.L >> wdt;                  // members of the group
-  if (v < (1u << wdt)) {
+  // a digit clipped to zero width (top window with sub-bucket spreading) has weight 0 everywhere:
+  // its groups are only needed for digit 0, whose v = 0..: sum also yields the window total
+  if (v < (1u << wdt) && !(wdt == 0 && d > 0)) {
     const uint32_t stride = 1u << rounds;
-    for (int k = 0; k < gm.CH; k++) {
-      uint32_t m = ch * gm.CH + k;
+    const uint32_t chlen = (gsize + gm.NP - 1) / gm.NP;   // = CH except for clipped digits
+    for (uint32_t k = 0; k < chlen; k++) {
+      uint32_t m = ch * chlen + k;
       if (m >= gsize) break;
       uint32_t low = m & ((1u << sh) - 1), high = m >> sh;
       uint32_t idx = (high << (sh + wdt)) | (v << sh) | low;

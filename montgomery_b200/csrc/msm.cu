@@ -63,25 +63,15 @@ int ensure(mgb_ctx* ctx, DevBuf& b, size_t bytes) {
 }
 #define ENS(ctx, buf, bytes) do { int r_ = ensure(ctx, buf, bytes); if (r_) return r_; } while (0)
 
-// Window size: about log2(n) - 4 (average bucket of ~64 half-scalars for GLV), moved to the nearest c
-// whose top window is not nearly empty: with signed digits the top window holds mag_bits - (K-1)c
-// bits, and if that is much smaller than c its few buckets collect 2^(c - top) times the average
-// load and force extra accumulation rounds (the CPU analogue is handled by splitBuckets' top-window
-// weighting, src/msm-common.ts:89-96).  The reference's own table (msm-common.ts:25-41) is tuned
-// for 16 CPU threads and is not used here.
+// Window size: log2(n) - 4, i.e. an average bucket of ~64 half-scalars (GLV) -- enough for the
+// batched additions to amortise, few enough buckets for the reduction.  A sparse top window (few
+// digit bits) is balanced by sub-bucket spreading (MsmParams::top_sub), not avoided.  The reference's
+// own table (msm-common.ts:25-41) is tuned for 16 CPU threads and is not used here.
 int default_window(int mag_bits, size_t n) {
   int lg = 0;
   while (((size_t)1 << lg) < n) lg++;
-  const int c0 = std::max(5, std::min(lg - 4, 22));
-  static const int order[] = {0, -1, 1, -2, 2, -3, 3};
-  for (int off : order) {
-    int c = c0 + off;
-    if (c < 4 || c > 23) continue;
-    int K = (mag_bits + c - 1) / c;
-    int top = mag_bits - (K - 1) * c;
-    if (top >= c - 2) return c;
-  }
-  return c0;
+  (void)mag_bits;
+  return std::max(5, std::min(lg - 4, 22));
 }
 
 inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
@@ -139,6 +129,10 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   pr.L = 1u << (c - 1);
   pr.nbuckets = (uint32_t)pr.K * pr.L;
   pr.nent = (uint32_t)(n * CV::HALVES * pr.K);
+  {
+    const int top_bits = CV::MAG_BITS - (pr.K - 1) * c;   // the top digit is at most 2^top_bits
+    pr.top_sub = std::max(0, (c - 1) - top_bits);
+  }
   if ((size_t)n * CV::HALVES * pr.K >= (1ull << 31)) return fail(ctx, MGB_E_INVALID, "n * windows exceeds 2^31 entries");
   // geometry of the bucket reduction: c-1 index bits in D digits of <= 5 bits
   ReduceGeom gm;
@@ -203,9 +197,11 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   launches += 4;
   CU(ctx, cudaGetLastError());
   CU(ctx, cudaMemcpyAsync(ctx->h_pinned + 64, misc, 8, cudaMemcpyDeviceToHost, st));
+  CU(ctx, cudaMemcpyAsync(ctx->h_pinned + 66, (uint32_t*)ctx->counts.p + pr.nbuckets, 4, cudaMemcpyDeviceToHost, st));
   CU(ctx, cudaEventRecord(ctx->ev[EV_SORT], st));
   CU(ctx, cudaStreamSynchronize(st));
   const uint32_t nslots = ctx->h_pinned[64], maxcount = ctx->h_pinned[65];
+  if (ctx->h_pinned[66]) return fail(ctx, MGB_E_INVALID, "internal: a half-scalar exceeded its bound");
 
   // ---- bucket accumulation rounds
   // Full depth is ceil(log2(max bucket)); for the usual near-uniform digit distribution the last
@@ -223,9 +219,14 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
     PairEnt* pin = (PairEnt*)((r & 1) ? ctx->pairs2.p : ctx->pairs.p);
     PairEnt* pout = (PairEnt*)((r & 1) ? ctx->pairs.p : ctx->pairs2.p);
     if constexpr (CV::BATCH_AFFINE) {
-      constexpr int E = 32, MINB = 4;
+      constexpr int EMAX = 32, MINB = 4;
       constexpr bool INL = true;
-      k_batch_add<CV, E, MINB, INL><<<ctx->sm_count * MINB, 128, 0, st>>>((uint32_t*)ctx->V.p, pin, misc + 2 + r, r, pout, misc + 3 + r);
+      // expected pairs of this round ~ nslots / 2^(r+1); aim at >= 2 tiles per resident warp
+      const uint64_t est = (uint64_t)nslots >> (r + 1);
+      const uint64_t warps = (uint64_t)ctx->sm_count * MINB * 4;
+      int E = EMAX;
+      while (E > 4 && est < warps * 32ull * E / 2) E >>= 1;
+      k_batch_add<CV, EMAX, MINB, INL><<<ctx->sm_count * MINB, 128, 0, st>>>((uint32_t*)ctx->V.p, pin, misc + 2 + r, r, E, pout, misc + 3 + r);
     } else {
       k_pair_add<CV><<<ctx->sm_count * 8, 256, 0, st>>>((uint32_t*)ctx->V.p, pin, misc + 2 + r, r, pout, misc + 3 + r);
     }

@@ -168,3 +168,19 @@ def test_closed_form_large(engines, label, logn):
     res_dev, _ = eng.msm(sc[::-1].copy(), n=n)
     k2 = sum(s * int(ai) for s, ai in zip(reversed(s_ints), a)) % O.q
     assert res_dev == O.result_of(O.scale(k2, O.G))
+
+
+@pytest.mark.parametrize("label", list(CURVES))
+def test_all_window_sizes(engines, label):
+    """Every window size c (sparse top windows, clipped reduction digits, tiny bucket counts) gives the
+    same point -- the reference exposes c as an option (msm-batched-affine.ts:74-77)."""
+    n = 300
+    eng = engines(label, 1 << 10)
+    O = OracleCurve(label)
+    eng.random_points(n, seed=777)
+    pts = _points_from_engine(eng, n)
+    sc = inputs.random_scalars(O.q, n, seed=778)
+    exp = O.msm(inputs.scalars_to_ints(sc), pts)
+    for c in range(2, 23):
+        res, tm = eng.msm(sc, n=n, c=c)
+        assert res == exp, (label, c, tm)
