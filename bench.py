@@ -168,34 +168,20 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     curve = m.curves.BY_LABEL[args.curve]
     n = 1 << args.logn
-    eng = m.MsmEngine(curve, local, n)
-    eng.random_points(n, SEED_POINTS + rank)            # this rank's shard of the global point set
+    from montgomery_b200.distributed import ShardedMsm
+    sharded = ShardedMsm(curve, local, n)
+    eng = sharded.engine
+    sharded.random_points(n, SEED_POINTS)               # rank r: seed + r -> this rank's shard of the global point set
     nsets = 4
     host_sets = [torch.from_numpy(inputs.random_scalars(curve.q, n, SEED_SCALARS + 1000 * rank + i)).pin_memory() for i in range(nsets)]
     dev_sets = [h.cuda(non_blocking=False) for h in host_sets]
     torch.cuda.synchronize()
     opts_c = args.c or None
-    pbytes = eng.partial_bytes
-    partial = torch.zeros(pbytes // 4, dtype=torch.int32, device="cuda")
-    gathered = torch.zeros(world * (pbytes // 4), dtype=torch.int32, device="cuda")
 
     def step(i, e2e):
         """one MSM over this rank's shard (+ all-gather and combine when world > 1)"""
         k = i % nsets
-        if world == 1:
-            if e2e:
-                res, tm = eng.msm(host_sets[k].numpy(), n=n, c=opts_c)
-            else:
-                res, tm = eng.msm(None, n=n, c=opts_c, device_ptr=dev_sets[k].data_ptr())
-            return res, tm
-        if e2e:
-            tm = eng.msm_partial(host_sets[k].data_ptr(), False, n, partial.data_ptr(), c=opts_c)
-        else:
-            tm = eng.msm_partial(dev_sets[k].data_ptr(), True, n, partial.data_ptr(), c=opts_c)
-        dist.all_gather_into_tensor(gathered, partial)
-        torch.cuda.current_stream().synchronize()
-        res = eng.combine_partials(gathered.data_ptr(), world)
-        return res, tm
+        return sharded.msm(host_sets[k] if e2e else dev_sets[k], n, on_device=not e2e, c=opts_c)
 
     def barrier():
         torch.cuda.synchronize()
@@ -215,7 +201,7 @@ def run_b200(args):
         res = None
         for i in range(args.steps):
             res, tm = step(args.warmup + i, e2e)
-            launches += tm["n_launches"] + (1 if world > 1 else 0)
+            launches += tm["n_launches"]
             for key in ("h2d_scalars", "decompose_slice", "sort", "accumulate", "reduce", "final_sum", "total"):
                 phases[key] = phases.get(key, 0.0) + tm[key] / args.steps
         barrier()
