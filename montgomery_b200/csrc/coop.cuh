@@ -1,0 +1,179 @@
+// Block-cooperative point doubling / addition for the serial tail of the MSM (Horner over the
+// windows: ~110 dependent doublings, reference msm-batched-affine.ts:322-334).
+//
+// A dependent chain of field multiplications on ONE warp is bound by that warp's SMSP multiplier
+// pipe (277 IMAD.WIDE x 4 cycles per 377-bit product), so instruction-level parallelism inside a
+// thread buys nothing.  The four warps of a 128-thread block sit on the four SMSPs of an SM: each
+// takes one of the independent multiplications of a formula level and the operands travel through
+// shared memory.  XYZZ doubling = 3 levels instead of 9 sequential products, addition = 4 instead
+// of 14; extended twisted-Edwards addition = 3 instead of 9.
+#pragma once
+#include "ec.cuh"
+
+namespace mgb {
+
+template <class P>
+struct CoopMem {  // slots of N limbs in shared memory
+  uint32_t* base;
+  MGB_DEV Fe<P> ld(int slot) const {
+    Fe<P> r;
+    _Pragma("unroll") for (int i = 0; i < P::N; i++) r.v[i] = base[slot * P::N + i];
+    return r;
+  }
+  MGB_DEV void st(int slot, const Fe<P>& a) const {
+    _Pragma("unroll") for (int i = 0; i < P::N; i++) base[slot * P::N + i] = a.v[i];
+  }
+};
+
+// slot map: 0..3 = P (accumulator), 4..7 = Q (second operand), 8.. = temporaries, flags after the slots
+static constexpr int COOP_SLOTS = 24;
+
+template <class P>
+struct CoopWeierstrass {
+  typedef Field<P> F;
+  typedef Fe<P> fe;
+  typedef Weierstrass<P> G;
+  enum { X = 0, Y = 1, ZZ = 2, ZZZ = 3, X2 = 4, Y2 = 5, ZZ2 = 6, ZZZ2 = 7, T = 8 };
+
+  // P <- 2P  (dbl-2008-s-1, a = 0)
+  MGB_DEV static void dbl(CoopMem<P> m, volatile int* flag) {
+    const int warp = threadIdx.x >> 5;
+    const bool act = (threadIdx.x & 31) == 0;
+    if (threadIdx.x == 0) *flag = F::is_zero(m.ld(ZZ)) || F::is_zero(m.ld(Y)) ? 1 : 0;   // infinity or 2-torsion
+    __syncthreads();
+    if (*flag) {
+      if (threadIdx.x == 0 && !F::is_zero(m.ld(ZZ))) { m.st(X, F::zero()); m.st(Y, F::one()); m.st(ZZ, F::zero()); m.st(ZZZ, F::zero()); }
+      __syncthreads();
+      return;
+    }
+    if (act) {
+      if (warp == 0) { fe U = F::dbl(m.ld(Y)); m.st(T + 0, U); m.st(T + 1, F::sqr(U)); }
+      if (warp == 1) { fe xx = F::sqr(m.ld(X)); m.st(T + 2, F::add(F::dbl(xx), xx)); }
+    }
+    __syncthreads();
+    if (act) {
+      if (warp == 0) m.st(T + 3, F::mul(m.ld(T + 0), m.ld(T + 1)));       // W = U*V
+      if (warp == 1) m.st(T + 4, F::mul(m.ld(X), m.ld(T + 1)));           // S = X*V
+      if (warp == 2) m.st(T + 5, F::sqr(m.ld(T + 2)));                    // M^2
+      if (warp == 3) m.st(T + 6, F::mul(m.ld(T + 1), m.ld(ZZ)));          // ZZ' = V*ZZ
+    }
+    __syncthreads();
+    if (act) {
+      if (warp == 0) m.st(T + 7, F::mul(m.ld(T + 3), m.ld(Y)));           // W*Y
+      if (warp == 1) m.st(T + 8, F::mul(m.ld(T + 3), m.ld(ZZZ)));         // ZZZ' = W*ZZZ
+      if (warp == 2) {
+        fe S = m.ld(T + 4);
+        fe x3 = F::sub(m.ld(T + 5), F::dbl(S));
+        m.st(T + 9, x3);
+        m.st(T + 10, F::mul(m.ld(T + 2), F::sub(S, x3)));                 // M*(S - X3)
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      m.st(X, m.ld(T + 9));
+      m.st(Y, F::sub(m.ld(T + 10), m.ld(T + 7)));
+      m.st(ZZ, m.ld(T + 6));
+      m.st(ZZZ, m.ld(T + 8));
+    }
+    __syncthreads();
+  }
+
+  // P <- P + Q  (add-2008-s; the degenerate cases fall back to the complete serial formula)
+  MGB_DEV static void add(CoopMem<P> m, volatile int* flag) {
+    const int warp = threadIdx.x >> 5;
+    const bool act = (threadIdx.x & 31) == 0;
+    if (threadIdx.x == 0) *flag = (F::is_zero(m.ld(ZZ)) ? 1 : 0) | (F::is_zero(m.ld(ZZ2)) ? 2 : 0);
+    __syncthreads();
+    int f = *flag;
+    if (f) {
+      if (threadIdx.x == 0 && (f & 1) && !(f & 2)) { m.st(X, m.ld(X2)); m.st(Y, m.ld(Y2)); m.st(ZZ, m.ld(ZZ2)); m.st(ZZZ, m.ld(ZZZ2)); }
+      __syncthreads();
+      return;
+    }
+    if (act) {
+      if (warp == 0) m.st(T + 0, F::mul(m.ld(X), m.ld(ZZ2)));     // U1
+      if (warp == 1) m.st(T + 1, F::mul(m.ld(X2), m.ld(ZZ)));     // U2
+      if (warp == 2) m.st(T + 2, F::mul(m.ld(Y), m.ld(ZZZ2)));    // S1
+      if (warp == 3) m.st(T + 3, F::mul(m.ld(Y2), m.ld(ZZZ)));    // S2
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *flag = F::is_zero(F::sub(m.ld(T + 1), m.ld(T + 0))) ? 1 : 0;
+    __syncthreads();
+    if (*flag) {   // same x: doubling or cancellation -- rare, serial
+      if (threadIdx.x == 0) {
+        typename G::acc a, b;
+        a.X = m.ld(X); a.Y = m.ld(Y); a.ZZ = m.ld(ZZ); a.ZZZ = m.ld(ZZZ);
+        b.X = m.ld(X2); b.Y = m.ld(Y2); b.ZZ = m.ld(ZZ2); b.ZZZ = m.ld(ZZZ2);
+        a = G::add(a, b);
+        m.st(X, a.X); m.st(Y, a.Y); m.st(ZZ, a.ZZ); m.st(ZZZ, a.ZZZ);
+      }
+      __syncthreads();
+      return;
+    }
+    if (act) {
+      if (warp == 0) { fe Pd = F::sub(m.ld(T + 1), m.ld(T + 0)); m.st(T + 4, Pd); m.st(T + 5, F::sqr(Pd)); }   // P, PP
+      if (warp == 1) { fe R = F::sub(m.ld(T + 3), m.ld(T + 2)); m.st(T + 6, R); m.st(T + 7, F::sqr(R)); }      // R, RR
+      if (warp == 2) m.st(T + 8, F::mul(m.ld(ZZ), m.ld(ZZ2)));
+      if (warp == 3) m.st(T + 9, F::mul(m.ld(ZZZ), m.ld(ZZZ2)));
+    }
+    __syncthreads();
+    if (act) {
+      if (warp == 0) m.st(T + 10, F::mul(m.ld(T + 4), m.ld(T + 5)));    // PPP
+      if (warp == 1) m.st(T + 11, F::mul(m.ld(T + 0), m.ld(T + 5)));    // Q = U1*PP
+      if (warp == 2) m.st(T + 12, F::mul(m.ld(T + 8), m.ld(T + 5)));    // ZZ3
+    }
+    __syncthreads();
+    if (act) {
+      if (warp == 0) {
+        fe Q = m.ld(T + 11);
+        fe x3 = F::sub(F::sub(m.ld(T + 7), m.ld(T + 10)), F::dbl(Q));
+        m.st(T + 13, x3);
+        m.st(T + 14, F::mul(m.ld(T + 6), F::sub(Q, x3)));               // R*(Q - X3)
+      }
+      if (warp == 1) m.st(T + 15, F::mul(m.ld(T + 2), m.ld(T + 10)));   // S1*PPP
+      if (warp == 2) m.st(T + 4, F::mul(m.ld(T + 9), m.ld(T + 10)));    // ZZZ3 (T+4 = P is dead)
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      m.st(X, m.ld(T + 13));
+      m.st(Y, F::sub(m.ld(T + 14), m.ld(T + 15)));
+      m.st(ZZ, m.ld(T + 12));
+      m.st(ZZZ, m.ld(T + 4));
+    }
+    __syncthreads();
+  }
+};
+
+template <class P, class C>
+struct CoopTwistedEdwards {
+  typedef Field<P> F;
+  typedef Fe<P> fe;
+  typedef TwistedEdwards<P, C> G;
+  enum { X = 0, Y = 1, Z = 2, Tt = 3, T = 8 };
+
+  // P <- P + Q with Q at slot qbase (4 = second operand, 0 = P itself, i.e. doubling); unified, complete
+  MGB_DEV static void add_from(CoopMem<P> m, int qb) {
+    const int warp = threadIdx.x >> 5;
+    const bool act = (threadIdx.x & 31) == 0;
+    if (act) {
+      if (warp == 0) m.st(T + 0, F::mul(F::sub(m.ld(Y), m.ld(X)), F::sub(m.ld(qb + Y), m.ld(qb + X))));   // A
+      if (warp == 1) m.st(T + 1, F::mul(F::add(m.ld(Y), m.ld(X)), F::add(m.ld(qb + Y), m.ld(qb + X))));   // B
+      if (warp == 2) m.st(T + 2, F::mul(F::mul(m.ld(Tt), m.ld(qb + Tt)), G::k2d()));                       // C
+      if (warp == 3) m.st(T + 3, F::dbl(F::mul(m.ld(Z), m.ld(qb + Z))));                                   // D
+    }
+    __syncthreads();
+    if (act) {
+      fe A = m.ld(T + 0), B = m.ld(T + 1), Cc = m.ld(T + 2), D = m.ld(T + 3);
+      fe E = F::sub(B, A), Ff = F::sub(D, Cc), Gg = F::add(D, Cc), H = F::add(B, A);
+      if (warp == 0) m.st(X, F::mul(E, Ff));
+      if (warp == 1) m.st(Y, F::mul(Gg, H));
+      if (warp == 2) m.st(Tt, F::mul(E, H));
+      if (warp == 3) m.st(Z, F::mul(Ff, Gg));
+    }
+    __syncthreads();
+  }
+  MGB_DEV static void dbl(CoopMem<P> m, volatile int*) { add_from(m, 0); }
+  MGB_DEV static void add(CoopMem<P> m, volatile int*) { add_from(m, 4); }
+};
+
+}  // namespace mgb

@@ -13,6 +13,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "ec.cuh"
+#include "coop.cuh"
 
 namespace mgb {
 
@@ -58,6 +59,7 @@ struct WeierstrassPolicy {
   typedef typename G::acc acc;
   typedef typename G::affine vpoint;   // materialised bucket element
   typedef GL Glv;
+  typedef CoopWeierstrass<FP> Coop;
   static constexpr int N = FP::N;
   static constexpr bool USE_GLV = true;
   static constexpr bool BATCH_AFFINE = true;
@@ -133,6 +135,7 @@ struct TwistedEdwardsPolicy {
   typedef TwistedEdwards<FP, CC> G;
   typedef typename G::acc acc;
   typedef typename G::acc vpoint;
+  typedef CoopTwistedEdwards<FP, CC> Coop;
   static constexpr int N = FP::N;
   static constexpr bool USE_GLV = false;
   static constexpr bool BATCH_AFFINE = false;
@@ -457,7 +460,8 @@ MGB_DEV void prefetch_point(const uint32_t* V, uint32_t slot) {
 template <class CV, int EMAX, int MINB, bool INL>
 __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ V, const PairEnt* __restrict__ pairs,
                                                          const uint32_t* __restrict__ npairs_ptr, int r, int E,
-                                                         PairEnt* __restrict__ pairs_out, uint32_t* __restrict__ npairs_out) {
+                                                         PairEnt* __restrict__ pairs_out, uint32_t* __restrict__ npairs_out,
+                                                         uint32_t* __restrict__ tile_counter) {
   typedef typename CV::P FP;
   typedef typename CV::F F;
   typedef typename CV::G G;
@@ -469,10 +473,13 @@ __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ 
   const uint32_t ntiles = (npairs + TILE - 1) / TILE;
   const uint32_t step = 1u << r;
   const int lane = threadIdx.x & 31;
-  const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-
-  for (uint32_t tile = gwarp; tile < ntiles; tile += nwarps) {
+  // tiles are handed out dynamically: warps drift apart (inversion latency varies), and a static
+  // split would leave the tail of every round to a few warps
+  while (true) {
+    uint32_t tile = 0;
+    if (lane == 0) tile = atomicAdd(tile_counter, 1u);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if (tile >= ntiles) break;
     fe pre[EMAX];
     fe run = F::one();
     // software pipeline: slot indices two pairs ahead, x coordinates one pair ahead, so the loads of
@@ -668,16 +675,28 @@ __global__ void __launch_bounds__(192) k_window_sums(MsmParams pr, ReduceGeom gm
   }
 }
 
-// result = sum_w 2^(c*w) S_w by Horner (msm-batched-affine.ts:322-334).  One thread.
+// result = sum_w 2^(c*w) S_w by Horner (msm-batched-affine.ts:322-334): (K-1)*c dependent doublings.
+// One 128-thread block; the four warps share the multiplications of each formula level (coop.cuh).
 template <class CV>
-__global__ void k_final(int K, int c, const uint32_t* __restrict__ Sw, uint32_t* __restrict__ out_acc) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  typename CV::acc res = CV::ld_acc(Sw + (size_t)(K - 1) * CV::ACC_LIMBS);
+__global__ void __launch_bounds__(128) k_final(int K, int c, const uint32_t* __restrict__ Sw, uint32_t* __restrict__ out_acc) {
+  typedef typename CV::P FP;
+  constexpr int N = CV::N;
+  __shared__ uint32_t sm[COOP_SLOTS * N];
+  __shared__ int flag;
+  CoopMem<FP> m{sm};
+  // accumulator slots 0..3 and operand slots 4..7 hold the 4 coordinates of CV::acc in order
+  auto load_point = [&](int slot0, const uint32_t* src) {
+    if (threadIdx.x < 4 * N) sm[slot0 * N + threadIdx.x] = src[threadIdx.x];
+  };
+  load_point(0, Sw + (size_t)(K - 1) * CV::ACC_LIMBS);
+  __syncthreads();
   for (int w = K - 2; w >= 0; w--) {
-    for (int d = 0; d < c; d++) res = CV::dbl(res);
-    res = CV::add(res, CV::ld_acc(Sw + (size_t)w * CV::ACC_LIMBS));
+    for (int d = 0; d < c; d++) CV::Coop::dbl(m, &flag);
+    load_point(4, Sw + (size_t)w * CV::ACC_LIMBS);
+    __syncthreads();
+    CV::Coop::add(m, &flag);
   }
-  CV::st_acc(out_acc, res);
+  if (threadIdx.x < 4 * N) out_acc[threadIdx.x] = sm[threadIdx.x];
 }
 
 // sum `count` partial accumulators (multi-GPU combine) and/or normalise: out = canonical x||y + flag

@@ -1,5 +1,6 @@
 // Host orchestration + C ABI of the MSM engine (see include/montgomery_b200.h).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -225,12 +226,25 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
       const uint64_t est = (uint64_t)nslots >> (r + 1);
       const uint64_t warps = (uint64_t)ctx->sm_count * MINB * 4;
       int E = EMAX;
-      while (E > 4 && est < warps * 32ull * E / 2) E >>= 1;
-      k_batch_add<CV, EMAX, MINB, INL><<<ctx->sm_count * MINB, 128, 0, st>>>((uint32_t*)ctx->V.p, pin, misc + 2 + r, r, E, pout, misc + 3 + r);
+      while (E > 8 && est < warps * 32ull * E * 3) E >>= 1;
+      if (const char* ev = getenv("MGB_DEBUG_E")) {   // tuning aid: comma-separated E per round
+        int k = 0; const char* q = ev;
+        while (k < r && (q = strchr(q, ',')) != nullptr) { q++; k++; }
+        if (q && k == r && atoi(q) > 0) E = std::min(EMAX, atoi(q));
+      }
+      k_batch_add<CV, EMAX, MINB, INL><<<ctx->sm_count * MINB, 128, 0, st>>>((uint32_t*)ctx->V.p, pin, misc + 2 + r, r, E, pout, misc + 3 + r,
+                                                                             misc + 64 + r);
     } else {
       k_pair_add<CV><<<ctx->sm_count * 8, 256, 0, st>>>((uint32_t*)ctx->V.p, pin, misc + 2 + r, r, pout, misc + 3 + r);
     }
     launches += 1;
+    if (getenv("MGB_DEBUG_ROUNDS")) {   // tuning aid: per-round wall time (synchronises!)
+      cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+      cudaEventRecord(e1, st); cudaEventSynchronize(e1);
+      static thread_local float last = 0; float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[EV_SORT], e1);
+      fprintf(stderr, "  round %d: +%.3f ms (cum %.3f)\n", r, ms - (r ? last : 0), ms); last = ms;
+      cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
   }
   CU(ctx, cudaGetLastError());
   CU(ctx, cudaEventRecord(ctx->ev[EV_ACC], st));
@@ -247,7 +261,7 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   launches++;
   CU(ctx, cudaGetLastError());
   CU(ctx, cudaEventRecord(ctx->ev[EV_REDUCE], st));
-  k_final<CV><<<1, 32, 0, st>>>(pr.K, pr.c, (const uint32_t*)ctx->redW[0].p, (uint32_t*)ctx->acc_out.p);
+  k_final<CV><<<1, 128, 0, st>>>(pr.K, pr.c, (const uint32_t*)ctx->redW[0].p, (uint32_t*)ctx->acc_out.p);
   launches++;
   CU(ctx, cudaGetLastError());
   if (tm) {
