@@ -149,7 +149,7 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
       minw = std::min(minw, gm.width[d]);
     }
     const uint32_t gmax = pr.L >> minw;        // largest group
-    gm.CH = 8;
+    gm.CH = 2;
     gm.NP = 1;
     while ((uint32_t)gm.NP * gm.CH < gmax) gm.NP <<= 1;
   }
@@ -220,13 +220,13 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
     PairEnt* pin = (PairEnt*)((r & 1) ? ctx->pairs2.p : ctx->pairs.p);
     PairEnt* pout = (PairEnt*)((r & 1) ? ctx->pairs.p : ctx->pairs2.p);
     if constexpr (CV::BATCH_AFFINE) {
-      constexpr int EMAX = 32, MINB = 4;
+      constexpr int EMAX = 64, MINB = 4;
       constexpr bool INL = true;
       // expected pairs of this round ~ nslots / 2^(r+1); aim at >= 2 tiles per resident warp
       const uint64_t est = (uint64_t)nslots >> (r + 1);
       const uint64_t warps = (uint64_t)ctx->sm_count * MINB * 4;
       int E = EMAX;
-      while (E > 8 && est < warps * 32ull * E * 3) E >>= 1;
+      while (E > 4 && 10 * est < warps * 32ull * E * 9) E >>= 1;   // measured optimum: largest tile with >= 0.9 tiles per resident warp
       if (const char* ev = getenv("MGB_DEBUG_E")) {   // tuning aid: comma-separated E per round
         int k = 0; const char* q = ev;
         while (k < r && (q = strchr(q, ',')) != nullptr) { q++; k++; }
