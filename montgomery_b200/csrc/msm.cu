@@ -221,7 +221,7 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
     PairEnt* pout = (PairEnt*)((r & 1) ? ctx->pairs.p : ctx->pairs2.p);
     if constexpr (CV::BATCH_AFFINE) {
       constexpr int EMAX = 64, MINB = 4;
-      constexpr bool INL = true;
+      constexpr bool INL = false;
       // expected pairs of this round ~ nslots / 2^(r+1); aim at >= 2 tiles per resident warp
       const uint64_t est = (uint64_t)nslots >> (r + 1);
       const uint64_t warps = (uint64_t)ctx->sm_count * MINB * 4;
