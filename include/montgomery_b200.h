@@ -121,7 +121,8 @@ int mgb_field_op(int device, int field, int op, const uint8_t* a, const uint8_t*
 /* Integer-pipe microbenchmarks (roofline denominator).  mode: 0 = mad.lo.u32 (IMAD), 1 = mad.hi.u32,
  * 2 = mad.wide.u32 with 64-bit accumulate, 3 = mad.lo.cc/madc.hi.cc carry chain (IMAD.WIDE.U32.X:
  * the full 32x32+64->64 multiply-accumulate the field multiplication is made of), 4/5 = Fp377 /
- * Fr377 Montgomery multiplications through the out-of-line call, 6/7 = the same inlined.  All
+ * Fr377 Montgomery multiplications through the out-of-line call, 6/7 = the same inlined, 8/9 = chains
+ * of Fp377 division-step inversions on all lanes / on lane 0 of each warp (threads <= 128).  All
  * multiplicands change every iteration (a loop-invariant product would be hoisted by ptxas).
  * Returns operations per second (lane operations for modes 0-3, field multiplications for 4-7) in
  * *ops_per_s and the kernel time in *ms. */

@@ -402,18 +402,21 @@ MGB_DEV void emit_pair(bool active, PairEnt ent, PairEnt* __restrict__ pairs, ui
 }
 
 template <class CV>
-__global__ void __launch_bounds__(256) k_scatter(MsmParams pr, const uint32_t* __restrict__ ent_bucket, const uint32_t* __restrict__ ent_rank,
+__global__ void __launch_bounds__(256) k_scatter(MsmParams pr, int w_begin, int Kg, const uint32_t* __restrict__ ent_bucket, const uint32_t* __restrict__ ent_rank,
                                                  const uint32_t* __restrict__ offs, const uint32_t* __restrict__ table, uint32_t* __restrict__ V,
                                                  PairEnt* __restrict__ pairs, uint32_t* __restrict__ npairs) {
-  size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // thread -> (half h, window w of the group [w_begin, w_begin + Kg), point i)
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool active = false;
   PairEnt ent = {0u, 0u};
-  if (pos < pr.nent) {
+  if (t < (size_t)pr.n * CV::HALVES * Kg) {
+    uint32_t el = (uint32_t)(t / pr.n), i = (uint32_t)(t - (size_t)el * pr.n);
+    uint32_t h = el / (uint32_t)Kg, w = (uint32_t)w_begin + el % (uint32_t)Kg;
+    size_t pos = (size_t)(h * pr.K + w) * pr.n + i;
     uint32_t b = ent_bucket[pos];
     if (b != NO_BUCKET) {
       uint32_t rk = ent_rank[pos];
-      uint32_t e = (uint32_t)(pos / pr.n), i = (uint32_t)(pos - (size_t)e * pr.n);
-      const bool endo = (CV::HALVES == 2) && e >= (uint32_t)pr.K;
+      const bool endo = h != 0;
       uint32_t o = offs[b], n = offs[b + 1] - o, j = rk & ~REF_NEG;
       uint32_t slot = o + j;
       CV::store_v(V, slot, CV::load_entry(table, i, endo, (rk & REF_NEG) != 0));
@@ -457,9 +460,9 @@ MGB_DEV void prefetch_point(const uint32_t* V, uint32_t slot) {
   asm volatile("prefetch.global.L1 [%0];" ::"l"(p + CV::V_LIMBS * 4 - 4));
 }
 
-template <class CV, int EMAX, int MINB, bool INL>
+template <class CV, int EMAX, int MINB, bool INL, bool BLOCK>
 __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ V, const PairEnt* __restrict__ pairs,
-                                                         const uint32_t* __restrict__ npairs_ptr, int r, int E,
+                                                         const uint32_t* __restrict__ npairs_ptr, int r, int E_big, uint32_t n_big,
                                                          PairEnt* __restrict__ pairs_out, uint32_t* __restrict__ npairs_out,
                                                          uint32_t* __restrict__ tile_counter) {
   typedef typename CV::P FP;
@@ -469,22 +472,45 @@ __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ 
   const uint32_t npairs = *npairs_ptr;
   // E (<= EMAX) pairs per lane: large tiles amortise the inversion, small ones keep every warp busy
   // in the late rounds that have few pairs
-  const uint32_t TILE = 32u * (uint32_t)E;
-  const uint32_t ntiles = (npairs + TILE - 1) / TILE;
+  // BLOCK = false: a tile is 32*E pairs owned by one warp, warps are independent.
+  // BLOCK = true : a tile is 128*E pairs owned by the block; the four warps share ONE inversion
+  //                (two block barriers per tile).  Used for the late rounds, which have so few pairs
+  //                that the serial length of a tile, not throughput, sets the time: four times fewer
+  //                pairs per lane for the same pairs-per-inversion.
+  constexpr uint32_t WPT = BLOCK ? 4u : 1u;                 // warps per tile
+  // Guided tile sizes: the first n_big tiles hold E_big pairs per lane (few inversions), the rest a
+  // quarter of that, so the end of the round is not one long tile per straggling warp.
+  const int E_small = E_big >= 16 ? E_big / 4 : E_big;
+  const uint32_t TILE_BIG = 32u * WPT * (uint32_t)E_big, TILE_SMALL = 32u * WPT * (uint32_t)E_small;
+  const uint32_t nbig = min(n_big, npairs / TILE_BIG);
+  const uint32_t rest = npairs - nbig * TILE_BIG;
+  const uint32_t ntiles = nbig + (rest + TILE_SMALL - 1) / TILE_SMALL;
   const uint32_t step = 1u << r;
   const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  __shared__ uint32_t sm_tot[BLOCK ? 4 * CV::N : 1];        // warp totals, then per-warp inverses
+  __shared__ uint32_t sm_tile;
   // tiles are handed out dynamically: warps drift apart (inversion latency varies), and a static
   // split would leave the tail of every round to a few warps
   while (true) {
     uint32_t tile = 0;
-    if (lane == 0) tile = atomicAdd(tile_counter, 1u);
-    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if (BLOCK) {
+      __syncthreads();                                      // previous tile fully consumed (sm_tot, sm_tile)
+      if (threadIdx.x == 0) sm_tile = atomicAdd(tile_counter, 1u);
+      __syncthreads();
+      tile = sm_tile;
+    } else {
+      if (lane == 0) tile = atomicAdd(tile_counter, 1u);
+      tile = __shfl_sync(0xffffffffu, tile, 0);
+    }
     if (tile >= ntiles) break;
+    const int E = tile < nbig ? E_big : E_small;
+    const uint32_t tile_base = tile < nbig ? tile * TILE_BIG : nbig * TILE_BIG + (tile - nbig) * TILE_SMALL;
     fe pre[EMAX];
     fe run = F::one();
     // software pipeline: slot indices two pairs ahead, x coordinates one pair ahead, so the loads of
     // pair e+1 are in flight during the multiplication of pair e
-    const uint32_t base = tile * TILE + lane;
+    const uint32_t base = tile_base + (BLOCK ? (uint32_t)warp * 32u * (uint32_t)E : 0u) + lane;
     uint32_t s1 = (base < npairs) ? pairs[base].slot : NO_BUCKET;
     uint32_t s2 = (base + 32 < npairs) ? pairs[base + 32].slot : NO_BUCKET;
     fe xa_n = F::zero(), xb_n = F::zero();
@@ -515,23 +541,43 @@ __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ 
       if (lane + dlt <= 31) sfx = ns;
     }
     fe total = shfl_fe<FP>(pfx, 31);
-    fe inv = total;
-    if (lane == 0) inv = F::inv_divsteps(total);
-    inv = shfl_fe<FP>(inv, 0);
+    fe inv = total;                                // -> 1 / (this warp's total)
+    if (BLOCK) {
+      if (lane == 0) st_fe<FP>(sm_tot + warp * CV::N, total);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        fe t0 = ld_fe<FP>(sm_tot), t1 = ld_fe<FP>(sm_tot + CV::N), t2 = ld_fe<FP>(sm_tot + 2 * CV::N), t3 = ld_fe<FP>(sm_tot + 3 * CV::N);
+        fe t01 = F::mul(t0, t1), t23 = F::mul(t2, t3);
+        fe iall = F::inv_divsteps(F::mul(t01, t23));
+        fe i01 = F::mul(iall, t23), i23 = F::mul(iall, t01);
+        st_fe<FP>(sm_tot, F::mul(i01, t1));
+        st_fe<FP>(sm_tot + CV::N, F::mul(i01, t0));
+        st_fe<FP>(sm_tot + 2 * CV::N, F::mul(i23, t3));
+        st_fe<FP>(sm_tot + 3 * CV::N, F::mul(i23, t2));
+      }
+      __syncthreads();
+      inv = ld_fe<FP>(sm_tot + warp * CV::N);
+    } else {
+      if (lane == 0) inv = F::inv_divsteps(total);
+      inv = shfl_fe<FP>(inv, 0);
+    }
     fe left = shfl_fe<FP>(pfx, lane == 0 ? 0 : lane - 1);
     fe right = shfl_fe<FP>(sfx, lane == 31 ? 31 : lane + 1);
     fe u = inv;                                   // -> 1 / (this lane's total)
     if (lane > 0) u = F::mul(u, left);
     if (lane < 31) u = F::mul(u, right);
-    PairEnt nxt = {NO_BUCKET, 0u};
+    // pair entries two iterations ahead, operands prefetched to L1 one iteration ahead
+    PairEnt nxt = {NO_BUCKET, 0u}, nn = {NO_BUCKET, 0u};
     if (base + (E - 1) * 32 < npairs) nxt = pairs[base + (E - 1) * 32];
+    if (E >= 2 && base + (E - 2) * 32 < npairs) nn = pairs[base + (E - 2) * 32];
     _Pragma("unroll 1") for (int e = E - 1; e >= 0; e--) {
       const PairEnt ent = nxt;
       const bool valid = ent.slot != NO_BUCKET;
-      nxt.slot = NO_BUCKET;
-      if (e > 0 && base + (e - 1) * 32 < npairs) {
-        nxt = pairs[base + (e - 1) * 32];
-        prefetch_point<CV>(V, nxt.slot);           // next pair's operands -> L1 while this pair is computed
+      nxt = nn;
+      nn.slot = NO_BUCKET;
+      if (e >= 2 && base + (e - 2) * 32 < npairs) nn = pairs[base + (e - 2) * 32];
+      if (nxt.slot != NO_BUCKET) {
+        prefetch_point<CV>(V, nxt.slot);
         prefetch_point<CV>(V, nxt.slot + step);
       }
       fe inv_den = INL ? F::mul_inl(u, pre[e]) : F::mul(u, pre[e]);
@@ -584,12 +630,13 @@ struct ReduceGeom {
 };
 
 template <class CV>
-__global__ void __launch_bounds__(128) k_group_partial(MsmParams pr, ReduceGeom gm, int rounds, const uint32_t* __restrict__ V,
+__global__ void __launch_bounds__(128) k_group_partial(MsmParams pr, ReduceGeom gm, int w_begin, int Kg, int rounds, const uint32_t* __restrict__ V,
                                                        const uint32_t* __restrict__ offs, uint32_t* __restrict__ P) {
   // thread -> (window w, digit d, value v, chunk ch)
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t total = (uint32_t)pr.K * gm.D * 32 * gm.NP;
+  uint32_t total = (uint32_t)Kg * gm.D * 32 * gm.NP;
   if (t >= total) return;
+  t += (uint32_t)w_begin * gm.D * 32 * gm.NP;          // global (window, digit, value, chunk) index
   uint32_t ch = t % gm.NP, g = t / gm.NP;
   uint32_t v = g & 31, wd = g >> 5;
   uint32_t d = wd % gm.D, w = wd / gm.D;
@@ -641,9 +688,9 @@ MGB_DEV typename CV::acc shfl_acc(const typename CV::acc& a, int src) {
 // lanes (S_v = sum_{v' >= v} G_v', X = sum_{v >= 1} S_v), then thread 0 assembles
 // S_w = sum_d 2^(sh_d) X_d + sum_l B_l.
 template <class CV>
-__global__ void __launch_bounds__(192) k_window_sums(MsmParams pr, ReduceGeom gm, const uint32_t* __restrict__ P, uint32_t* __restrict__ Sw) {
+__global__ void __launch_bounds__(192) k_window_sums(MsmParams pr, ReduceGeom gm, int w_begin, const uint32_t* __restrict__ P, uint32_t* __restrict__ Sw) {
   __shared__ uint32_t sm[7 * CV::ACC_LIMBS];
-  const int lane = threadIdx.x & 31, d = threadIdx.x >> 5, w = blockIdx.x;
+  const int lane = threadIdx.x & 31, d = threadIdx.x >> 5, w = w_begin + blockIdx.x;
   if (d < gm.D) {
     typename CV::acc G = CV::acc_zero();
     if (lane < (1 << gm.width[d])) G = CV::ld_acc(P + ((size_t)((w * gm.D + d) * 32 + lane) * gm.NP) * CV::ACC_LIMBS);

@@ -27,6 +27,8 @@ struct mgb_ctx {
   int curve = 0, device = 0;
   size_t max_points = 0, npoints = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t aux[3] = {};          // extra streams: window groups are pipelined against each other
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {};
   cudaEvent_t ev[EV_COUNT] = {};
   DevBuf table, scalars, ent_bucket, ent_rank, counts, offs, tile_sums, pairs, pairs2, V, redU[2], redW[2], misc, acc_out, out_xy, stage;
   uint32_t* h_pinned = nullptr;  // [0..31] out xy limbs + flag, [64..] misc readback
@@ -172,15 +174,17 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   ENS(ctx, ctx->offs, ((size_t)pr.nbuckets + 1) * 4);
   const uint32_t ntiles = cdiv(pr.nbuckets, SCAN_TILE);
   ENS(ctx, ctx->tile_sums, (size_t)ntiles * 4);
-  ENS(ctx, ctx->pairs, ((size_t)pr.nent / 2 + 1) * sizeof(PairEnt));
-  ENS(ctx, ctx->pairs2, ((size_t)pr.nent / 4 + 1) * sizeof(PairEnt));
+  ENS(ctx, ctx->pairs, ((size_t)pr.nent / 2 + 8) * sizeof(PairEnt));
+  ENS(ctx, ctx->pairs2, ((size_t)pr.nent / 4 + 8) * sizeof(PairEnt));
   ENS(ctx, ctx->V, ((size_t)pr.nent + 1) * CV::V_LIMBS * 4);
   ENS(ctx, ctx->redU[0], (size_t)ngroups * gm.NP * CV::ACC_LIMBS * 4);
   ENS(ctx, ctx->redW[0], (size_t)pr.K * CV::ACC_LIMBS * 4);
-  ENS(ctx, ctx->misc, 128 * 4);
-  uint32_t* misc = (uint32_t*)ctx->misc.p;  // [0] grand total, [1] max bucket, [2 + r] pair count of round r
+  ENS(ctx, ctx->misc, 512 * 4);
+  // misc: [0] grand total, [1] max bucket, [8 + 64 g + r] pair count of round r of window group g,
+  //       [264 + 64 g + r] tile counter of that round
+  uint32_t* misc = (uint32_t*)ctx->misc.p;
   CU(ctx, cudaMemsetAsync(ctx->counts.p, 0, ((size_t)pr.nbuckets + 1) * 4, st));
-  CU(ctx, cudaMemsetAsync(misc, 0, 128 * 4, st));
+  CU(ctx, cudaMemsetAsync(misc, 0, 512 * 4, st));
 
   // ---- digits + histogram
   k_digits<CV><<<cdiv(n, 256), 256, 0, st>>>(pr, d_scalars, (uint32_t*)ctx->ent_bucket.p, (uint32_t*)ctx->ent_rank.p, (uint32_t*)ctx->counts.p);
@@ -188,26 +192,22 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   CU(ctx, cudaGetLastError());
   CU(ctx, cudaEventRecord(ctx->ev[EV_DIGITS], st));
 
-  // ---- offsets + scatter of references
+  // ---- bucket offsets; the totals come back to the host to size the rounds
   k_scan_tiles<<<ntiles, SCAN_T, 0, st>>>((const uint32_t*)ctx->counts.p, (uint32_t*)ctx->offs.p, (uint32_t*)ctx->tile_sums.p, pr.nbuckets, misc + 1);
   k_scan_sums<<<1, SCAN_T, 0, st>>>((uint32_t*)ctx->tile_sums.p, ntiles, misc);
   k_scan_add<<<ntiles, SCAN_T, 0, st>>>((uint32_t*)ctx->offs.p, (const uint32_t*)ctx->tile_sums.p, pr.nbuckets, misc);
-  k_scatter<CV><<<cdiv(pr.nent, 256), 256, 0, st>>>(pr, (const uint32_t*)ctx->ent_bucket.p, (const uint32_t*)ctx->ent_rank.p,
-                                                   (const uint32_t*)ctx->offs.p, (const uint32_t*)ctx->table.p, (uint32_t*)ctx->V.p,
-                                                   (PairEnt*)ctx->pairs.p, misc + 2);
-  launches += 4;
+  launches += 3;
   CU(ctx, cudaGetLastError());
   CU(ctx, cudaMemcpyAsync(ctx->h_pinned + 64, misc, 8, cudaMemcpyDeviceToHost, st));
   CU(ctx, cudaMemcpyAsync(ctx->h_pinned + 66, (uint32_t*)ctx->counts.p + pr.nbuckets, 4, cudaMemcpyDeviceToHost, st));
-  CU(ctx, cudaEventRecord(ctx->ev[EV_SORT], st));
   CU(ctx, cudaStreamSynchronize(st));
   const uint32_t nslots = ctx->h_pinned[64], maxcount = ctx->h_pinned[65];
   if (ctx->h_pinned[66]) return fail(ctx, MGB_E_INVALID, "internal: a half-scalar exceeded its bound");
 
-  // ---- bucket accumulation rounds
-  // Full depth is ceil(log2(max bucket)); for the usual near-uniform digit distribution the last
-  // rounds hold a handful of pairs each and cost a full batch latency, so they are left to the
-  // reduction kernel (which sums whatever a bucket has left).  Skewed inputs run the full depth.
+  // Depth of the bucket trees.  Full depth is ceil(log2(max bucket)); for the usual near-uniform
+  // digit distribution the last rounds hold a handful of pairs each and cost a full batch latency,
+  // so they are left to the reduction kernel (which sums whatever a bucket has left).  Skewed
+  // inputs run the full depth.
   int r_full = 0;
   while ((1u << r_full) < maxcount) r_full++;
   const uint32_t nonempty_bound = std::min<uint32_t>(pr.nbuckets, std::max<uint32_t>(nslots, 1));
@@ -216,49 +216,81 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   while ((1u << r_typ) < avg) r_typ++;
   int rounds = (r_full <= r_typ + 4) ? std::min(r_full, r_typ) : r_full;
   if (opts && opts->verbose > 1) rounds = r_full;
-  for (int r = 0; r < rounds; r++) {
-    PairEnt* pin = (PairEnt*)((r & 1) ? ctx->pairs2.p : ctx->pairs.p);
-    PairEnt* pout = (PairEnt*)((r & 1) ? ctx->pairs.p : ctx->pairs2.p);
-    if constexpr (CV::BATCH_AFFINE) {
-      constexpr int EMAX = 64, MINB = 4;
-      constexpr bool INL = false;
-      // expected pairs of this round ~ nslots / 2^(r+1); aim at >= 2 tiles per resident warp
-      const uint64_t est = (uint64_t)nslots >> (r + 1);
-      const uint64_t warps = (uint64_t)ctx->sm_count * MINB * 4;
-      int E = EMAX;
-      while (E > 4 && 10 * est < warps * 32ull * E * 9) E >>= 1;   // measured optimum: largest tile with >= 0.9 tiles per resident warp
-      if (const char* ev = getenv("MGB_DEBUG_E")) {   // tuning aid: comma-separated E per round
-        int k = 0; const char* q = ev;
-        while (k < r && (q = strchr(q, ',')) != nullptr) { q++; k++; }
-        if (q && k == r && atoi(q) > 0) E = std::min(EMAX, atoi(q));
-      }
-      k_batch_add<CV, EMAX, MINB, INL><<<ctx->sm_count * MINB, 128, 0, st>>>((uint32_t*)ctx->V.p, pin, misc + 2 + r, r, E, pout, misc + 3 + r,
-                                                                             misc + 64 + r);
-    } else {
-      k_pair_add<CV><<<ctx->sm_count * 8, 256, 0, st>>>((uint32_t*)ctx->V.p, pin, misc + 2 + r, r, pout, misc + 3 + r);
-    }
-    launches += 1;
-    if (getenv("MGB_DEBUG_ROUNDS")) {   // tuning aid: per-round wall time (synchronises!)
-      cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-      cudaEventRecord(e1, st); cudaEventSynchronize(e1);
-      static thread_local float last = 0; float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[EV_SORT], e1);
-      fprintf(stderr, "  round %d: +%.3f ms (cum %.3f)\n", r, ms - (r ? last : 0), ms); last = ms;
-      cudaEventDestroy(e0); cudaEventDestroy(e1);
-    }
-  }
-  CU(ctx, cudaGetLastError());
-  CU(ctx, cudaEventRecord(ctx->ev[EV_ACC], st));
 
-  // ---- bucket reduction (digit-decomposed weights, see engine.cuh)
-  k_group_partial<CV><<<cdiv(ngroups * gm.NP, 128), 128, 0, st>>>(pr, gm, rounds, (const uint32_t*)ctx->V.p, (const uint32_t*)ctx->offs.p,
-                                                                  (uint32_t*)ctx->redU[0].p);
-  launches++;
-  for (int half = gm.NP / 2; half >= 1; half >>= 1) {
-    k_tree_round<CV><<<cdiv((size_t)ngroups * half, 128), 128, 0, st>>>(ngroups, gm.NP, half, (uint32_t*)ctx->redU[0].p);
+  // ---- window groups, pipelined on separate streams: every round ends with a tail in which few
+  // tiles are left (and the late rounds and the reduction are latency-bound throughout); the
+  // kernels of another, independent group of windows fill the SMs meanwhile.
+  int G = 1;   // measured on B200: 2 groups change the total by < 1 %; the mechanism stays for tuning / larger parts
+  if (const char* ev = getenv("MGB_DEBUG_GROUPS")) G = std::max(1, std::min(4, atoi(ev)));
+  G = std::min(G, pr.K);
+  CU(ctx, cudaEventRecord(ctx->ev_fork, st));
+  size_t pair_off = 0, pair2_off = 0;
+  for (int g = 0; g < G; g++) {
+    cudaStream_t sg = g == 0 ? st : ctx->aux[g - 1];
+    if (g > 0) CU(ctx, cudaStreamWaitEvent(sg, ctx->ev_fork, 0));
+    const int w_begin = (int)((long long)pr.K * g / G), w_end = (int)((long long)pr.K * (g + 1) / G), Kg = w_end - w_begin;
+    const size_t nent_g = (size_t)n * CV::HALVES * Kg;
+    PairEnt* pl[2] = {(PairEnt*)ctx->pairs.p + pair_off, (PairEnt*)ctx->pairs2.p + pair2_off};
+    pair_off += nent_g / 2 + 1;
+    pair2_off += nent_g / 4 + 1;
+    uint32_t* cnt = misc + 8 + 64 * g;
+    uint32_t* tcnt = misc + 264 + 64 * g;
+    k_scatter<CV><<<cdiv(nent_g, 256), 256, 0, sg>>>(pr, w_begin, Kg, (const uint32_t*)ctx->ent_bucket.p, (const uint32_t*)ctx->ent_rank.p,
+                                                    (const uint32_t*)ctx->offs.p, (const uint32_t*)ctx->table.p, (uint32_t*)ctx->V.p, pl[0], cnt);
     launches++;
+    if (g == 0) CU(ctx, cudaEventRecord(ctx->ev[EV_SORT], st));
+    for (int r = 0; r < rounds; r++) {
+      PairEnt* pin = pl[r & 1];
+      PairEnt* pout = pl[(r & 1) ^ 1];
+      if constexpr (CV::BATCH_AFFINE) {
+        constexpr int EMAX = 64, MINB = 4;
+        constexpr bool INL = false;
+        // expected pairs of this round ~ slots of the group / 2^(r+1)
+        const uint64_t est = ((uint64_t)nslots * Kg / pr.K) >> (r + 1);
+        const uint64_t warps = (uint64_t)ctx->sm_count * MINB * 4;
+        // tile shape: big tiles of E pairs per lane, about 1.5 per resident warp, then tiles of E/4
+        int E = EMAX;
+        while (E > 4 && est < warps * 32ull * E) E >>= 1;
+        uint32_t n_big = (uint32_t)(warps + warps / 2);
+        bool block_tiles = false;
+        if (const char* ev = getenv("MGB_DEBUG_E")) {   // tuning aid: comma-separated E per round, negative = block-level tiles
+          int k = 0; const char* q = ev;
+          while (k < r && (q = strchr(q, ',')) != nullptr) { q++; k++; }
+          if (q && k == r && atoi(q) != 0) { int v = atoi(q); block_tiles = v < 0; E = std::min(EMAX, std::abs(v)); }
+        }
+        if (const char* ev = getenv("MGB_DEBUG_NBIG")) n_big = (uint32_t)(atof(ev) * warps);
+        if (block_tiles)
+          k_batch_add<CV, EMAX, MINB, INL, true><<<ctx->sm_count * MINB, 128, 0, sg>>>((uint32_t*)ctx->V.p, pin, cnt + r, r, E, n_big / 4, pout, cnt + r + 1, tcnt + r);
+        else
+          k_batch_add<CV, EMAX, MINB, INL, false><<<ctx->sm_count * MINB, 128, 0, sg>>>((uint32_t*)ctx->V.p, pin, cnt + r, r, E, n_big, pout, cnt + r + 1, tcnt + r);
+      } else {
+        k_pair_add<CV><<<ctx->sm_count * 8, 256, 0, sg>>>((uint32_t*)ctx->V.p, pin, cnt + r, r, pout, cnt + r + 1);
+      }
+      launches += 1;
+      if (G == 1 && getenv("MGB_DEBUG_ROUNDS")) {   // tuning aid: per-round wall time (synchronises!)
+        cudaEvent_t e1; cudaEventCreate(&e1);
+        cudaEventRecord(e1, st); cudaEventSynchronize(e1);
+        static thread_local float last = 0; float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[EV_SORT], e1);
+        fprintf(stderr, "  round %d: +%.3f ms (cum %.3f)\n", r, ms - (r ? last : 0), ms); last = ms;
+        cudaEventDestroy(e1);
+      }
+    }
+    if (g == 0) CU(ctx, cudaEventRecord(ctx->ev[EV_ACC], st));
+    // bucket reduction of the group's windows (digit-decomposed weights, see engine.cuh)
+    const uint32_t ngroups_g = (uint32_t)Kg * gm.D * 32;
+    uint32_t* Pg = (uint32_t*)ctx->redU[0].p + (size_t)w_begin * gm.D * 32 * gm.NP * CV::ACC_LIMBS;
+    k_group_partial<CV><<<cdiv(ngroups_g * gm.NP, 128), 128, 0, sg>>>(pr, gm, w_begin, Kg, rounds, (const uint32_t*)ctx->V.p, (const uint32_t*)ctx->offs.p,
+                                                                     (uint32_t*)ctx->redU[0].p);
+    launches++;
+    for (int half = gm.NP / 2; half >= 1; half >>= 1) {
+      k_tree_round<CV><<<cdiv((size_t)ngroups_g * half, 128), 128, 0, sg>>>(ngroups_g, gm.NP, half, Pg);
+      launches++;
+    }
+    k_window_sums<CV><<<Kg, 192, 0, sg>>>(pr, gm, w_begin, (const uint32_t*)ctx->redU[0].p, (uint32_t*)ctx->redW[0].p);
+    launches++;
+    if (g > 0) CU(ctx, cudaEventRecord(ctx->ev_join[g - 1], sg));
   }
-  k_window_sums<CV><<<pr.K, 192, 0, st>>>(pr, gm, (const uint32_t*)ctx->redU[0].p, (uint32_t*)ctx->redW[0].p);
-  launches++;
+  for (int g = 1; g < G; g++) CU(ctx, cudaStreamWaitEvent(st, ctx->ev_join[g - 1], 0));
   CU(ctx, cudaGetLastError());
   CU(ctx, cudaEventRecord(ctx->ev[EV_REDUCE], st));
   k_final<CV><<<1, 128, 0, st>>>(pr.K, pr.c, (const uint32_t*)ctx->redW[0].p, (uint32_t*)ctx->acc_out.p);
@@ -281,10 +313,11 @@ int finish_timing(mgb_ctx* ctx, mgb_timing* tm) {
   tm->reduce = el(EV_ACC, EV_REDUCE);
   tm->final_sum = el(EV_REDUCE, EV_FINAL);
   tm->total = el(EV_START, EV_FINAL);
-  uint32_t h[64];
-  CU(ctx, cudaMemcpy(h, (uint32_t*)ctx->misc.p + 2, sizeof(h), cudaMemcpyDeviceToHost));
+  uint32_t h[256];
+  CU(ctx, cudaMemcpy(h, (uint32_t*)ctx->misc.p + 8, sizeof(h), cudaMemcpyDeviceToHost));
   uint64_t s = 0;
-  for (int r = 0; r < tm->rounds && r < 64; r++) s += h[r];
+  for (int g = 0; g < 4; g++)
+    for (int r = 0; r < tm->rounds && r < 63; r++) s += h[64 * g + r];
   tm->n_pairs = s;
   return 0;
 }
@@ -377,6 +410,8 @@ int mgb_create(mgb_ctx** out, int curve, int device, size_t max_points) {
     CU(ctx, cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
     CU(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 3; i++) { CU(ctx, cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking)); CU(ctx, cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming)); }
+    CU(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     for (int i = 0; i < EV_COUNT; i++) CU(ctx, cudaEventCreate(&ctx->ev[i]));
     CU(ctx, cudaMallocHost((void**)&ctx->h_pinned, 256 * 4));
     return ensure(ctx, ctx->table, max_points * entry_bytes(curve));
@@ -450,6 +485,8 @@ void mgb_destroy(mgb_ctx* ctx) {
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   for (int i = 0; i < EV_COUNT; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  for (int i = 0; i < 3; i++) { if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]); if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   delete ctx;
 }
 

@@ -114,6 +114,22 @@ __global__ void __launch_bounds__(1024) k_mulbench(uint32_t* out, uint32_t seed,
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// inversion latency: dependent chain of division-step inverses, all lanes or lane 0 only
+template <class P, bool LANE0>
+__global__ void __launch_bounds__(128) k_invbench(uint32_t* out, uint32_t seed, int iters) {
+  typedef Field<P> F;
+  Fe<P> a = F::one();
+  a.v[0] ^= (seed ^ threadIdx.x ^ (blockIdx.x << 8)) & 0xffffff;
+  if (!LANE0 || (threadIdx.x & 31) == 0) {
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) { a = F::inv_divsteps(a); a.v[0] ^= 5; }
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < P::N; k++) s ^= a.v[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 thread_local std::string g_err;
 #define CUT(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_err = std::string(#call) + ": " + cudaGetErrorString(e_); return MGB_E_CUDA; } } while (0)
 
@@ -160,10 +176,13 @@ int mgb_microbench(int device, int mode, int blocks_per_sm, int threads, int ite
       case 5: k_mulbench<Fr377, false><<<grid, threads>>>(d, 12345u, it); break;
       case 6: k_mulbench<Fp377, true><<<grid, threads>>>(d, 12345u, it); break;
       case 7: k_mulbench<Fr377, true><<<grid, threads>>>(d, 12345u, it); break;
+      case 8: k_invbench<Fp377, false><<<grid, threads>>>(d, 12345u, it); break;
+      case 9: k_invbench<Fp377, true><<<grid, threads>>>(d, 12345u, it); break;
       default: break;
     }
   };
-  if (mode < 0 || mode > 7) return MGB_E_INVALID;
+  if (mode < 0 || mode > 9) return MGB_E_INVALID;
+  if (mode >= 8 && threads > 128) return MGB_E_INVALID;
   launch(iters / 8 + 1);  // warm-up
   CUT(cudaDeviceSynchronize());
   CUT(cudaEventRecord(e0));
@@ -176,6 +195,7 @@ int mgb_microbench(int device, int mode, int blocks_per_sm, int threads, int ite
   double per_thread;
   if (mode <= 2) per_thread = 16.0 * 8 * iters;        // instructions per thread
   else if (mode == 3) per_thread = 16.0 * 8 * iters;   // wide MADs per thread
+  else if (mode >= 8) per_thread = (mode == 9 ? 1.0 / 32 : 1.0) * iters;   // inversions per thread
   else per_thread = 2.0 * iters;                        // field multiplications per thread
   *ops_per_s = per_thread * (double)grid * threads / (ms * 1e-3);
   if (ms_out) *ms_out = ms;
