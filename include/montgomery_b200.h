@@ -46,11 +46,15 @@ enum mgb_error {
 
 /* Per-call options; mirrors `{c?, useSafeAdditions?}` of msm-batched-affine.ts:74-77 and
  * `{c?}` of msm-basic.ts:35-41.  c = 0 picks the engine's window size.  `unsafe` is accepted for
- * API parity with `msmUnsafe`; the engine's additions are always complete, so it changes nothing. */
+ * API parity with `msmUnsafe`; the engine's additions are always complete, so it changes nothing.
+ * `projective` = 1 selects the reference's `msmProjective` variant on Weierstrass curves
+ * (src/parallel.ts:69-87: msm-basic over projective coordinates, no GLV, no batched-affine
+ * additions) -- an independent path used as a cross-check, as in src/msm.test.ts:73-82. */
 typedef struct mgb_opts {
   int c;
   int unsafe;
   int verbose;
+  int projective;
 } mgb_opts;
 
 /* Per-phase device times in milliseconds (CUDA events on the context's stream); the analogue of

@@ -83,15 +83,15 @@ class MsmEngine:
         return xy.reshape(n, self.curve.point_bytes), z
 
     # ---- msm
-    def _opts(self, c, unsafe):
-        return _native.MgbOpts(int(c or 0), int(bool(unsafe)), 0)
+    def _opts(self, c, unsafe, projective=False):
+        return _native.MgbOpts(int(c or 0), int(bool(unsafe)), 0, int(bool(projective)))
 
-    def msm(self, scalars, n=None, c=None, unsafe=False, device_ptr=None):
+    def msm(self, scalars, n=None, c=None, unsafe=False, device_ptr=None, projective=False):
         """scalars: (n, 32) uint8 host array (or bytes); or device_ptr = raw device pointer."""
         out = np.zeros(self.curve.point_bytes, dtype=np.uint8)
         is_zero = ctypes.c_int(0)
         tm = _native.MgbTiming()
-        opts = self._opts(c, unsafe)
+        opts = self._opts(c, unsafe, projective)
         if device_ptr is not None:
             self._check(self.lib.mgb_msm_device(self._h, ctypes.c_void_p(device_ptr), n, ctypes.byref(opts), _ptr(out),
                                                 ctypes.byref(is_zero), ctypes.byref(tm)))
@@ -177,6 +177,13 @@ class _Parallel:
             for row in log:
                 print(*row)
         return {"result": res, "log": log, "timing": tm}
+
+    def msmProjective(self, scalars, points, N, options=None):
+        """msm-basic over projective coordinates, no GLV (src/parallel.ts:69-87); Weierstrass curves only."""
+        assert self._m.curve.kind == "weierstrass"
+        options = options or {}
+        res, tm = points.engine.msm(scalars[:N] if isinstance(scalars, np.ndarray) else scalars, n=N, c=options.get("c"), projective=True)
+        return {"result": res, "log": _log_from_timing(tm), "timing": tm}
 
     def msmUnsafe(self, scalars, points, N, verbose=False, options=None):
         options = dict(options or {})

@@ -188,9 +188,37 @@ struct TwistedEdwardsPolicy {
   }
 };
 
+// The reference's `msmProjective` (src/parallel.ts:69-87): msm-basic over projective coordinates on a
+// Weierstrass curve -- no GLV, no batched-affine additions.  Same table and accumulator types as the
+// main policy, so it runs on the same context; kept as an independent path that the tests compare
+// against the batched-affine one, as src/msm.test.ts:73-82 does.
+template <class MAIN, int SCALAR_BITS>
+struct WeierstrassBasicPolicy : MAIN {
+  typedef typename MAIN::P FP;
+  typedef typename MAIN::F F;
+  typedef typename MAIN::G G;
+  typedef typename MAIN::acc acc;
+  typedef acc vpoint;
+  static constexpr int N = MAIN::N;
+  static constexpr bool USE_GLV = false;
+  static constexpr bool BATCH_AFFINE = false;
+  static constexpr int HALVES = 1;
+  static constexpr int MAG_LIMBS = 8;
+  static constexpr int MAG_BITS = SCALAR_BITS + 1;
+  static constexpr int V_LIMBS = 4 * N;
+  MGB_DEV static vpoint load_entry(const uint32_t* table, uint32_t idx, bool, bool negate) {
+    return G::from_affine(MAIN::load_entry(table, idx, false, negate));
+  }
+  MGB_DEV static vpoint load_v(const uint32_t* V, uint32_t slot) { return MAIN::ld_acc(V + (size_t)slot * V_LIMBS); }
+  MGB_DEV static void store_v(uint32_t* V, uint32_t slot, const vpoint& p) { MAIN::st_acc(V + (size_t)slot * V_LIMBS, p); }
+  MGB_DEV static acc add_v(const acc& a, const vpoint& p) { return G::add(a, p); }
+};
+
 typedef WeierstrassPolicy<Fp377, Bls12377Consts, Glv377, 127> CurveBls377;     // |k| < 2^126 (gen_constants.py self-check; reference maxBits = 126)
 typedef WeierstrassPolicy<FpPallas, PallasConsts, GlvPallas, 128> CurvePallas;  // |k| < 2^127
 typedef TwistedEdwardsPolicy<Fr377, Ed377Consts> CurveEd377;
+typedef WeierstrassBasicPolicy<CurveBls377, 253> CurveBls377Basic;
+typedef WeierstrassBasicPolicy<CurvePallas, 255> CurvePallasBasic;
 
 // ---------------------------------------------------------------- small multi-limb helpers (scalar side)
 template <int NA, int NB>

@@ -385,6 +385,10 @@ int msm_common(mgb_ctx* ctx, const void* scalars, bool dev, size_t n, const mgb_
   if (!ctx || !out_xy || (!scalars && n)) return fail(ctx, MGB_E_INVALID, "mgb_msm: NULL argument");
   if (n > ctx->npoints) return fail(ctx, ctx->npoints ? MGB_E_INVALID : MGB_E_STATE, "mgb_msm: n exceeds the number of points set");
   CU(ctx, cudaSetDevice(ctx->device));
+  if (opts && opts->projective) {
+    if (ctx->curve == MGB_BLS12_377_G1) return msm_impl<CurveBls377Basic>(ctx, scalars, dev, n, opts, out_xy, out_is_zero, tm);
+    if (ctx->curve == MGB_PALLAS) return msm_impl<CurvePallasBasic>(ctx, scalars, dev, n, opts, out_xy, out_is_zero, tm);
+  }
   DISPATCH(ctx, msm_impl, ctx, scalars, dev, n, opts, out_xy, out_is_zero, tm);
 }
 

@@ -184,3 +184,21 @@ def test_all_window_sizes(engines, label):
     for c in range(2, 23):
         res, tm = eng.msm(sc, n=n, c=c)
         assert res == exp, (label, c, tm)
+
+
+@pytest.mark.parametrize("label", ["bls12-377", "pallas"])
+def test_msm_projective_equals_batched_affine(label):
+    """src/msm.test.ts:73-82: `msmProjective` (msm-basic, no GLV) == `msmUnsafe` (batched affine + GLV),
+    through the reference-shaped host API."""
+    mod = m.Weierstrass.create(CURVES[label])
+    O = OracleCurve(label)
+    for logn in (0, 3, 7, 12):
+        n = 1 << logn
+        pts = mod.Parallel.randomPointsFast(n, seed=60 + logn)
+        sc = mod.Parallel.randomScalars(n, seed=61 + logn)
+        a = mod.Parallel.msmUnsafe(sc, pts, n)["result"]
+        b = mod.Parallel.msmProjective(sc, pts, n)["result"]
+        assert a == b, (label, logn)
+        if logn <= 7:
+            P = [None if q["isZero"] else (q["x"], q["y"]) for q in pts.toBigints()]
+            assert a == O.msm(inputs.scalars_to_ints(sc), P)
