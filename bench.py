@@ -103,6 +103,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def _measured_peak(key):
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return json.load(fh).get(key)
+    except Exception:
+        return None
+
+
 def dist_setup(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -245,6 +253,11 @@ def run_b200(args):
         "dominant_kernel": {"name": "k_batch_add", "phase_ms": acc_ms, "share_of_step": acc_ms / phases["total"],
                             "pairs_per_step": int(tm["n_pairs"]), "field_mults_per_s": 6.0 * tm["n_pairs"] / (acc_ms * 1e-3)},
     }
+    # HBM side of the path (north star: "HBM GB/s for the sort and gather phases"): the scatter kernel reads one
+    # 96-byte point per sorted entry (coalesced) and writes it to its bucket slot (scattered)
+    ent_bytes = 2 * 2 * curve.coord_bytes + 16      # point read + point write + digit/rank entry read + pair entry
+    hbm = {"sort_scatter_gbs": tm["n_pairs"] and (n * 2 * tm["K"] * ent_bytes) / (phases["sort"] * 1e-3) / 1e9,
+           "sort_ms": phases["sort"], "hbm_peak_gbs": _measured_peak("hbm_gbs")}
     line = {
         "metric": "msm_points_per_s", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -255,7 +268,7 @@ def run_b200(args):
         "msm_ms": ms_step, "phases_ms": phases, "result_x": hex(res["x"]),
         "e2e": {"value": e2e_value, "unit": "points/s", "ms_per_step": el_e2e / args.steps * 1e3,
                 "h2d_bytes_per_step": n * 32 * world, "d2h_bytes_per_step": (2 * curve.coord_bytes + 4) * world, "phases_ms": phases_e2e},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "hbm_phases": hbm,
     }
     if world == 1 and not args.no_cpu_baseline:
         ncpu = 1 << min(args.logn, args.cpu_logn)

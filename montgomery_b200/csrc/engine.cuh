@@ -703,6 +703,25 @@ __global__ void __launch_bounds__(128) k_tree_round(uint32_t ngroups, int NP, in
   CV::st_acc(a, CV::add(CV::ld_acc(a), CV::ld_acc(a + (size_t)half * CV::ACC_LIMBS)));
 }
 
+// the last tree levels of all groups in one launch: one warp per group, its <= 32 remaining partial
+// sums reduced with shuffles
+template <class CV>
+MGB_DEV typename CV::acc shfl_acc(const typename CV::acc& a, int src);
+
+template <class CV>
+__global__ void __launch_bounds__(128) k_tree_tail(uint32_t ngroups, int NP, int remaining, uint32_t* __restrict__ P) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (g >= ngroups) return;
+  uint32_t* base = P + (size_t)g * NP * CV::ACC_LIMBS;
+  typename CV::acc a = lane < remaining ? CV::ld_acc(base + (size_t)lane * CV::ACC_LIMBS) : CV::acc_zero();
+  _Pragma("unroll 1") for (int dl = 16; dl >= 1; dl >>= 1) {
+    typename CV::acc o = shfl_acc<CV>(a, lane + dl > 31 ? lane : lane + dl);
+    if (lane < dl && dl < remaining) a = CV::add(a, o);
+  }
+  if (lane == 0) CV::st_acc(base, a);
+}
+
 template <class CV>
 MGB_DEV typename CV::acc shfl_acc(const typename CV::acc& a, int src) {
   typename CV::acc r;

@@ -282,8 +282,13 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
     k_group_partial<CV><<<cdiv(ngroups_g * gm.NP, 128), 128, 0, sg>>>(pr, gm, w_begin, Kg, rounds, (const uint32_t*)ctx->V.p, (const uint32_t*)ctx->offs.p,
                                                                      (uint32_t*)ctx->redU[0].p);
     launches++;
-    for (int half = gm.NP / 2; half >= 1; half >>= 1) {
-      k_tree_round<CV><<<cdiv((size_t)ngroups_g * half, 128), 128, 0, sg>>>(ngroups_g, gm.NP, half, Pg);
+    int remaining = gm.NP;
+    for (; remaining > 32; remaining >>= 1) {
+      k_tree_round<CV><<<cdiv((size_t)ngroups_g * (remaining / 2), 128), 128, 0, sg>>>(ngroups_g, gm.NP, remaining / 2, Pg);
+      launches++;
+    }
+    if (remaining > 1) {
+      k_tree_tail<CV><<<cdiv((size_t)ngroups_g * 32, 128), 128, 0, sg>>>(ngroups_g, gm.NP, remaining, Pg);
       launches++;
     }
     k_window_sums<CV><<<Kg, 192, 0, sg>>>(pr, gm, w_begin, (const uint32_t*)ctx->redU[0].p, (uint32_t*)ctx->redW[0].p);
