@@ -12,7 +12,7 @@
  * throws or aborts across the ABI); `mgb_last_error` gives the message.  The caller owns all host
  * buffers; the context owns all device memory and its stream.  One in-flight call per context.
  * Byte formats are the reference's (src/parallel.ts:97-133,209-249): scalar = 32 bytes little
- * endian; Weierstrass point = x||y, each ceil(bits/8) bytes LE (2*48 for BLS12-377, 2*32 for
+ * endian; Weierstrass point = x||y, each ceil(bits/8) bytes LE (2*48 for BLS12-377 / BLS12-381, 2*32 for
  * Pallas); twisted-Edwards point = x||y, 2*32 bytes LE.  The result is the canonical affine point
  * (coordinates in [0,p), LE) plus an is_zero flag (Weierstrass infinity -> x = y = 0, flag 1, as
  * src/curve-affine.ts:369-371; twisted-Edwards neutral -> (0,1), flag 1).
@@ -32,7 +32,8 @@ typedef struct mgb_ctx mgb_ctx;
 enum mgb_curve {
   MGB_BLS12_377_G1 = 0,     /* src/concrete/bls12-377.params.ts, msm-batched-affine + GLV   */
   MGB_PALLAS = 1,           /* src/concrete/pasta.params.ts, msm-batched-affine + GLV       */
-  MGB_ED_ON_BLS12_377 = 2   /* src/concrete/ed-on-bls12-377.params.ts, msm-basic, no GLV    */
+  MGB_ED_ON_BLS12_377 = 2,  /* src/concrete/ed-on-bls12-377.params.ts, msm-basic, no GLV    */
+  MGB_BLS12_381_G1 = 3      /* src/concrete/bls12-381.params.ts, msm-batched-affine + GLV   */
 };
 
 enum mgb_error {
@@ -117,7 +118,7 @@ int mgb_combine_partials(mgb_ctx* ctx, const void* d_partials, int count,
 
 /* Test hooks for the field layer (the analogue of the Wasm exports checked by src/field.test.ts):
  * applies op elementwise on the device to n elements given as canonical LE bytes in/out.
- * field: 0 = BLS12-377 Fp, 1 = BLS12-377 Fr (= ed-on-377 base field), 2 = Pallas Fp.
+ * field: 0 = BLS12-377 Fp, 1 = BLS12-377 Fr (= ed-on-377 base field), 2 = Pallas Fp, 3 = BLS12-381 Fp.
  * op: 0 mul, 1 add, 2 sub, 3 inverse (Fermat), 4 square, 5 inverse (binary gcd), 6 negate,
  * 7 inverse (division steps, the one the MSM uses). */
 int mgb_field_op(int device, int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n);

@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmontgomery_b200.so")
 
-BLS12_377_G1, PALLAS, ED_ON_BLS12_377 = 0, 1, 2
+BLS12_377_G1, PALLAS, ED_ON_BLS12_377, BLS12_381_G1 = 0, 1, 2, 3
 
 
 class MgbOpts(ctypes.Structure):

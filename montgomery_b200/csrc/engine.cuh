@@ -217,8 +217,10 @@ struct WeierstrassBasicPolicy : MAIN {
 typedef WeierstrassPolicy<Fp377, Bls12377Consts, Glv377, 127> CurveBls377;     // |k| < 2^126 (gen_constants.py self-check; reference maxBits = 126)
 typedef WeierstrassPolicy<FpPallas, PallasConsts, GlvPallas, 128> CurvePallas;  // |k| < 2^127
 typedef TwistedEdwardsPolicy<Fr377, Ed377Consts> CurveEd377;
+typedef WeierstrassPolicy<Fp381, Bls12381Consts, Glv381, 128> CurveBls381;      // |k| < 2^127; fourth curve of src/msm.test.ts:31
 typedef WeierstrassBasicPolicy<CurveBls377, 253> CurveBls377Basic;
 typedef WeierstrassBasicPolicy<CurvePallas, 255> CurvePallasBasic;
+typedef WeierstrassBasicPolicy<CurveBls381, 255> CurveBls381Basic;
 
 // ---------------------------------------------------------------- small multi-limb helpers (scalar side)
 template <int NA, int NB>

@@ -16,14 +16,15 @@
 
 namespace mgb {
 
-// -p^-1 mod 2^32 (= 2^32 - 1 for every supported prime) as a RUNTIME value: if ptxas can see that the
-// Montgomery quotient digit is a plain negation it folds the sign into the modulus immediates and
-// splits every modulus product into IMAD.X + IMAD.HI.U32.X (6 issue cycles on the multiplier pipe)
-// instead of one IMAD.WIDE.U32.X (4 cycles) -- measured +24% on the whole multiplication.
+// -p^-1 mod 2^32 as a RUNTIME value, one entry per field (P::ID).  For the primes with p = 1 mod 2^32
+// the factor is 2^32 - 1, and if ptxas can see that the Montgomery quotient digit is a plain
+// negation it folds the sign into the modulus immediates and splits every modulus product into
+// IMAD.X + IMAD.HI.U32.X (6 issue cycles on the multiplier pipe) instead of one IMAD.WIDE.U32.X
+// (4 cycles) -- measured +24% on the whole multiplication.
 #ifdef MGB_HOST_EMU
-static const uint32_t c_mgb_minv = 0xffffffffu;
+static const uint32_t c_mgb_minv[4] = MGB_MINV_TABLE;
 #else
-static __device__ __constant__ uint32_t c_mgb_minv = 0xffffffffu;
+static __device__ __constant__ uint32_t c_mgb_minv[4] = MGB_MINV_TABLE;
 #endif
 
 template <class P>
@@ -35,7 +36,6 @@ template <class P>
 struct Field {
   static constexpr int N = P::N;
   typedef Fe<P> fe;
-  static_assert(P::M0 == 0xffffffffu, "engine assumes p = 1 mod 2^32");
   static_assert(N % 2 == 0, "even limb count");
 
   MGB_DEV static fe zero() { fe r; _Pragma("unroll") for (int i = 0; i < N; i++) r.v[i] = 0; return r; }
@@ -120,14 +120,19 @@ struct Field {
         }
         O[N - 1] = ptx::addc(O[N - 1], 0);
       }
-      const uint32_t m = E[0] * c_mgb_minv;
+      const uint32_t m = E[0] * c_mgb_minv[P::ID];
       _Pragma("unroll") for (int j = 0; j < N; j += 2) {
         O[j] = (j == 0) ? ptx::mad_lo_cc(P::mod(j + 1), m, O[j]) : ptx::madc_lo_cc(P::mod(j + 1), m, O[j]);
         O[j + 1] = ptx::madc_hi_cc(P::mod(j + 1), m, O[j + 1]);
       }
-      // E pair 0 += p[0]*m with p[0] = 1: limb 0 becomes 0, carry (E[0] != 0) goes into limb 1
-      (void)ptx::add_cc(E[0], 0xffffffffu);
-      E[1] = ptx::addc_cc(E[1], 0);
+      if constexpr (P::mod(0) == 1u) {
+        // E pair 0 += p[0]*m with p[0] = 1: limb 0 becomes 0, carry (E[0] != 0) goes into limb 1
+        (void)ptx::add_cc(E[0], 0xffffffffu);
+        E[1] = ptx::addc_cc(E[1], 0);
+      } else {
+        E[0] = ptx::mad_lo_cc(P::mod(0), m, E[0]);      // becomes 0 by the choice of m
+        E[1] = ptx::madc_hi_cc(P::mod(0), m, E[1]);
+      }
       _Pragma("unroll") for (int j = 2; j < N; j += 2) {
         E[j] = ptx::madc_lo_cc(P::mod(j), m, E[j]);
         E[j + 1] = ptx::madc_hi_cc(P::mod(j), m, E[j + 1]);
@@ -271,9 +276,9 @@ struct Field {
         int32_t md = (u & sd) + (v & se), me = (q & sd) + (r & se);
         int64_t cd = (int64_t)u * d[0] + (int64_t)v * e[0];
         int64_t ce = (int64_t)q * d[0] + (int64_t)r * e[0];
-        // p^-1 mod 2^30 = 1: pick md, me so that the low 30 bits cancel
-        md -= (int32_t)(((uint32_t)cd + (uint32_t)md) & (uint32_t)M30);
-        me -= (int32_t)(((uint32_t)ce + (uint32_t)me) & (uint32_t)M30);
+        // pick md, me so that the low 30 bits of cd + p*md (ce + p*me) cancel
+        md -= (int32_t)((P::MINV30 * (uint32_t)cd + (uint32_t)md) & (uint32_t)M30);
+        me -= (int32_t)((P::MINV30 * (uint32_t)ce + (uint32_t)me) & (uint32_t)M30);
         cd += (int64_t)P::mod30(0) * md;
         ce += (int64_t)P::mod30(0) * me;
         cd >>= 30; ce >>= 30;

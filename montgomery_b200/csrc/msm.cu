@@ -375,6 +375,7 @@ int msm_partial_impl(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n
     case MGB_BLS12_377_G1: return fn<CurveBls377>(__VA_ARGS__);             \
     case MGB_PALLAS: return fn<CurvePallas>(__VA_ARGS__);                   \
     case MGB_ED_ON_BLS12_377: return fn<CurveEd377>(__VA_ARGS__);           \
+    case MGB_BLS12_381_G1: return fn<CurveBls381>(__VA_ARGS__);             \
     default: return fail(ctx, MGB_E_INVALID, "unknown curve");              \
   }
 
@@ -382,6 +383,7 @@ size_t entry_bytes(int curve) {
   switch (curve) {
     case MGB_BLS12_377_G1: return CurveBls377::ENTRY_LIMBS * 4;
     case MGB_PALLAS: return CurvePallas::ENTRY_LIMBS * 4;
+    case MGB_BLS12_381_G1: return CurveBls381::ENTRY_LIMBS * 4;
     default: return CurveEd377::ENTRY_LIMBS * 4;
   }
 }
@@ -393,6 +395,7 @@ int msm_common(mgb_ctx* ctx, const void* scalars, bool dev, size_t n, const mgb_
   if (opts && opts->projective) {
     if (ctx->curve == MGB_BLS12_377_G1) return msm_impl<CurveBls377Basic>(ctx, scalars, dev, n, opts, out_xy, out_is_zero, tm);
     if (ctx->curve == MGB_PALLAS) return msm_impl<CurvePallasBasic>(ctx, scalars, dev, n, opts, out_xy, out_is_zero, tm);
+    if (ctx->curve == MGB_BLS12_381_G1) return msm_impl<CurveBls381Basic>(ctx, scalars, dev, n, opts, out_xy, out_is_zero, tm);
   }
   DISPATCH(ctx, msm_impl, ctx, scalars, dev, n, opts, out_xy, out_is_zero, tm);
 }
@@ -403,7 +406,7 @@ extern "C" {
 
 int mgb_create(mgb_ctx** out, int curve, int device, size_t max_points) {
   if (!out) return fail(nullptr, MGB_E_INVALID, "mgb_create: out is NULL");
-  if (curve < 0 || curve > 2) return fail(nullptr, MGB_E_INVALID, "mgb_create: unknown curve");
+  if (curve < 0 || curve > 3) return fail(nullptr, MGB_E_INVALID, "mgb_create: unknown curve");
   if (max_points == 0 || max_points > (1ull << 28)) return fail(nullptr, MGB_E_INVALID, "mgb_create: max_points must be in [1, 2^28]");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -466,6 +469,7 @@ size_t mgb_partial_bytes(const mgb_ctx* ctx) {
   switch (ctx->curve) {
     case MGB_BLS12_377_G1: return CurveBls377::ACC_LIMBS * 4;
     case MGB_PALLAS: return CurvePallas::ACC_LIMBS * 4;
+    case MGB_BLS12_381_G1: return CurveBls381::ACC_LIMBS * 4;
     default: return CurveEd377::ACC_LIMBS * 4;
   }
 }

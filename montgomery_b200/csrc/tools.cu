@@ -138,9 +138,9 @@ thread_local std::string g_err;
 extern "C" {
 
 int mgb_field_op(int device, int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
-  if (!a || !b || !out || field < 0 || field > 2) return MGB_E_INVALID;
+  if (!a || !b || !out || field < 0 || field > 3) return MGB_E_INVALID;
   CUT(cudaSetDevice(device));
-  const int N = field == 0 ? 12 : 8;
+  const int N = (field == 0 || field == 3) ? 12 : 8;
   size_t bytes = n * N * 4;
   uint32_t *da, *db, *dout;
   CUT(cudaMalloc(&da, bytes)); CUT(cudaMalloc(&db, bytes)); CUT(cudaMalloc(&dout, bytes));
@@ -149,7 +149,8 @@ int mgb_field_op(int device, int field, int op, const uint8_t* a, const uint8_t*
   unsigned grid = (unsigned)((n + 127) / 128);
   if (field == 0) k_field_op<Fp377><<<grid, 128>>>(op, (uint32_t)n, da, db, dout);
   else if (field == 1) k_field_op<Fr377><<<grid, 128>>>(op, (uint32_t)n, da, db, dout);
-  else k_field_op<FpPallas><<<grid, 128>>>(op, (uint32_t)n, da, db, dout);
+  else if (field == 2) k_field_op<FpPallas><<<grid, 128>>>(op, (uint32_t)n, da, db, dout);
+  else k_field_op<Fp381><<<grid, 128>>>(op, (uint32_t)n, da, db, dout);
   CUT(cudaGetLastError());
   CUT(cudaMemcpy(out, dout, bytes, cudaMemcpyDeviceToHost));
   cudaFree(da); cudaFree(db); cudaFree(dout);

@@ -23,10 +23,11 @@ def carr(name, x, n):
             % (name, n, body))
 
 
-def field_struct(name, p, n):
+def field_struct(name, p, n, fid):
     R = 1 << (32 * n)
     assert 2 * p < R
     out = "struct %s {\n" % name
+    out += "  static constexpr int ID = %d;   // index into the run-time table of Montgomery factors\n" % fid
     out += "  static constexpr int N = %d;\n" % n
     out += "  static constexpr int BITS = %d;\n" % p.bit_length()
     out += "  static constexpr uint32_t M0 = 0x%08xu;  // -p^-1 mod 2^32\n" % ((-pow(p, -1, 1 << 32)) % (1 << 32))
@@ -37,7 +38,7 @@ def field_struct(name, p, n):
     out += carr("pm2", p - 2, n)          # Fermat exponent
     n30 = (p.bit_length() + 1 + 29) // 30 + (1 if (p.bit_length() + 1) % 30 == 0 else 0)
     n30 = max(n30, (32 * n + 29) // 30)   # must also hold any packed 32n-bit value
-    assert p % (1 << 30) == 1             # modulus^-1 mod 2^30 = 1 (used by the divsteps inverse)
+    out += "  static constexpr uint32_t MINV30 = 0x%08xu;  // p^-1 mod 2^30 (division-step inverse)\n" % pow(p, -1, 1 << 30)
     body = ",".join("0x%08x" % ((p >> (30 * i)) & 0x3FFFFFFF) for i in range(n30))
     out += "  static constexpr int N30 = %d;  // signed 30-bit limbs of the divsteps inverse\n" % n30
     out += ("  __host__ __device__ static constexpr int32_t mod30(int i) { constexpr int32_t t[%d] = {%s}; return t[i]; }\n" % (n30, body))
@@ -109,9 +110,18 @@ def main():
            0x9A20DF36571AC3CD906B256080BA8454453C177AAF3131BB50A67BF1A806781)
 
     out = "// GENERATED by montgomery_b200/gen_constants.py -- do not edit.\n#pragma once\n#include <cstdint>\nnamespace mgb {\n\n"
-    out += field_struct("Fp377", p377, 12)
-    out += field_struct("Fr377", q377, 8)     # scalar field of BLS12-377 = base field of ed-on-BLS12-377
-    out += field_struct("FpPallas", ppal, 8)
+    p381 = 0x1A0111EA397FE69A4B1BA7B6434BACD764774B84F38512BF6730D2A0F6B0F6241EABFFFEB153FFFFB9FEFFFFFFFFAAAB
+    q381 = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+    lam381 = 0xD201000000010000 ** 2 - 1                                  # src/concrete/bls12-381.params.ts:24
+    beta381 = 0x1A0111EA397FE699EC02408663D4DE85AA0D857D89759AD4897D29650FB85F9B409427EB4F49FFFD8BFD00000000AAAC
+    g381 = (0x17F1D3A73197D7942695638C4FA9AC0FC3688C4F9774B905A14E3A3F171BAC586C55E83FF97A1AEFFB3AF00ADB22C6BB,
+            0x08B3F481E3AAA0F1A09E30ED741D8AE4FCF5E095D5D00AF600DB18CB2C04B3EDD03CC744A2888AE40CAA232946C5E7E1)
+    out += field_struct("Fp377", p377, 12, 0)
+    out += field_struct("Fr377", q377, 8, 1)     # scalar field of BLS12-377 = base field of ed-on-BLS12-377
+    out += field_struct("FpPallas", ppal, 8, 2)
+    out += field_struct("Fp381", p381, 12, 3)
+    out += "// -p^-1 mod 2^32 per field ID (loaded at run time, see field.cuh)\n"
+    out += "#define MGB_MINV_TABLE {%s}\n\n" % ", ".join("0x%08xu" % ((-pow(pp, -1, 1 << 32)) % (1 << 32)) for pp in (p377, q377, ppal, p381))
 
     def mont(x, p, n):
         return x * (1 << (32 * n)) % p
@@ -129,6 +139,12 @@ def main():
     out += carr("gx", mont(gpal[0], ppal, 8), 8)
     out += carr("gy", mont(gpal[1], ppal, 8), 8)
     out += "  static constexpr int SCALAR_BITS = 255;\n};\n\n"
+    out += "struct Bls12381Consts {\n"
+    out += carr("beta", mont(beta381, p381, 12), 12)
+    out += carr("b3", mont(3 * 4, p381, 12), 12)
+    out += carr("gx", mont(g381[0], p381, 12), 12)
+    out += carr("gy", mont(g381[1], p381, 12), 12)
+    out += "  static constexpr int SCALAR_BITS = 255;\n};\n\n"
     out += "struct Ed377Consts {\n"
     out += carr("k", mont(2 * 3021, q377, 8), 8)     # k = 2d
     out += carr("gx", mont(ged[0], q377, 8), 8)
@@ -139,12 +155,14 @@ def main():
     out += s
     s, infopal = glv_struct("GlvPallas", qpal, lampal)
     out += s
+    s, info381 = glv_struct("Glv381", q381, lam381)
+    out += s
     out += "}  // namespace mgb\n"
     sys.stdout.write(out)
     # self-check of the decomposition bound (stderr)
     import random
     rnd = random.Random(1)
-    for (q, lam, info, nm) in ((q377, lam377, info377, "377"), (qpal, lampal, infopal, "pallas")):
+    for (q, lam, info, nm) in ((q377, lam377, info377, "377"), (qpal, lampal, infopal, "pallas"), (q381, lam381, info381, "381")):
         v00, v01, v10, v11, g0, g1, sg0, sg1 = info
         mx = 0
         for _ in range(20000):

@@ -7,7 +7,7 @@ import subprocess
 import numpy as np
 
 from .glv import GlvScalar
-from .params import BLS12_377, ED_ON_BLS12_377, PALLAS
+from .params import BLS12_377, BLS12_381, ED_ON_BLS12_377, PALLAS
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "libmsm_cpu.so")
@@ -56,7 +56,8 @@ def _glv_struct(prm):
     return s
 
 
-_CURVES = {"bls12-377": (0, BLS12_377, 6, 48), "pallas": (1, PALLAS, 4, 32), "ed-on-bls12-377": (2, ED_ON_BLS12_377, 4, 32)}
+_CURVES = {"bls12-377": (0, BLS12_377, 6, 48), "pallas": (1, PALLAS, 4, 32), "ed-on-bls12-377": (2, ED_ON_BLS12_377, 4, 32),
+           "bls12-381": (3, BLS12_381, 6, 48)}
 
 
 def msm(label, scalars_bytes: np.ndarray, points_bytes: np.ndarray, n: int, threads: int = 0, c: int = 0):

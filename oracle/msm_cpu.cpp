@@ -832,7 +832,7 @@ struct ref_glv_consts {
   int32_t m_bits, k_bits, max_bits;
 };
 
-// curve: 0 = BLS12-377 G1, 1 = Pallas, 2 = ed-on-BLS12-377.  mod/beta: little-endian 64-bit limbs.
+// curve: 0 = BLS12-377 G1, 1 = Pallas, 2 = ed-on-BLS12-377, 3 = BLS12-381 G1.  mod/beta: little-endian 64-bit limbs.
 // Returns 0; *ms_out = wall time of the MSM proper (inputs already converted, like the reference's timing).
 int ref_msm(int curve, const uint64_t* mod, const uint64_t* beta_or_d, const ref_glv_consts* glv,
             const uint8_t* scalars, const uint8_t* points, size_t n, int threads, int c,
@@ -849,6 +849,7 @@ int ref_msm(int curve, const uint64_t* mod, const uint64_t* beta_or_d, const ref
     case 0: return msm_weierstrass<6>(mod, beta_or_d, 377, g, scalars, points, n, threads, c, out_xy, out_zero, ms_out);
     case 1: return msm_weierstrass<4>(mod, beta_or_d, 255, g, scalars, points, n, threads, c, out_xy, out_zero, ms_out);
     case 2: return msm_te<4>(mod, beta_or_d[0], 251, scalars, points, n, threads, c, out_xy, out_zero, ms_out);
+    case 3: return msm_weierstrass<6>(mod, beta_or_d, 381, g, scalars, points, n, threads, c, out_xy, out_zero, ms_out);
   }
   return -1;
 }
@@ -861,6 +862,7 @@ int ref_known_dlog_points(int curve, const uint64_t* mod, const uint64_t* d_or_n
     case 0: gen_points_w<6>(mod, gx, gy, 48, seed, n, threads, out_xy); return 0;
     case 1: gen_points_w<4>(mod, gx, gy, 32, seed, n, threads, out_xy); return 0;
     case 2: gen_points_te<4>(mod, d_or_null[0], gx, gy, seed, n, threads, out_xy); return 0;
+    case 3: gen_points_w<6>(mod, gx, gy, 48, seed, n, threads, out_xy); return 0;
   }
   return -1;
 }

@@ -16,7 +16,7 @@ import random
 import sys
 
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
-from oracle.params import BLS12_377, PALLAS, ED_ON_BLS12_377  # noqa: E402
+from oracle.params import BLS12_377, BLS12_381, PALLAS, ED_ON_BLS12_377  # noqa: E402
 from oracle.weierstrass import AffineCurve, ProjectiveCurve  # noqa: E402
 from oracle.twisted_edwards import TwistedEdwardsCurve  # noqa: E402
 from oracle.msm import msm, msm_naive  # noqa: E402
@@ -28,7 +28,7 @@ PREFIXES = [1, 2, 3, 7, 16, 48]
 def main():
     rnd = random.Random(0x6D6F6E74)
     out = {}
-    for prm in (BLS12_377, PALLAS):
+    for prm in (BLS12_377, PALLAS, BLS12_381):
         A, P = AffineCurve(prm), ProjectiveCurve(prm)
         pts = [A.point_from_x(rnd.randrange(prm.p)) for _ in range(NPTS)]
         assert all(A.is_on_curve(Q) and A.is_in_subgroup(Q) for Q in pts[:4])

@@ -1,12 +1,12 @@
 """Shared test helpers: oracle curve objects and conversions (tests may import oracle/)."""
 import numpy as np
 
-from oracle.params import BLS12_377, ED_ON_BLS12_377, PALLAS
+from oracle.params import BLS12_377, BLS12_381, ED_ON_BLS12_377, PALLAS
 from oracle.twisted_edwards import TwistedEdwardsCurve
 from oracle.weierstrass import AffineCurve, ProjectiveCurve
 from oracle.msm import msm as oracle_msm
 
-ORACLE_PARAMS = {"bls12-377": BLS12_377, "pallas": PALLAS, "ed-on-bls12-377": ED_ON_BLS12_377}
+ORACLE_PARAMS = {"bls12-377": BLS12_377, "pallas": PALLAS, "ed-on-bls12-377": ED_ON_BLS12_377, "bls12-381": BLS12_381}
 
 
 class OracleCurve:

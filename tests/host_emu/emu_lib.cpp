@@ -71,11 +71,13 @@ extern "C" {
 void emu_fe_op(int field, int op, uint32_t* out, const uint32_t* a, const uint32_t* b) {
   if (field == 0) fe_op<Fp377>(op, out, a, b);
   else if (field == 1) fe_op<Fr377>(op, out, a, b);
-  else fe_op<FpPallas>(op, out, a, b);
+  else if (field == 2) fe_op<FpPallas>(op, out, a, b);
+  else fe_op<Fp381>(op, out, a, b);
 }
 void emu_w_op(int curve, int op, uint32_t* out, const uint32_t* a, const uint32_t* b) {
   if (curve == 0) w_op<Fp377>(op, out, a, b);
-  else w_op<FpPallas>(op, out, a, b);
+  else if (curve == 1) w_op<FpPallas>(op, out, a, b);
+  else w_op<Fp381>(op, out, a, b);
 }
 void emu_te_op(int op, uint32_t* out, const uint32_t* a, const uint32_t* b) { te_op<Fr377, Ed377Consts>(op, out, a, b); }
 }

@@ -6,10 +6,10 @@ import random
 import numpy as np
 import pytest
 
-from oracle.params import BLS12_377, PALLAS
+from oracle.params import BLS12_377, BLS12_381, PALLAS
 
 pytestmark = pytest.mark.gpu
-FIELDS = [(BLS12_377.p, 12), (BLS12_377.q, 8), (PALLAS.p, 8)]
+FIELDS = [(BLS12_377.p, 12), (BLS12_377.q, 8), (PALLAS.p, 8), (BLS12_381.p, 12)]
 
 
 def _run(lib, fid, op, a_vals, b_vals, nlimbs):
@@ -23,7 +23,7 @@ def _run(lib, fid, op, a_vals, b_vals, nlimbs):
     return [int.from_bytes(out[i * nb:(i + 1) * nb].tobytes(), "little") for i in range(len(a_vals))]
 
 
-@pytest.mark.parametrize("fid", [0, 1, 2])
+@pytest.mark.parametrize("fid", [0, 1, 2, 3])
 def test_field_ops_gpu(fid):
     from montgomery_b200 import _native
     lib = _native.lib()

@@ -13,7 +13,8 @@ from oracle.params import KAT_BLS12_377_POINT, KAT_ED377_POINT
 from tests.helpers import OracleCurve, points_to_bytes, scalars_to_bytes
 
 pytestmark = pytest.mark.gpu
-CURVES = {"bls12-377": m.curves.BLS12_377, "pallas": m.curves.PALLAS, "ed-on-bls12-377": m.curves.ED_ON_BLS12_377}
+CURVES = {"bls12-377": m.curves.BLS12_377, "pallas": m.curves.PALLAS, "ed-on-bls12-377": m.curves.ED_ON_BLS12_377,
+          "bls12-381": m.curves.BLS12_381}
 
 
 @pytest.fixture(scope="module")
@@ -150,7 +151,7 @@ def test_degenerate_inputs(engines, label):
 
 
 @pytest.mark.parametrize("label,logn", [("bls12-377", 14), ("bls12-377", 16), ("pallas", 16), ("ed-on-bls12-377", 16),
-                                        ("bls12-377", 20), ("pallas", 18), ("ed-on-bls12-377", 18)])
+                                        ("bls12-377", 20), ("pallas", 18), ("ed-on-bls12-377", 18), ("bls12-381", 16)])
 def test_closed_form_large(engines, label, logn):
     """Known-dlog points P_i = a_i G: result must equal [(sum s_i a_i) mod q] G."""
     n = 1 << logn
@@ -186,7 +187,7 @@ def test_all_window_sizes(engines, label):
         assert res == exp, (label, c, tm)
 
 
-@pytest.mark.parametrize("label", ["bls12-377", "pallas"])
+@pytest.mark.parametrize("label", ["bls12-377", "pallas", "bls12-381"])
 def test_msm_projective_equals_batched_affine(label):
     """src/msm.test.ts:73-82: `msmProjective` (msm-basic, no GLV) == `msmUnsafe` (batched affine + GLV),
     through the reference-shaped host API."""

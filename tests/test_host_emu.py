@@ -8,12 +8,12 @@ import subprocess
 
 import pytest
 
-from oracle.params import BLS12_377, ED_ON_BLS12_377, PALLAS
+from oracle.params import BLS12_377, BLS12_381, ED_ON_BLS12_377, PALLAS
 from oracle.twisted_edwards import TwistedEdwardsCurve
 from oracle.weierstrass import AffineCurve
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-FIELDS = [(BLS12_377.p, 12), (BLS12_377.q, 8), (PALLAS.p, 8)]
+FIELDS = [(BLS12_377.p, 12), (BLS12_377.q, 8), (PALLAS.p, 8), (BLS12_381.p, 12)]
 
 
 @pytest.fixture(scope="module")
@@ -35,7 +35,7 @@ def I(a, n, k):
     return [sum(int(a[j * n + i]) << (32 * i) for i in range(n)) for j in range(k)]
 
 
-@pytest.mark.parametrize("fid", [0, 1, 2])
+@pytest.mark.parametrize("fid", [0, 1, 2, 3])
 def test_field_ops(emu, fid):
     p, n = FIELDS[fid]
     R = 1 << (32 * n)
@@ -66,7 +66,7 @@ def test_field_ops(emu, fid):
         assert I(out, n, 1)[0] == 0
 
 
-@pytest.mark.parametrize("cid,prm,n", [(0, BLS12_377, 12), (1, PALLAS, 8)], ids=["bls12-377", "pallas"])
+@pytest.mark.parametrize("cid,prm,n", [(0, BLS12_377, 12), (1, PALLAS, 8), (2, BLS12_381, 12)], ids=["bls12-377", "pallas", "bls12-381"])
 def test_weierstrass_ops(emu, cid, prm, n):
     p = prm.p
     R = 1 << (32 * n)

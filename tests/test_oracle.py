@@ -5,12 +5,12 @@ import pytest
 
 from oracle.glv import GlvScalar, signed_digits, window_size
 from oracle.msm import msm, msm_naive
-from oracle.params import BLS12_377, ED_ON_BLS12_377, KAT_BLS12_377_POINT, KAT_ED377_POINT, PALLAS
+from oracle.params import BLS12_377, BLS12_381, ED_ON_BLS12_377, KAT_BLS12_377_POINT, KAT_ED377_POINT, PALLAS
 from oracle.twisted_edwards import TwistedEdwardsCurve
 from oracle.weierstrass import AffineCurve, ProjectiveCurve
 
 
-@pytest.mark.parametrize("prm", [BLS12_377, PALLAS], ids=lambda p: p.label)
+@pytest.mark.parametrize("prm", [BLS12_377, PALLAS, BLS12_381], ids=lambda p: p.label)
 def test_generator_on_curve_and_subgroup(prm):
     # src/bigint/curves.test.ts:20-51
     A = AffineCurve(prm)
@@ -48,7 +48,7 @@ def test_kat_ed377():
     assert T.to_affine(msm(T, [2, T.q - 1], [pt, pt])) == (x, y)
 
 
-@pytest.mark.parametrize("label", ["bls12-377", "pallas", "ed-on-bls12-377"])
+@pytest.mark.parametrize("label", ["bls12-377", "pallas", "ed-on-bls12-377", "bls12-381"])
 def test_msm_identities(label):
     # src/bigint/msm.test.ts:18-59
     rnd = random.Random(7)
@@ -56,7 +56,7 @@ def test_msm_identities(label):
         C = TwistedEdwardsCurve(ED_ON_BLS12_377)
         eq, zero = C.is_equal, C.zero
     else:
-        C = ProjectiveCurve({"bls12-377": BLS12_377, "pallas": PALLAS}[label])
+        C = ProjectiveCurve({"bls12-377": BLS12_377, "pallas": PALLAS, "bls12-381": BLS12_381}[label])
         eq, zero = C.is_equal, C.zero
     q = C.q
     n = 12
@@ -76,7 +76,7 @@ def test_msm_identities(label):
 
 
 def test_golden_vectors_match_oracle(golden):
-    for label, C in (("bls12-377", ProjectiveCurve(BLS12_377)), ("pallas", ProjectiveCurve(PALLAS))):
+    for label, C in (("bls12-377", ProjectiveCurve(BLS12_377)), ("pallas", ProjectiveCurve(PALLAS)), ("bls12-381", ProjectiveCurve(BLS12_381))):
         g = golden[label]
         pts = [(int(x, 16), int(y, 16), 1) for x, y in g["points"]]
         sc = [int(s, 16) for s in g["scalars"]]
@@ -92,7 +92,7 @@ def test_golden_vectors_match_oracle(golden):
     assert [hex(r[0]), hex(r[1])] == g["results"]["16"]
 
 
-@pytest.mark.parametrize("prm", [BLS12_377, PALLAS], ids=lambda p: p.label)
+@pytest.mark.parametrize("prm", [BLS12_377, PALLAS, BLS12_381], ids=lambda p: p.label)
 def test_glv_decomposition(prm):
     # src/scalar-glv.ts:92-103 : s0 + s1*lambda = s (mod q), halves below maxBits
     g = GlvScalar(prm.q, prm.lam)
@@ -125,7 +125,7 @@ def test_cpu_restatement_matches_python_oracle(golden):
     import numpy as np
     from oracle import cpu_ref
     from tests.helpers import OracleCurve, points_to_bytes, scalars_to_bytes
-    for label, cb in (("bls12-377", 48), ("pallas", 32), ("ed-on-bls12-377", 32)):
+    for label, cb in (("bls12-377", 48), ("pallas", 32), ("ed-on-bls12-377", 32), ("bls12-381", 48)):
         g = golden[label]
         pts = [(int(x, 16), int(y, 16)) for x, y in g["points"]]
         sc = [int(s, 16) for s in g["scalars"]]
