@@ -203,3 +203,19 @@ def test_msm_projective_equals_batched_affine(label):
         if logn <= 7:
             P = [None if q["isZero"] else (q["x"], q["y"]) for q in pts.toBigints()]
             assert a == O.msm(inputs.scalars_to_ints(sc), P)
+
+
+@pytest.mark.parametrize("label", ["bls12-377", "ed-on-bls12-377"])
+def test_extreme_bucket_skew(engines, label):
+    """All scalars equal: every point of a window lands in ONE bucket, so the bucket trees run at full
+    depth (14+ rounds) instead of the usual log2(average).  Expected: s * sum(P_i) = s * (sum a_i) G."""
+    n = 1 << 14
+    eng = engines(label, n)
+    O = OracleCurve(label)
+    eng.random_points(n, seed=4321)
+    a = inputs.known_dlogs(4321, n)
+    for s in (7, O.q - 2):
+        sc = scalars_to_bytes([s] * n)
+        res, tm = eng.msm(sc, n=n)
+        assert tm["rounds"] >= 14
+        assert res == O.result_of(O.scale(s * sum(int(v) for v in a), O.G)), (label, s, tm)
