@@ -66,15 +66,19 @@ int ensure(mgb_ctx* ctx, DevBuf& b, size_t bytes) {
 }
 #define ENS(ctx, buf, bytes) do { int r_ = ensure(ctx, buf, bytes); if (r_) return r_; } while (0)
 
-// Window size: log2(n) - 4, i.e. an average bucket of ~64 half-scalars (GLV) -- enough for the
-// batched additions to amortise, few enough buckets for the reduction.  A sparse top window (few
-// digit bits) is balanced by sub-bucket spreading (MsmParams::top_sub), not avoided.  The reference's
-// own table (msm-common.ts:25-41) is tuned for 16 CPU threads and is not used here.
+// Window size.  Large inputs: log2(n) - 4, i.e. an average bucket of ~64 half-scalars (GLV) -- enough
+// for the batched additions to amortise their inversions, few enough buckets for the reduction
+// (measured at 2^20: c = 15 / 16 / 17 -> 10.8 / 9.1 / 9.9 ms).  Small inputs are bound by the latency
+// of a round, not by throughput, so they take log2(n) - 2: smaller buckets, two rounds fewer
+// (measured at 2^16: c = 12 / 14 -> 2.65 / 2.41 ms).  A sparse top window is balanced by sub-bucket
+// spreading (MsmParams::top_sub), not avoided.  The reference's own table (msm-common.ts:25-41) is
+// tuned for 16 CPU threads and is not used here.
 int default_window(int mag_bits, size_t n) {
   int lg = 0;
   while (((size_t)1 << lg) < n) lg++;
   (void)mag_bits;
-  return std::max(5, std::min(lg - 4, 22));
+  const int c = lg >= 18 ? lg - 4 : lg - 2;
+  return std::max(5, std::min(c, 22));
 }
 
 inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
@@ -250,7 +254,7 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
         const uint64_t warps = (uint64_t)ctx->sm_count * MINB * 4;
         // tile shape: big tiles of E pairs per lane, about 1.5 per resident warp, then tiles of E/4
         int E = EMAX;
-        while (E > 4 && est < warps * 32ull * E) E >>= 1;
+        while (E > 4 && 10 * est < 9 * warps * 32ull * E) E >>= 1;   // measured: largest tile with >= 0.9 tiles per resident warp
         uint32_t n_big = (uint32_t)(warps + warps / 2);
         bool block_tiles = false;
         if (const char* ev = getenv("MGB_DEBUG_E")) {   // tuning aid: comma-separated E per round, negative = block-level tiles
