@@ -80,6 +80,10 @@ struct WeierstrassPolicy {
     if (negate) r.y = F::neg(r.y);
     return r;
   }
+  // x coordinate of the point a reference word (index | endo | negate) stands for
+  MGB_DEV static Fe<FP> load_entry_x(const uint32_t* table, uint32_t ref) {
+    return ldg_fe<FP>(table + (size_t)(ref & REF_IDX) * ENTRY_LIMBS + ((ref & REF_ENDO) ? 2 * N : 0));
+  }
   MGB_DEV static vpoint load_v(const uint32_t* V, uint32_t slot) {
     const uint32_t* e = V + (size_t)slot * V_LIMBS;
     vpoint r; r.x = ld_fe<FP>(e); r.y = ld_fe<FP>(e + N); return r;
@@ -349,6 +353,7 @@ __global__ void __launch_bounds__(256) k_digits(MsmParams pr, const uint32_t* __
 static constexpr int SCAN_T = 1024;
 static constexpr int SCAN_ITEMS = 4;
 static constexpr int SCAN_TILE = SCAN_T * SCAN_ITEMS;
+static constexpr int SCAN_ROUNDS = 16;   // tree rounds whose exact size the scan reports
 
 MGB_DEV uint32_t block_excl_scan(uint32_t val, uint32_t* total_out, uint32_t* sm /* 32 words */) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -368,19 +373,34 @@ MGB_DEV uint32_t block_excl_scan(uint32_t val, uint32_t* total_out, uint32_t* sm
   return base + x - val;
 }
 
-// in: counts[n]; out: offs[n] (exclusive, tile-local), tile_sums[tile]; also global max of counts
+// in: counts[n]; out: offs[n] (exclusive, tile-local), tile_sums[tile]; also global max of counts.
+// Every bucket is given an EVEN number of slots (count rounded up), so that the round-0 pairs of the
+// in-place bucket trees are the aligned slot pairs (2q, 2q+1) and need no pair list.
 static __global__ void __launch_bounds__(SCAN_T) k_scan_tiles(const uint32_t* __restrict__ counts, uint32_t* __restrict__ offs,
-                                                       uint32_t* __restrict__ tile_sums, uint32_t n, uint32_t* __restrict__ maxcount) {
+                                                       uint32_t* __restrict__ tile_sums, uint32_t n, uint32_t* __restrict__ maxcount,
+                                                       uint32_t* __restrict__ round_pairs /* [r] += additions of tree round r, r < SCAN_ROUNDS */) {
   __shared__ uint32_t sm[32];
   uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-  uint32_t v[SCAN_ITEMS], sum = 0, mx = 0;
-  _Pragma("unroll") for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = (base + k < n) ? counts[base + k] : 0; sum += v[k]; mx = max(mx, v[k]); }
+  uint32_t v[SCAN_ITEMS], sum = 0, mx = 0, rp[SCAN_ROUNDS];
+  _Pragma("unroll") for (int r = 0; r < SCAN_ROUNDS; r++) rp[r] = 0;
+  _Pragma("unroll") for (int k = 0; k < SCAN_ITEMS; k++) {
+    uint32_t cnt = (base + k < n) ? counts[base + k] : 0;
+    mx = max(mx, cnt);
+    // a bucket of cnt elements has ceil((cnt - 2^r) / 2^(r+1)) additions in round r of its tree
+    _Pragma("unroll") for (int r = 0; r < SCAN_ROUNDS; r++) rp[r] += (cnt + (1u << r) - 1) >> (r + 1);
+    v[k] = (cnt + 1) & ~1u;
+    sum += v[k];
+  }
   uint32_t total;
   uint32_t ex = block_excl_scan(sum, &total, sm);
   _Pragma("unroll") for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) offs[base + k] = ex; ex += v[k]; }
   if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
   mx = __reduce_max_sync(0xffffffffu, mx);
   if ((threadIdx.x & 31) == 0 && mx) atomicMax(maxcount, mx);
+  _Pragma("unroll") for (int r = 0; r < SCAN_ROUNDS; r++) {
+    uint32_t t = __reduce_add_sync(0xffffffffu, rp[r]);
+    if ((threadIdx.x & 31) == 0 && t) atomicAdd(round_pairs + r, t);
+  }
 }
 // single block: exclusive scan of tile_sums[ntiles] in place, total -> *grand
 static __global__ void __launch_bounds__(SCAN_T) k_scan_sums(uint32_t* __restrict__ tile_sums, uint32_t ntiles, uint32_t* __restrict__ grand) {
@@ -405,20 +425,27 @@ static __global__ void __launch_bounds__(SCAN_T) k_scan_add(uint32_t* __restrict
 }
 
 // ---------------------------------------------------------------- k_scatter
-// Counting-sort scatter that MATERIALISES the points in bucket order, like the reference's
-// sortPoints (msm-batched-affine.ts:456-502): V[slot] = the point entry (endomorphism / negation
-// applied), slot = offs[bucket] + rank.  Consecutive threads read consecutive table entries
-// (coalesced); the 96-byte writes are scattered.  All later stages then address V by slot only.
+// Counting-sort scatter (the reference's sortPoints, msm-batched-affine.ts:456-502, copies the points
+// into bucket order).  Here a sorted slot only records WHICH point it stands for:
+//     refs[slot] = point index | endo << 30 | negate << 31,      slot = offs[bucket] + rank,
+// and round 0 of the bucket trees gathers its operands straight from the point table and writes the
+// sums to V[slot]: one write and one read of every sorted point (192 B per entry, ~1 ms at 2^20) are
+// never done.  Buckets start at even slots (k_scan_tiles), so round 0 pairs slot 2q with 2q+1; the
+// last element of an odd-sized bucket gets REF_EMPTY as its partner and is simply copied by round 0.
+// With V != nullptr (no round follows: every bucket has at most one element) the point is
+// materialised here instead.
 //
 // The in-place bucket tree (msm-batched-affine.ts:243-263): in round r the element at local index j
 // (multiple of 2^(r+1)) absorbs the element at j + 2^r if that is inside the bucket of size n.  The
 // rounds in which a slot is a left operand are r = 0 .. life-1 with
 //     life = min(ctz(j), floor(log2(n - j - 1)) + 1)        (0 if j is the last element),
-// so each pair-list entry carries (slot, life) and no bucket lookup is needed later.
+// kept per even slot (life8[slot / 2]); the pair lists of rounds >= 1 carry (slot, life), so no
+// bucket lookup is needed later.
 struct PairEnt {
   uint32_t slot;
   uint32_t life;
 };
+static constexpr uint32_t REF_EMPTY = 0xffffffffu;
 
 MGB_DEV void emit_pair(bool active, PairEnt ent, PairEnt* __restrict__ pairs, uint32_t* __restrict__ npairs) {
   uint32_t m = __ballot_sync(0xffffffffu, active);
@@ -433,35 +460,32 @@ MGB_DEV void emit_pair(bool active, PairEnt ent, PairEnt* __restrict__ pairs, ui
 
 template <class CV>
 __global__ void __launch_bounds__(256) k_scatter(MsmParams pr, int w_begin, int Kg, const uint32_t* __restrict__ ent_bucket, const uint32_t* __restrict__ ent_rank,
-                                                 const uint32_t* __restrict__ offs, const uint32_t* __restrict__ table, uint32_t* __restrict__ V,
-                                                 PairEnt* __restrict__ pairs, uint32_t* __restrict__ npairs) {
+                                                 const uint32_t* __restrict__ offs, const uint32_t* __restrict__ counts, const uint32_t* __restrict__ table,
+                                                 uint32_t* __restrict__ V, uint32_t* __restrict__ refs, uint8_t* __restrict__ life8) {
   // thread -> (half h, window w of the group [w_begin, w_begin + Kg), point i)
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool active = false;
-  PairEnt ent = {0u, 0u};
-  if (t < (size_t)pr.n * CV::HALVES * Kg) {
-    uint32_t el = (uint32_t)(t / pr.n), i = (uint32_t)(t - (size_t)el * pr.n);
-    uint32_t h = el / (uint32_t)Kg, w = (uint32_t)w_begin + el % (uint32_t)Kg;
-    size_t pos = (size_t)(h * pr.K + w) * pr.n + i;
-    uint32_t b = ent_bucket[pos];
-    if (b != NO_BUCKET) {
-      uint32_t rk = ent_rank[pos];
-      const bool endo = h != 0;
-      uint32_t o = offs[b], n = offs[b + 1] - o, j = rk & ~REF_NEG;
-      uint32_t slot = o + j;
-      CV::store_v(V, slot, CV::load_entry(table, i, endo, (rk & REF_NEG) != 0));
-      uint32_t rest = n - j - 1;                          // elements after this one
-      uint32_t life = 0;
-      if (rest) {
-        life = 32 - __clz(rest);                          // floor(log2(rest)) + 1
-        if (j) life = min(life, (uint32_t)(__ffs(j) - 1));
-      }
-      ent.slot = slot;
-      ent.life = life;
-      active = life > 0;
-    }
+  if (t >= (size_t)pr.n * CV::HALVES * Kg) return;
+  uint32_t el = (uint32_t)(t / pr.n), i = (uint32_t)(t - (size_t)el * pr.n);
+  uint32_t h = el / (uint32_t)Kg, w = (uint32_t)w_begin + el % (uint32_t)Kg;
+  size_t pos = (size_t)(h * pr.K + w) * pr.n + i;
+  uint32_t b = ent_bucket[pos];
+  if (b == NO_BUCKET) return;
+  uint32_t rk = ent_rank[pos];
+  const bool endo = h != 0;
+  uint32_t n = counts[b], j = rk & ~REF_NEG;
+  uint32_t slot = offs[b] + j;
+  if (V) { CV::store_v(V, slot, CV::load_entry(table, i, endo, (rk & REF_NEG) != 0)); return; }
+  refs[slot] = i | (endo ? REF_ENDO : 0u) | (rk & REF_NEG);
+  if (j & 1) return;
+  uint32_t rest = n - j - 1;                          // elements after this one
+  uint32_t life = 0;
+  if (rest) {
+    life = 32 - __clz(rest);                          // floor(log2(rest)) + 1
+    if (j) life = min(life, (uint32_t)(__ffs(j) - 1));
+  } else {
+    refs[slot + 1] = REF_EMPTY;                       // padding slot of an odd-sized bucket
   }
-  emit_pair(active, ent, pairs, npairs);
+  life8[slot >> 1] = (uint8_t)life;
 }
 
 // ---------------------------------------------------------------- k_batch_add (Weierstrass)
@@ -490,16 +514,35 @@ MGB_DEV void prefetch_point(const uint32_t* V, uint32_t slot) {
   asm volatile("prefetch.global.L1 [%0];" ::"l"(p + CV::V_LIMBS * 4 - 4));
 }
 
-template <class CV, int EMAX, int MINB, bool INL, bool BLOCK>
+template <class CV>
+MGB_DEV void prefetch_entry(const uint32_t* table, uint32_t ref) {
+  // the operand is 2N contiguous limbs: x | y, or y | beta*x for the endomorphism image
+  const char* p = reinterpret_cast<const char*>(table + (size_t)(ref & REF_IDX) * CV::ENTRY_LIMBS + ((ref & REF_ENDO) ? CV::N : 0));
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 2 * CV::N * 4 - 4));
+}
+template <class CV>
+MGB_DEV typename CV::vpoint load_ref(const uint32_t* table, uint32_t ref) {
+  return CV::load_entry(table, ref & REF_IDX, (ref & REF_ENDO) != 0, (ref & REF_NEG) != 0);
+}
+
+// FIRST = true is round 0: pair q is the aligned slot pair (2q, 2q+1) of the window group's slot range
+// [offs[b_begin], offs[b_end]); its operands are the table points refs[2q], refs[2q+1] (see
+// k_scatter; REF_EMPTY = no partner, the element is copied); V is only written.  No pair list is read.
+template <class CV, int EMAX, int MINB, bool INL, bool BLOCK, bool FIRST>
 __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ V, const PairEnt* __restrict__ pairs,
                                                          const uint32_t* __restrict__ npairs_ptr, int r, int E_big, uint32_t n_big,
                                                          PairEnt* __restrict__ pairs_out, uint32_t* __restrict__ npairs_out,
-                                                         uint32_t* __restrict__ tile_counter) {
+                                                         uint32_t* __restrict__ tile_counter,
+                                                         const uint32_t* __restrict__ refs, const uint8_t* __restrict__ life8,
+                                                         const uint32_t* __restrict__ table, const uint32_t* __restrict__ offs,
+                                                         uint32_t b_begin, uint32_t b_end) {
   typedef typename CV::P FP;
   typedef typename CV::F F;
   typedef typename CV::G G;
   typedef Fe<FP> fe;
-  const uint32_t npairs = *npairs_ptr;
+  const uint32_t q0 = FIRST ? offs[b_begin] >> 1 : 0u;
+  const uint32_t npairs = FIRST ? (offs[b_end] >> 1) - q0 : *npairs_ptr;
   // E (<= EMAX) pairs per lane: large tiles amortise the inversion, small ones keep every warp busy
   // in the late rounds that have few pairs
   // BLOCK = false: a tile is 32*E pairs owned by one warp, warps are independent.
@@ -541,20 +584,43 @@ __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ 
     // software pipeline: slot indices two pairs ahead, x coordinates one pair ahead, so the loads of
     // pair e+1 are in flight during the multiplication of pair e
     const uint32_t base = tile_base + (BLOCK ? (uint32_t)warp * 32u * (uint32_t)E : 0u) + lane;
-    uint32_t s1 = (base < npairs) ? pairs[base].slot : NO_BUCKET;
-    uint32_t s2 = (base + 32 < npairs) ? pairs[base + 32].slot : NO_BUCKET;
+    auto slot_at = [&](int e) -> uint32_t { return (e < E && base + (uint32_t)e * 32u < npairs) ? pairs[base + (uint32_t)e * 32u].slot : NO_BUCKET; };
+    auto refs_at = [&](int e) -> uint2 {   // FIRST: the two point references of pair e (coalesced across the warp)
+      return (e < E && base + (uint32_t)e * 32u < npairs) ? reinterpret_cast<const uint2*>(refs)[q0 + base + (uint32_t)e * 32u] : make_uint2(REF_EMPTY, REF_EMPTY);
+    };
+    uint32_t s1 = NO_BUCKET, s2 = NO_BUCKET;
+    uint2 r1 = make_uint2(REF_EMPTY, REF_EMPTY), r2 = r1;   // FIRST: references of pairs e+1, e+2
+    uint32_t lra[FIRST ? EMAX : 1], lrb[FIRST ? EMAX : 1];  // FIRST: kept for the backward pass
     fe xa_n = F::zero(), xb_n = F::zero();
-    if (s1 != NO_BUCKET) { xa_n = CV::load_v_x(V, s1); xb_n = CV::load_v_x(V, s1 + step); }
-    _Pragma("unroll 1") for (int e = 0; e < E; e++) {
-      const uint32_t s = s1;
-      const fe xa = xa_n, xb = xb_n;
-      s1 = s2;
-      s2 = (e + 2 < E && base + (e + 2) * 32 < npairs) ? pairs[base + (e + 2) * 32].slot : NO_BUCKET;
+    if constexpr (FIRST) {
+      r1 = refs_at(0); r2 = refs_at(1);
+      if (r1.x != REF_EMPTY) xa_n = CV::load_entry_x(table, r1.x);
+      if (r1.y != REF_EMPTY) xb_n = CV::load_entry_x(table, r1.y);
+    } else {
+      s1 = slot_at(0); s2 = slot_at(1);
       if (s1 != NO_BUCKET) { xa_n = CV::load_v_x(V, s1); xb_n = CV::load_v_x(V, s1 + step); }
+    }
+    _Pragma("unroll 1") for (int e = 0; e < E; e++) {
+      const fe xa = xa_n, xb = xb_n;
+      uint32_t s = s1;
+      if constexpr (FIRST) {
+        lra[e] = r1.x; lrb[e] = r1.y;
+        s = (r1.x != REF_EMPTY && r1.y != REF_EMPTY) ? 0u : NO_BUCKET;   // a real addition?
+        r1 = r2;
+        r2 = refs_at(e + 2);
+        if (r1.x != REF_EMPTY) xa_n = CV::load_entry_x(table, r1.x);
+        if (r1.y != REF_EMPTY) xb_n = CV::load_entry_x(table, r1.y);
+      } else {
+        s1 = s2;
+        s2 = slot_at(e + 2);
+        if (s1 != NO_BUCKET) { xa_n = CV::load_v_x(V, s1); xb_n = CV::load_v_x(V, s1 + step); }
+      }
       fe d = F::one();
       if (s != NO_BUCKET) {
         if (!G::prepare_x(xa, xb, d)) {  // rare: an operand is infinity or the x coordinates coincide
-          typename CV::vpoint A = CV::load_v(V, s), B = CV::load_v(V, s + step);
+          typename CV::vpoint A, B;
+          if constexpr (FIRST) { A = load_ref<CV>(table, lra[e]); B = load_ref<CV>(table, lrb[e]); }
+          else { A = CV::load_v(V, s); B = CV::load_v(V, s + step); }
           (void)G::add_prepare(A, B, d);
         }
       }
@@ -597,26 +663,46 @@ __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ 
     if (lane > 0) u = F::mul(u, left);
     if (lane < 31) u = F::mul(u, right);
     // pair entries two iterations ahead, operands prefetched to L1 one iteration ahead
-    PairEnt nxt = {NO_BUCKET, 0u}, nn = {NO_BUCKET, 0u};
-    if (base + (E - 1) * 32 < npairs) nxt = pairs[base + (E - 1) * 32];
-    if (E >= 2 && base + (E - 2) * 32 < npairs) nn = pairs[base + (E - 2) * 32];
+    auto ent_at = [&](int e) -> PairEnt {
+      PairEnt x = {NO_BUCKET, 0u};
+      if (e >= 0 && base + (uint32_t)e * 32u < npairs) {
+        if constexpr (FIRST) { x.slot = 2u * (q0 + base + (uint32_t)e * 32u); x.life = life8[q0 + base + (uint32_t)e * 32u]; }
+        else x = pairs[base + (uint32_t)e * 32u];
+      }
+      return x;
+    };
+    PairEnt nxt = ent_at(E - 1), nn = ent_at(E - 2);
     _Pragma("unroll 1") for (int e = E - 1; e >= 0; e--) {
       const PairEnt ent = nxt;
       const bool valid = ent.slot != NO_BUCKET;
       nxt = nn;
-      nn.slot = NO_BUCKET;
-      if (e >= 2 && base + (e - 2) * 32 < npairs) nn = pairs[base + (e - 2) * 32];
+      nn = ent_at(e - 2);
       if (nxt.slot != NO_BUCKET) {
-        prefetch_point<CV>(V, nxt.slot);
-        prefetch_point<CV>(V, nxt.slot + step);
+        if constexpr (FIRST) {
+          prefetch_entry<CV>(table, lra[e - 1]);
+          if (lrb[e - 1] != REF_EMPTY) prefetch_entry<CV>(table, lrb[e - 1]);
+        } else {
+          prefetch_point<CV>(V, nxt.slot);
+          prefetch_point<CV>(V, nxt.slot + step);
+        }
       }
       fe inv_den = INL ? F::mul_inl(u, pre[e]) : F::mul(u, pre[e]);
       if (valid) {
-        typename CV::vpoint A = CV::load_v(V, ent.slot), B = CV::load_v(V, ent.slot + step);
-        fe d;
-        int kind = G::add_prepare(A, B, d);
-        u = INL ? F::mul_inl(u, d) : F::mul(u, d);
-        CV::store_v(V, ent.slot, G::template add_finish<INL>(kind, A, B, inv_den));
+        typename CV::vpoint A, B;
+        bool lone = false;
+        if constexpr (FIRST) {
+          A = load_ref<CV>(table, lra[e]);
+          lone = lrb[e] == REF_EMPTY;
+          if (!lone) B = load_ref<CV>(table, lrb[e]);
+        } else { A = CV::load_v(V, ent.slot); B = CV::load_v(V, ent.slot + step); }
+        if (lone) {
+          CV::store_v(V, ent.slot, A);              // no partner: denominator was 1
+        } else {
+          fe d;
+          int kind = G::add_prepare(A, B, d);
+          u = INL ? F::mul_inl(u, d) : F::mul(u, d);
+          CV::store_v(V, ent.slot, G::template add_finish<INL>(kind, A, B, inv_den));
+        }
       }
       emit_pair(valid && (uint32_t)(r + 1) < ent.life, ent, pairs_out, npairs_out);
     }
@@ -624,19 +710,32 @@ __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ 
 }
 
 // ---------------------------------------------------------------- k_pair_add (twisted Edwards: no inversion needed)
-template <class CV>
+template <class CV, bool FIRST>
 __global__ void __launch_bounds__(256) k_pair_add(uint32_t* __restrict__ V, const PairEnt* __restrict__ pairs,
                                                   const uint32_t* __restrict__ npairs_ptr, int r,
-                                                  PairEnt* __restrict__ pairs_out, uint32_t* __restrict__ npairs_out) {
-  const uint32_t npairs = *npairs_ptr;
+                                                  PairEnt* __restrict__ pairs_out, uint32_t* __restrict__ npairs_out,
+                                                  const uint32_t* __restrict__ refs, const uint8_t* __restrict__ life8,
+                                                  const uint32_t* __restrict__ table, const uint32_t* __restrict__ offs,
+                                                  uint32_t b_begin, uint32_t b_end) {
+  const uint32_t q0 = FIRST ? offs[b_begin] >> 1 : 0u;
+  const uint32_t npairs = FIRST ? (offs[b_end] >> 1) - q0 : *npairs_ptr;
   const uint32_t step = 1u << r;
   const uint32_t nround = (npairs + 31) & ~31u;   // whole warps iterate together (ballot in emit_pair)
   for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nround; idx += gridDim.x * blockDim.x) {
     const bool valid = idx < npairs;
     PairEnt ent = {0u, 0u};
     if (valid) {
-      ent = pairs[idx];
-      CV::store_v(V, ent.slot, CV::add(CV::load_v(V, ent.slot), CV::load_v(V, ent.slot + step)));
+      if constexpr (FIRST) {
+        const uint2 rr = reinterpret_cast<const uint2*>(refs)[q0 + idx];
+        ent.slot = 2u * (q0 + idx);
+        ent.life = life8[q0 + idx];
+        typename CV::vpoint A = load_ref<CV>(table, rr.x);
+        if (rr.y != REF_EMPTY) A = CV::add(A, load_ref<CV>(table, rr.y));
+        CV::store_v(V, ent.slot, A);
+      } else {
+        ent = pairs[idx];
+        CV::store_v(V, ent.slot, CV::add(CV::load_v(V, ent.slot), CV::load_v(V, ent.slot + step)));
+      }
     }
     emit_pair(valid && (uint32_t)(r + 1) < ent.life, ent, pairs_out, npairs_out);
   }
@@ -661,7 +760,7 @@ struct ReduceGeom {
 
 template <class CV>
 __global__ void __launch_bounds__(128) k_group_partial(MsmParams pr, ReduceGeom gm, int w_begin, int Kg, int rounds, const uint32_t* __restrict__ V,
-                                                       const uint32_t* __restrict__ offs, uint32_t* __restrict__ P) {
+                                                       const uint32_t* __restrict__ offs, const uint32_t* __restrict__ counts, uint32_t* __restrict__ P) {
   // thread -> (window w, digit d, value v, chunk ch)
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t total = (uint32_t)Kg * gm.D * 32 * gm.NP;
@@ -688,7 +787,7 @@ __global__ void __launch_bounds__(128) k_group_partial(MsmParams pr, ReduceGeom 
       uint32_t low = m & ((1u << sh) - 1), high = m >> sh;
       uint32_t idx = (high << (sh + wdt)) | (v << sh) | low;
       uint32_t b = w * pr.L + idx;
-      uint32_t o = offs[b], n = offs[b + 1] - o;
+      uint32_t o = offs[b], n = counts[b];
       for (uint32_t q = 0; q < n; q += stride) acc = CV::add_v(acc, CV::load_v(V, o + q));
     }
   }

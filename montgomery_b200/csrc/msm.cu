@@ -30,7 +30,7 @@ struct mgb_ctx {
   cudaStream_t aux[3] = {};          // extra streams: window groups are pipelined against each other
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {};
   cudaEvent_t ev[EV_COUNT] = {};
-  DevBuf table, scalars, ent_bucket, ent_rank, counts, offs, tile_sums, pairs, pairs2, V, redU[2], redW[2], misc, acc_out, out_xy, stage;
+  DevBuf table, scalars, ent_bucket, ent_rank, counts, offs, tile_sums, pairs, pairs2, V, refs, life8, redU[2], redW[2], misc, acc_out, out_xy, stage;
   uint32_t* h_pinned = nullptr;  // [0..31] out xy limbs + flag, [64..] misc readback
   int sm_count = 148;
   std::string err;
@@ -178,17 +178,19 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   ENS(ctx, ctx->offs, ((size_t)pr.nbuckets + 1) * 4);
   const uint32_t ntiles = cdiv(pr.nbuckets, SCAN_TILE);
   ENS(ctx, ctx->tile_sums, (size_t)ntiles * 4);
-  ENS(ctx, ctx->pairs, ((size_t)pr.nent / 2 + 8) * sizeof(PairEnt));
-  ENS(ctx, ctx->pairs2, ((size_t)pr.nent / 4 + 8) * sizeof(PairEnt));
-  ENS(ctx, ctx->V, ((size_t)pr.nent + 1) * CV::V_LIMBS * 4);
+  // every non-empty bucket occupies an even number of slots (k_scan_tiles)
+  const size_t max_slots = std::min<size_t>((size_t)pr.nent + pr.nbuckets, 2 * (size_t)pr.nent) + 2;
+  ENS(ctx, ctx->pairs, ((size_t)pr.nent / 4 + 8) * sizeof(PairEnt));     // pair lists of rounds 1, 3, ..
+  ENS(ctx, ctx->pairs2, ((size_t)pr.nent / 8 + 8) * sizeof(PairEnt));    // rounds 2, 4, ..
+  ENS(ctx, ctx->V, max_slots * CV::V_LIMBS * 4);
   ENS(ctx, ctx->redU[0], (size_t)ngroups * gm.NP * CV::ACC_LIMBS * 4);
   ENS(ctx, ctx->redW[0], (size_t)pr.K * CV::ACC_LIMBS * 4);
-  ENS(ctx, ctx->misc, 512 * 4);
-  // misc: [0] grand total, [1] max bucket, [8 + 64 g + r] pair count of round r of window group g,
+  ENS(ctx, ctx->misc, 1024 * 4);
+  // misc: [0] grand total of (padded) slots, [1] max bucket, [512 + r] exact number of additions of tree round r, [8 + 64 g + r] pair count of round r of window group g,
   //       [264 + 64 g + r] tile counter of that round
   uint32_t* misc = (uint32_t*)ctx->misc.p;
   CU(ctx, cudaMemsetAsync(ctx->counts.p, 0, ((size_t)pr.nbuckets + 1) * 4, st));
-  CU(ctx, cudaMemsetAsync(misc, 0, 512 * 4, st));
+  CU(ctx, cudaMemsetAsync(misc, 0, 1024 * 4, st));
 
   // ---- digits + histogram
   k_digits<CV><<<cdiv(n, 256), 256, 0, st>>>(pr, d_scalars, (uint32_t*)ctx->ent_bucket.p, (uint32_t*)ctx->ent_rank.p, (uint32_t*)ctx->counts.p);
@@ -197,29 +199,43 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   CU(ctx, cudaEventRecord(ctx->ev[EV_DIGITS], st));
 
   // ---- bucket offsets; the totals come back to the host to size the rounds
-  k_scan_tiles<<<ntiles, SCAN_T, 0, st>>>((const uint32_t*)ctx->counts.p, (uint32_t*)ctx->offs.p, (uint32_t*)ctx->tile_sums.p, pr.nbuckets, misc + 1);
+  k_scan_tiles<<<ntiles, SCAN_T, 0, st>>>((const uint32_t*)ctx->counts.p, (uint32_t*)ctx->offs.p, (uint32_t*)ctx->tile_sums.p, pr.nbuckets, misc + 1, misc + 512);
   k_scan_sums<<<1, SCAN_T, 0, st>>>((uint32_t*)ctx->tile_sums.p, ntiles, misc);
   k_scan_add<<<ntiles, SCAN_T, 0, st>>>((uint32_t*)ctx->offs.p, (const uint32_t*)ctx->tile_sums.p, pr.nbuckets, misc);
   launches += 3;
   CU(ctx, cudaGetLastError());
   CU(ctx, cudaMemcpyAsync(ctx->h_pinned + 64, misc, 8, cudaMemcpyDeviceToHost, st));
   CU(ctx, cudaMemcpyAsync(ctx->h_pinned + 66, (uint32_t*)ctx->counts.p + pr.nbuckets, 4, cudaMemcpyDeviceToHost, st));
+  CU(ctx, cudaMemcpyAsync(ctx->h_pinned + 68, misc + 512, SCAN_ROUNDS * 4, cudaMemcpyDeviceToHost, st));
   CU(ctx, cudaStreamSynchronize(st));
   const uint32_t nslots = ctx->h_pinned[64], maxcount = ctx->h_pinned[65];
+  const uint32_t* round_pairs = ctx->h_pinned + 68;
   if (ctx->h_pinned[66]) return fail(ctx, MGB_E_INVALID, "internal: a half-scalar exceeded its bound");
+  (void)nslots;
 
-  // Depth of the bucket trees.  Full depth is ceil(log2(max bucket)); for the usual near-uniform
-  // digit distribution the last rounds hold a handful of pairs each and cost a full batch latency,
-  // so they are left to the reduction kernel (which sums whatever a bucket has left).  Skewed
-  // inputs run the full depth.
+  // Depth of the bucket trees.  Full depth is ceil(log2(max bucket)).  A round costs at least one
+  // batch latency (~0.2 ms: prefix products, inversion, back-substitution) however few additions it
+  // holds, while an element left in a bucket costs the reduction ~2 ns; so the rounds stop where
+  // they would hold fewer than ~100 K additions (measured at 2^18 / 2^20 / 2^22: 5 / 7 / 7 rounds),
+  // and the reduction sums whatever a bucket has left.  Buckets far above the typical size (skewed
+  // scalars) force more rounds: at most 16 elements of any bucket are left to the reduction.
   int r_full = 0;
   while ((1u << r_full) < maxcount) r_full++;
-  const uint32_t nonempty_bound = std::min<uint32_t>(pr.nbuckets, std::max<uint32_t>(nslots, 1));
-  const uint32_t avg = (nslots + nonempty_bound - 1) / nonempty_bound;
-  int r_typ = 0;
-  while ((1u << r_typ) < avg) r_typ++;
-  int rounds = (r_full <= r_typ + 4) ? std::min(r_full, r_typ) : r_full;
+  int rounds = 0;
+  const uint32_t min_pairs = CV::BATCH_AFFINE ? 100000u : 20000u;   // rounds without an inversion have a much lower floor
+  while (rounds < r_full && rounds < SCAN_ROUNDS && round_pairs[rounds] >= min_pairs) rounds++;
+  rounds = std::max(rounds, r_full - 4);
   if (opts && opts->verbose > 1) rounds = r_full;
+  if (const char* ev = getenv("MGB_DEBUG_NROUNDS")) rounds = std::max(0, std::min(r_full, atoi(ev)));   // tuning aid
+  // round 0 gathers its operands from the point table (see k_scatter); without a round 0 the sorted
+  // points are materialised by the scatter as the reduction expects
+  const bool fuse = rounds > 0;
+  if (fuse) { ENS(ctx, ctx->refs, max_slots * 4); ENS(ctx, ctx->life8, max_slots / 2 + 1); }
+  uint32_t* refs = fuse ? (uint32_t*)ctx->refs.p : nullptr;
+  uint8_t* life8 = fuse ? (uint8_t*)ctx->life8.p : nullptr;
+  const uint32_t* table = (const uint32_t*)ctx->table.p;
+  const uint32_t* offs = (const uint32_t*)ctx->offs.p;
+  const uint32_t* counts = (const uint32_t*)ctx->counts.p;
 
   // ---- window groups, pipelined on separate streams: every round ends with a tail in which few
   // tiles are left (and the late rounds and the reduction are latency-bound throughout); the
@@ -234,13 +250,15 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
     if (g > 0) CU(ctx, cudaStreamWaitEvent(sg, ctx->ev_fork, 0));
     const int w_begin = (int)((long long)pr.K * g / G), w_end = (int)((long long)pr.K * (g + 1) / G), Kg = w_end - w_begin;
     const size_t nent_g = (size_t)n * CV::HALVES * Kg;
-    PairEnt* pl[2] = {(PairEnt*)ctx->pairs.p + pair_off, (PairEnt*)ctx->pairs2.p + pair2_off};
-    pair_off += nent_g / 2 + 1;
-    pair2_off += nent_g / 4 + 1;
+    // round r reads pl[r & 1] and writes pl[(r & 1) ^ 1]; round 0 reads no list
+    PairEnt* pl[2] = {(PairEnt*)ctx->pairs2.p + pair2_off, (PairEnt*)ctx->pairs.p + pair_off};
+    pair_off += nent_g / 4 + 1;
+    pair2_off += nent_g / 8 + 1;
+    const uint32_t b_begin = (uint32_t)w_begin * pr.L, b_end = (uint32_t)w_end * pr.L;
     uint32_t* cnt = misc + 8 + 64 * g;
     uint32_t* tcnt = misc + 264 + 64 * g;
     k_scatter<CV><<<cdiv(nent_g, 256), 256, 0, sg>>>(pr, w_begin, Kg, (const uint32_t*)ctx->ent_bucket.p, (const uint32_t*)ctx->ent_rank.p,
-                                                    (const uint32_t*)ctx->offs.p, (const uint32_t*)ctx->table.p, (uint32_t*)ctx->V.p, pl[0], cnt);
+                                                    offs, counts, table, fuse ? nullptr : (uint32_t*)ctx->V.p, refs, life8);
     launches++;
     if (g == 0) CU(ctx, cudaEventRecord(ctx->ev[EV_SORT], st));
     for (int r = 0; r < rounds; r++) {
@@ -249,8 +267,8 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
       if constexpr (CV::BATCH_AFFINE) {
         constexpr int EMAX = 64, MINB = 4;
         constexpr bool INL = false;
-        // expected pairs of this round ~ slots of the group / 2^(r+1)
-        const uint64_t est = ((uint64_t)nslots * Kg / pr.K) >> (r + 1);
+        // additions of this round (exact over all windows, from the scan)
+        const uint64_t est = (r < SCAN_ROUNDS ? (uint64_t)round_pairs[r] : 0) * Kg / pr.K;
         const uint64_t warps = (uint64_t)ctx->sm_count * MINB * 4;
         // tile shape: big tiles of E pairs per lane, about 1.5 per resident warp, then tiles of E/4
         int E = EMAX;
@@ -263,12 +281,18 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
           if (q && k == r && atoi(q) != 0) { int v = atoi(q); block_tiles = v < 0; E = std::min(EMAX, std::abs(v)); }
         }
         if (const char* ev = getenv("MGB_DEBUG_NBIG")) n_big = (uint32_t)(atof(ev) * warps);
-        if (block_tiles)
-          k_batch_add<CV, EMAX, MINB, INL, true><<<ctx->sm_count * MINB, 128, 0, sg>>>((uint32_t*)ctx->V.p, pin, cnt + r, r, E, n_big / 4, pout, cnt + r + 1, tcnt + r);
+        if (r == 0)
+          k_batch_add<CV, EMAX, MINB, INL, false, true><<<ctx->sm_count * MINB, 128, 0, sg>>>((uint32_t*)ctx->V.p, nullptr, nullptr, r, E, n_big, pout, cnt + r + 1, tcnt + r,
+                                                                                           refs, life8, table, offs, b_begin, b_end);
+        else if (block_tiles)
+          k_batch_add<CV, EMAX, MINB, INL, true, false><<<ctx->sm_count * MINB, 128, 0, sg>>>((uint32_t*)ctx->V.p, pin, cnt + r, r, E, n_big / 4, pout, cnt + r + 1, tcnt + r,
+                                                                                           nullptr, nullptr, nullptr, nullptr, 0, 0);
         else
-          k_batch_add<CV, EMAX, MINB, INL, false><<<ctx->sm_count * MINB, 128, 0, sg>>>((uint32_t*)ctx->V.p, pin, cnt + r, r, E, n_big, pout, cnt + r + 1, tcnt + r);
+          k_batch_add<CV, EMAX, MINB, INL, false, false><<<ctx->sm_count * MINB, 128, 0, sg>>>((uint32_t*)ctx->V.p, pin, cnt + r, r, E, n_big, pout, cnt + r + 1, tcnt + r,
+                                                                                            nullptr, nullptr, nullptr, nullptr, 0, 0);
       } else {
-        k_pair_add<CV><<<ctx->sm_count * 8, 256, 0, sg>>>((uint32_t*)ctx->V.p, pin, cnt + r, r, pout, cnt + r + 1);
+        if (r == 0) k_pair_add<CV, true><<<ctx->sm_count * 8, 256, 0, sg>>>((uint32_t*)ctx->V.p, nullptr, nullptr, r, pout, cnt + r + 1, refs, life8, table, offs, b_begin, b_end);
+        else k_pair_add<CV, false><<<ctx->sm_count * 8, 256, 0, sg>>>((uint32_t*)ctx->V.p, pin, cnt + r, r, pout, cnt + r + 1, nullptr, nullptr, nullptr, nullptr, 0, 0);
       }
       launches += 1;
       if (G == 1 && getenv("MGB_DEBUG_ROUNDS")) {   // tuning aid: per-round wall time (synchronises!)
@@ -283,7 +307,7 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
     // bucket reduction of the group's windows (digit-decomposed weights, see engine.cuh)
     const uint32_t ngroups_g = (uint32_t)Kg * gm.D * 32;
     uint32_t* Pg = (uint32_t*)ctx->redU[0].p + (size_t)w_begin * gm.D * 32 * gm.NP * CV::ACC_LIMBS;
-    k_group_partial<CV><<<cdiv(ngroups_g * gm.NP, 128), 128, 0, sg>>>(pr, gm, w_begin, Kg, rounds, (const uint32_t*)ctx->V.p, (const uint32_t*)ctx->offs.p,
+    k_group_partial<CV><<<cdiv(ngroups_g * gm.NP, 128), 128, 0, sg>>>(pr, gm, w_begin, Kg, rounds, (const uint32_t*)ctx->V.p, offs, counts,
                                                                      (uint32_t*)ctx->redU[0].p);
     launches++;
     int remaining = gm.NP;
@@ -322,11 +346,14 @@ int finish_timing(mgb_ctx* ctx, mgb_timing* tm) {
   tm->reduce = el(EV_ACC, EV_REDUCE);
   tm->final_sum = el(EV_REDUCE, EV_FINAL);
   tm->total = el(EV_START, EV_FINAL);
-  uint32_t h[256];
-  CU(ctx, cudaMemcpy(h, (uint32_t*)ctx->misc.p + 8, sizeof(h), cudaMemcpyDeviceToHost));
-  uint64_t s = 0;
+  uint32_t h[264];
+  CU(ctx, cudaMemcpy(h, (uint32_t*)ctx->misc.p, sizeof(h), cudaMemcpyDeviceToHost));
+  uint64_t s = 0;      // round 0 reads no pair list; its additions are counted by the scan
+  CU(ctx, cudaMemcpy(h, (uint32_t*)ctx->misc.p + 512, 4, cudaMemcpyDeviceToHost));
+  if (tm->rounds > 0) s = h[0];
+  CU(ctx, cudaMemcpy(h, (uint32_t*)ctx->misc.p, sizeof(h), cudaMemcpyDeviceToHost));
   for (int g = 0; g < 4; g++)
-    for (int r = 0; r < tm->rounds && r < 63; r++) s += h[64 * g + r];
+    for (int r = 1; r < tm->rounds && r < 63; r++) s += h[8 + 64 * g + r];
   tm->n_pairs = s;
   return 0;
 }
@@ -496,7 +523,7 @@ const char* mgb_last_error(const mgb_ctx* ctx) { return ctx ? ctx->err.c_str() :
 void mgb_destroy(mgb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  DevBuf* bufs[] = {&ctx->table, &ctx->scalars, &ctx->ent_bucket, &ctx->ent_rank, &ctx->counts, &ctx->offs, &ctx->tile_sums, &ctx->pairs, &ctx->pairs2, &ctx->V, &ctx->redU[0], &ctx->redU[1], &ctx->redW[0], &ctx->redW[1], &ctx->misc,
+  DevBuf* bufs[] = {&ctx->table, &ctx->scalars, &ctx->ent_bucket, &ctx->ent_rank, &ctx->counts, &ctx->offs, &ctx->tile_sums, &ctx->pairs, &ctx->pairs2, &ctx->V, &ctx->refs, &ctx->life8, &ctx->redU[0], &ctx->redU[1], &ctx->redW[0], &ctx->redW[1], &ctx->misc,
                     &ctx->acc_out, &ctx->out_xy, &ctx->stage};
   for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);

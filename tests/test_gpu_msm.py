@@ -207,8 +207,9 @@ def test_msm_projective_equals_batched_affine(label):
 
 @pytest.mark.parametrize("label", ["bls12-377", "ed-on-bls12-377"])
 def test_extreme_bucket_skew(engines, label):
-    """All scalars equal: every point of a window lands in ONE bucket, so the bucket trees run at full
-    depth (14+ rounds) instead of the usual log2(average).  Expected: s * sum(P_i) = s * (sum a_i) G."""
+    """All scalars equal: every point of a window lands in ONE bucket of 2^14 elements, so the bucket
+    trees run deep (the engine leaves at most 16 elements of a bucket to the reduction: >= 10 rounds)
+    instead of the usual ~log2(average).  Expected: s * sum(P_i) = s * (sum a_i) G."""
     n = 1 << 14
     eng = engines(label, n)
     O = OracleCurve(label)
@@ -217,5 +218,5 @@ def test_extreme_bucket_skew(engines, label):
     for s in (7, O.q - 2):
         sc = scalars_to_bytes([s] * n)
         res, tm = eng.msm(sc, n=n)
-        assert tm["rounds"] >= 14
+        assert tm["rounds"] >= 10
         assert res == O.result_of(O.scale(s * sum(int(v) for v in a), O.G)), (label, s, tm)
