@@ -242,6 +242,9 @@ struct Field {
       uint32_t f0 = (uint32_t)f[0] | ((uint32_t)f[1] << 30), g0 = (uint32_t)g[0] | ((uint32_t)g[1] << 30);
       int32_t u = 1, v = 0, q = 0, r = 1;
       int i = 30;
+      // -(f0^-1) mod 2^12 by two Newton steps from x = f0 (f0 odd: f0*f0 = 1 mod 8)
+      auto neg_inv = [](uint32_t fo) -> uint32_t { uint32_t x = fo; x *= 2u - fo * x; x *= 2u - fo * x; return 0u - x; };
+      uint32_t ninv = neg_inv(f0);
       while (true) {
         uint32_t lim = g0 | (0xffffffffu << i);
         const int zeros = MGB_CTZ(lim);   // trailing zeros of g0, at most i
@@ -252,8 +255,15 @@ struct Field {
           uint32_t tf = f0; f0 = g0; g0 = 0u - tf;
           int32_t tu = u; u = q; q = -tu;
           int32_t tv = v; v = r; r = -tv;
+          ninv = neg_inv(f0);
         }
-        g0 += f0; q += u; r += v;
+        // eta >= 0: up to min(eta + 1, i, 8) low bits of g can be cancelled at once by adding the
+        // multiple w of f with w = -g/f mod 2^bits (that many division steps with g odd, eta not
+        // changing sign) -- several times fewer iterations than one bit at a time
+        const int limit = (eta + 1 < i) ? eta + 1 : i;
+        const uint32_t m = (0xffffffffu >> (32 - limit)) & 255u;
+        const uint32_t w = (g0 * ninv) & m;
+        g0 += f0 * w; q += u * (int32_t)w; r += v * (int32_t)w;
       }
       // ---- (f, g) <- (u f + v g, q f + r g) / 2^30   (exact)
       {

@@ -180,7 +180,7 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   ENS(ctx, ctx->tile_sums, (size_t)ntiles * 4);
   // every non-empty bucket occupies an even number of slots (k_scan_tiles)
   const size_t max_slots = std::min<size_t>((size_t)pr.nent + pr.nbuckets, 2 * (size_t)pr.nent) + 2;
-  ENS(ctx, ctx->pairs, ((size_t)pr.nent / 4 + 8) * sizeof(PairEnt));     // pair lists of rounds 1, 3, ..
+  ENS(ctx, ctx->pairs, ((size_t)pr.nent / 4 + 8) * sizeof(PairEnt));           // pair lists of rounds 1, 3, ..
   ENS(ctx, ctx->pairs2, ((size_t)pr.nent / 8 + 8) * sizeof(PairEnt));    // rounds 2, 4, ..
   ENS(ctx, ctx->V, max_slots * CV::V_LIMBS * 4);
   ENS(ctx, ctx->redU[0], (size_t)ngroups * gm.NP * CV::ACC_LIMBS * 4);
@@ -270,10 +270,12 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
         // additions of this round (exact over all windows, from the scan)
         const uint64_t est = (r < SCAN_ROUNDS ? (uint64_t)round_pairs[r] : 0) * Kg / pr.K;
         const uint64_t warps = (uint64_t)ctx->sm_count * MINB * 4;
-        // tile shape: big tiles of E pairs per lane, about 1.5 per resident warp, then tiles of E/4
+        // tile shape: big tiles of E pairs per lane, at most 2 per resident warp, then tiles of E/4.
+        // Measured: the largest E that still gives 0.8 tiles per resident warp -- a batch (warp products
+        // + inversion) costs ~25 K issue cycles however small, so fewer, larger tiles win until warps idle.
         int E = EMAX;
-        while (E > 4 && 10 * est < 9 * warps * 32ull * E) E >>= 1;   // measured: largest tile with >= 0.9 tiles per resident warp
-        uint32_t n_big = (uint32_t)(warps + warps / 2);
+        while (E > 4 && 10 * est < 8 * warps * 32ull * E) E >>= 1;
+        uint32_t n_big = (uint32_t)(2 * warps);
         bool block_tiles = false;
         if (const char* ev = getenv("MGB_DEBUG_E")) {   // tuning aid: comma-separated E per round, negative = block-level tiles
           int k = 0; const char* q = ev;
