@@ -253,11 +253,14 @@ def run_b200(args):
         "dominant_kernel": {"name": "k_batch_add", "phase_ms": acc_ms, "share_of_step": acc_ms / phases["total"],
                             "pairs_per_step": int(tm["n_pairs"]), "field_mults_per_s": 6.0 * tm["n_pairs"] / (acc_ms * 1e-3)},
     }
-    # HBM side of the path (north star: "HBM GB/s for the sort and gather phases"): the scatter kernel reads one
-    # 96-byte point per sorted entry (coalesced) and writes it to its bucket slot (scattered)
-    ent_bytes = 2 * 2 * curve.coord_bytes + 16      # point read + point write + digit/rank entry read + pair entry
+    # HBM side of the path (north star: "HBM GB/s for the sort and gather phases").  The sort no longer copies points:
+    # per sorted entry the scatter reads digit + rank (8 B) and the bucket's offset + count (8 B, L2-resident) and writes
+    # a 4-byte point reference (+ half a byte of tree depth); the 96-byte gather of every point happens inside round 0 of
+    # k_batch_add, straight from the point table (2 x 96 B read + 96 B written per addition of round 0).
+    ent_bytes = 8 + 8 + 4 + 0.5
     hbm = {"sort_scatter_gbs": tm["n_pairs"] and (n * 2 * tm["K"] * ent_bytes) / (phases["sort"] * 1e-3) / 1e9,
-           "sort_ms": phases["sort"], "hbm_peak_gbs": _measured_peak("hbm_gbs")}
+           "sort_ms": phases["sort"], "hbm_peak_gbs": _measured_peak("hbm_gbs"),
+           "note": "sort = 3 scan kernels + scatter of 4-byte references; latency/atomic-bound, not bandwidth-bound at this size"}
     line = {
         "metric": "msm_points_per_s", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
