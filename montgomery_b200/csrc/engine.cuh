@@ -427,8 +427,9 @@ static __global__ void __launch_bounds__(SCAN_T) k_scan_add(uint32_t* __restrict
 // ---------------------------------------------------------------- k_scatter
 // Counting-sort scatter (the reference's sortPoints, msm-batched-affine.ts:456-502, copies the points
 // into bucket order).  Here a sorted slot only records WHICH point it stands for:
-//     refs[slot] = point index | endo << 30 | negate << 31,      slot = offs[bucket] + rank,
-// and round 0 of the bucket trees gathers its operands straight from the point table and writes the
+//     ref(slot) = point index | endo << 30 | negate << 31,      slot = offs[bucket] + rank,
+// kept per aligned slot pair: recs[slot / 2] = {ref(even), ref(odd)}, lifes[slot / 2] (see below);
+// round 0 of the bucket trees gathers its operands straight from the point table and writes the
 // sums to V[slot]: one write and one read of every sorted point (192 B per entry, ~1 ms at 2^20) are
 // never done.  Buckets start at even slots (k_scan_tiles), so round 0 pairs slot 2q with 2q+1; the
 // last element of an odd-sized bucket gets REF_EMPTY as its partner and is simply copied by round 0.
@@ -439,8 +440,8 @@ static __global__ void __launch_bounds__(SCAN_T) k_scan_add(uint32_t* __restrict
 // (multiple of 2^(r+1)) absorbs the element at j + 2^r if that is inside the bucket of size n.  The
 // rounds in which a slot is a left operand are r = 0 .. life-1 with
 //     life = min(ctz(j), floor(log2(n - j - 1)) + 1)        (0 if j is the last element),
-// kept per even slot (life8[slot / 2]); the pair lists of rounds >= 1 carry (slot, life), so no
-// bucket lookup is needed later.
+// kept per even slot (lifes[slot / 2]); the pair lists of rounds >= 1 carry (slot, life),
+// so no bucket lookup is needed later.
 struct PairEnt {
   uint32_t slot;
   uint32_t life;
@@ -461,7 +462,7 @@ MGB_DEV void emit_pair(bool active, PairEnt ent, PairEnt* __restrict__ pairs, ui
 template <class CV>
 __global__ void __launch_bounds__(256) k_scatter(MsmParams pr, int w_begin, int Kg, const uint32_t* __restrict__ ent_bucket, const uint32_t* __restrict__ ent_rank,
                                                  const uint32_t* __restrict__ offs, const uint32_t* __restrict__ counts, const uint32_t* __restrict__ table,
-                                                 uint32_t* __restrict__ V, uint32_t* __restrict__ refs, uint8_t* __restrict__ life8) {
+                                                 uint32_t* __restrict__ V, uint32_t* __restrict__ recs /* 2 words per aligned slot pair */, uint8_t* __restrict__ lifes) {
   // thread -> (half h, window w of the group [w_begin, w_begin + Kg), point i)
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t)pr.n * CV::HALVES * Kg) return;
@@ -475,31 +476,42 @@ __global__ void __launch_bounds__(256) k_scatter(MsmParams pr, int w_begin, int 
   uint32_t n = counts[b], j = rk & ~REF_NEG;
   uint32_t slot = offs[b] + j;
   if (V) { CV::store_v(V, slot, CV::load_entry(table, i, endo, (rk & REF_NEG) != 0)); return; }
-  refs[slot] = i | (endo ? REF_ENDO : 0u) | (rk & REF_NEG);
-  if (j & 1) return;
+  uint32_t* rec = recs + (size_t)(slot >> 1) * 2;
+  const uint32_t ref = i | (endo ? REF_ENDO : 0u) | (rk & REF_NEG);
+  if (j & 1) { rec[1] = ref; return; }
   uint32_t rest = n - j - 1;                          // elements after this one
   uint32_t life = 0;
   if (rest) {
     life = 32 - __clz(rest);                          // floor(log2(rest)) + 1
     if (j) life = min(life, (uint32_t)(__ffs(j) - 1));
   } else {
-    refs[slot + 1] = REF_EMPTY;                       // padding slot of an odd-sized bucket
+    rec[1] = REF_EMPTY;                               // padding slot of an odd-sized bucket
   }
-  life8[slot >> 1] = (uint8_t)life;
+  rec[0] = ref;
+  lifes[slot >> 1] = (uint8_t)life;
 }
 
 // ---------------------------------------------------------------- k_batch_add (Weierstrass)
 // Batched-affine additions with one field inversion per WARP tile of 32*E independent additions
 // (reference: batchAddNew / batchAddUnsafeNew, src/curve-affine.ts:376-522, and the Montgomery
 // trick of src/wasm/inverse.ts:220-271).  Warps are fully independent (no block barrier):
-//   1. every lane walks E pairs, loading only the x coordinates, and keeps the running product of
-//      the denominators; the prefix products go to a per-thread local array (L1/L2 resident);
+//   1. every lane walks E pairs, needing only the x coordinates, and keeps the running product of
+//      the denominators; the prefix products go to a per-warp scratch area in global memory;
 //   2. warp-wide inclusive prefix and suffix products of the 32 lane totals by shuffles;
 //   3. lane 0 inverts the grand total with the division-step inverse (the other warps of the
 //      SM keep the multiplier pipe busy meanwhile);
 //   4. every lane gets the inverse of its own total (2 multiplications), then walks its pairs
 //      backwards: recompute the denominator, peel off its inverse, finish the addition, store.
 // 6 multiplications per addition + 13/E for the warp products.  Emits the next round's pair list.
+//
+// Operand staging.  The operands of a pair are two random 96-byte reads (a gather from the point
+// table in round 0, from V later) that miss L1 and mostly L2; a warp has no registers to spare for
+// loads in flight (128 registers, 4 blocks per SM), and L1 prefetches were evicted before use by the
+// kernel's own streaming traffic (ncu: 29 % of the warp samples stalled on a long scoreboard).  So
+// every global input of an iteration -- pair entry, operands, stored prefix product -- is copied
+// asynchronously (cp.async, L2 -> shared memory, no registers, no L1) one iteration ahead (entries:
+// two ahead, their content gives the operand addresses) into a per-thread staging slot; an
+// iteration starts with cp.async.wait_group 0 and conflict-free 16-byte shared-memory reads.
 template <class P>
 MGB_DEV Fe<P> shfl_fe(const Fe<P>& a, int src) {
   Fe<P> r;
@@ -507,127 +519,161 @@ MGB_DEV Fe<P> shfl_fe(const Fe<P>& a, int src) {
   return r;
 }
 
-template <class CV>
-MGB_DEV void prefetch_point(const uint32_t* V, uint32_t slot) {
-  const char* p = reinterpret_cast<const char*>(V + (size_t)slot * CV::V_LIMBS);
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(p + CV::V_LIMBS * 4 - 4));
+MGB_DEV void cp_async16(void* smem, const void* gmem) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
 }
+MGB_DEV void cp_async4(void* smem, const void* gmem) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
+}
+MGB_DEV void cp_async8(void* smem, const void* gmem) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+}
+MGB_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+MGB_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-template <class CV>
-MGB_DEV void prefetch_entry(const uint32_t* table, uint32_t ref) {
-  // the operand is 2N contiguous limbs: x | y, or y | beta*x for the endomorphism image
-  const char* p = reinterpret_cast<const char*>(table + (size_t)(ref & REF_IDX) * CV::ENTRY_LIMBS + ((ref & REF_ENDO) ? CV::N : 0));
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 2 * CV::N * 4 - 4));
-}
 template <class CV>
 MGB_DEV typename CV::vpoint load_ref(const uint32_t* table, uint32_t ref) {
   return CV::load_entry(table, ref & REF_IDX, (ref & REF_ENDO) != 0, (ref & REF_NEG) != 0);
 }
 
-// FIRST = true is round 0: pair q is the aligned slot pair (2q, 2q+1) of the window group's slot range
-// [offs[b_begin], offs[b_end]); its operands are the table points refs[2q], refs[2q+1] (see
-// k_scatter; REF_EMPTY = no partner, the element is copied); V is only written.  No pair list is read.
-template <class CV, int EMAX, int MINB, bool INL, bool BLOCK, bool FIRST>
+// Round-0 record of the aligned slot pair (2q, 2q+1), written by k_scatter: recs[q] = (reference of
+// the left point, reference of the right one or REF_EMPTY: none, the left point is only copied),
+// lifes[q] = life of the left slot, one byte (only the backward pass needs it).
+// FIRST = true is round 0: pair q of the window group's slot range [offs[b_begin], offs[b_end]) is
+// recs[q]; operands come from the point table, V is only written, no pair list is read.
+template <class CV, int EMAX, int MINB, bool FIRST>
 __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ V, const PairEnt* __restrict__ pairs,
                                                          const uint32_t* __restrict__ npairs_ptr, int r, int E_big, uint32_t n_big,
                                                          PairEnt* __restrict__ pairs_out, uint32_t* __restrict__ npairs_out,
                                                          uint32_t* __restrict__ tile_counter,
-                                                         const uint32_t* __restrict__ refs, const uint8_t* __restrict__ life8,
-                                                         const uint32_t* __restrict__ table, const uint32_t* __restrict__ offs,
-                                                         uint32_t b_begin, uint32_t b_end) {
+                                                         const uint2* __restrict__ recs, const uint8_t* __restrict__ lifes,
+                                                         const uint32_t* __restrict__ table,
+                                                         const uint32_t* __restrict__ offs, uint32_t b_begin, uint32_t b_end,
+                                                         uint4* __restrict__ scratch) {
   typedef typename CV::P FP;
   typedef typename CV::F F;
   typedef typename CV::G G;
   typedef Fe<FP> fe;
+  constexpr int N = CV::N;
+  constexpr int CW = N / 4;             // 16-byte chunks per coordinate
+  constexpr int CPT = 2 * CW;           // per point (x | y contiguous)
+  constexpr int ST_A = 0, ST_B = CPT, ST_PRE = 2 * CPT, ST_ENT = 2 * CPT + CW, ST_TOTAL = ST_ENT + 3;
+  __shared__ uint4 stage[ST_TOTAL][128];   // [chunk][thread]: conflict-free 16-byte accesses
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
   const uint32_t q0 = FIRST ? offs[b_begin] >> 1 : 0u;
   const uint32_t npairs = FIRST ? (offs[b_end] >> 1) - q0 : *npairs_ptr;
-  // E (<= EMAX) pairs per lane: large tiles amortise the inversion, small ones keep every warp busy
-  // in the late rounds that have few pairs
-  // BLOCK = false: a tile is 32*E pairs owned by one warp, warps are independent.
-  // BLOCK = true : a tile is 128*E pairs owned by the block; the four warps share ONE inversion
-  //                (two block barriers per tile).  Used for the late rounds, which have so few pairs
-  //                that the serial length of a tile, not throughput, sets the time: four times fewer
-  //                pairs per lane for the same pairs-per-inversion.
-  constexpr uint32_t WPT = BLOCK ? 4u : 1u;                 // warps per tile
   // Guided tile sizes: the first n_big tiles hold E_big pairs per lane (few inversions), the rest a
   // quarter of that, so the end of the round is not one long tile per straggling warp.
   const int E_small = E_big >= 16 ? E_big / 4 : E_big;
-  const uint32_t TILE_BIG = 32u * WPT * (uint32_t)E_big, TILE_SMALL = 32u * WPT * (uint32_t)E_small;
+  const uint32_t TILE_BIG = 32u * (uint32_t)E_big, TILE_SMALL = 32u * (uint32_t)E_small;
   const uint32_t nbig = min(n_big, npairs / TILE_BIG);
   const uint32_t rest = npairs - nbig * TILE_BIG;
   const uint32_t ntiles = nbig + (rest + TILE_SMALL - 1) / TILE_SMALL;
   const uint32_t step = 1u << r;
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  __shared__ uint32_t sm_tot[BLOCK ? 4 * CV::N : 1];        // warp totals, then per-warp inverses
-  __shared__ uint32_t sm_tile;
+  // prefix products of this warp's current tile: chunk c of pair e at [(e * CW + c) * 32 + lane]
+  uint4* const my_pre = scratch + (size_t)(blockIdx.x * 4 + (tid >> 5)) * EMAX * CW * 32 + lane;
+
+  auto stage_fe = [&](int c0) -> fe {
+    fe x;
+    _Pragma("unroll") for (int c = 0; c < CW; c++) {
+      const uint4 q = stage[c0 + c][tid];
+      x.v[4 * c] = q.x; x.v[4 * c + 1] = q.y; x.v[4 * c + 2] = q.z; x.v[4 * c + 3] = q.w;
+    }
+    return x;
+  };
+  // a staged point: x | y as stored in V, or (round 0, endomorphism image) y | beta*x from the table entry
+  auto stage_point = [&](int c0, bool swapped, bool negate) -> typename CV::vpoint {
+    const fe lo = stage_fe(c0), hi = stage_fe(c0 + CW);
+    typename CV::vpoint p;
+    p.x = swapped ? hi : lo;
+    p.y = swapped ? lo : hi;
+    if (negate) p.y = F::neg(p.y);
+    return p;
+  };
+
   // tiles are handed out dynamically: warps drift apart (inversion latency varies), and a static
   // split would leave the tail of every round to a few warps
   while (true) {
     uint32_t tile = 0;
-    if (BLOCK) {
-      __syncthreads();                                      // previous tile fully consumed (sm_tot, sm_tile)
-      if (threadIdx.x == 0) sm_tile = atomicAdd(tile_counter, 1u);
-      __syncthreads();
-      tile = sm_tile;
-    } else {
-      if (lane == 0) tile = atomicAdd(tile_counter, 1u);
-      tile = __shfl_sync(0xffffffffu, tile, 0);
-    }
+    if (lane == 0) tile = atomicAdd(tile_counter, 1u);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
     if (tile >= ntiles) break;
     const int E = tile < nbig ? E_big : E_small;
-    const uint32_t tile_base = tile < nbig ? tile * TILE_BIG : nbig * TILE_BIG + (tile - nbig) * TILE_SMALL;
-    fe pre[EMAX];
-    fe run = F::one();
-    // software pipeline: slot indices two pairs ahead, x coordinates one pair ahead, so the loads of
-    // pair e+1 are in flight during the multiplication of pair e
-    const uint32_t base = tile_base + (BLOCK ? (uint32_t)warp * 32u * (uint32_t)E : 0u) + lane;
-    auto slot_at = [&](int e) -> uint32_t { return (e < E && base + (uint32_t)e * 32u < npairs) ? pairs[base + (uint32_t)e * 32u].slot : NO_BUCKET; };
-    auto refs_at = [&](int e) -> uint2 {   // FIRST: the two point references of pair e (coalesced across the warp)
-      return (e < E && base + (uint32_t)e * 32u < npairs) ? reinterpret_cast<const uint2*>(refs)[q0 + base + (uint32_t)e * 32u] : make_uint2(REF_EMPTY, REF_EMPTY);
-    };
-    uint32_t s1 = NO_BUCKET, s2 = NO_BUCKET;
-    uint2 r1 = make_uint2(REF_EMPTY, REF_EMPTY), r2 = r1;   // FIRST: references of pairs e+1, e+2
-    uint32_t lra[FIRST ? EMAX : 1], lrb[FIRST ? EMAX : 1];  // FIRST: kept for the backward pass
-    fe xa_n = F::zero(), xb_n = F::zero();
-    if constexpr (FIRST) {
-      r1 = refs_at(0); r2 = refs_at(1);
-      if (r1.x != REF_EMPTY) xa_n = CV::load_entry_x(table, r1.x);
-      if (r1.y != REF_EMPTY) xb_n = CV::load_entry_x(table, r1.y);
-    } else {
-      s1 = slot_at(0); s2 = slot_at(1);
-      if (s1 != NO_BUCKET) { xa_n = CV::load_v_x(V, s1); xb_n = CV::load_v_x(V, s1 + step); }
-    }
-    _Pragma("unroll 1") for (int e = 0; e < E; e++) {
-      const fe xa = xa_n, xb = xb_n;
-      uint32_t s = s1;
-      if constexpr (FIRST) {
-        lra[e] = r1.x; lrb[e] = r1.y;
-        s = (r1.x != REF_EMPTY && r1.y != REF_EMPTY) ? 0u : NO_BUCKET;   // a real addition?
-        r1 = r2;
-        r2 = refs_at(e + 2);
-        if (r1.x != REF_EMPTY) xa_n = CV::load_entry_x(table, r1.x);
-        if (r1.y != REF_EMPTY) xb_n = CV::load_entry_x(table, r1.y);
+    const uint32_t base = (tile < nbig ? tile * TILE_BIG : nbig * TILE_BIG + (tile - nbig) * TILE_SMALL) + lane;
+
+    // pair entry e -> staging slot (e mod 3); x = REF_EMPTY marks "no pair"
+    auto ent_slot = [&](int e) -> uint4* { return &stage[ST_ENT + (e + 3) % 3][tid]; };
+    auto fetch_ent = [&](int e, bool with_life) {
+      uint4* dst = ent_slot(e);
+      const uint32_t idx = base + (uint32_t)e * 32u;
+      if (e < 0 || e >= E || idx >= npairs) { dst->x = REF_EMPTY; return; }
+      if (FIRST) {
+        cp_async8(dst, recs + q0 + idx);
+        if (with_life) cp_async4(&dst->z, reinterpret_cast<const uint32_t*>(lifes) + ((q0 + idx) >> 2));   // the word holding the byte
       } else {
-        s1 = s2;
-        s2 = slot_at(e + 2);
-        if (s1 != NO_BUCKET) { xa_n = CV::load_v_x(V, s1); xb_n = CV::load_v_x(V, s1 + step); }
+        cp_async8(dst, pairs + idx);
       }
+    };
+    auto is_add = [&](const uint4& en) -> bool { return en.x != REF_EMPTY && !(FIRST && en.y == REF_EMPTY); };
+    // global address of operand A / B of an entry (2N contiguous limbs; round 0: see stage_point)
+    auto addr_a = [&](const uint4& en) -> const uint32_t* {
+      if (FIRST) return table + (size_t)(en.x & REF_IDX) * CV::ENTRY_LIMBS + ((en.x & REF_ENDO) ? N : 0);
+      return V + (size_t)en.x * CV::V_LIMBS;
+    };
+    auto addr_b = [&](const uint4& en) -> const uint32_t* {
+      if (FIRST) return table + (size_t)(en.y & REF_IDX) * CV::ENTRY_LIMBS + ((en.y & REF_ENDO) ? N : 0);
+      return V + (size_t)(en.x + step) * CV::V_LIMBS;
+    };
+    auto full_a = [&](const uint4& en) -> typename CV::vpoint { return FIRST ? load_ref<CV>(table, en.x) : CV::load_v(V, en.x); };
+    auto full_b = [&](const uint4& en) -> typename CV::vpoint { return FIRST ? load_ref<CV>(table, en.y) : CV::load_v(V, en.x + step); };
+
+    // ---- forward pass: running product of the denominators
+    auto issue_x = [&](int e) {   // x coordinates of pair e -> ST_A, ST_A + CW
+      const uint4 en = *ent_slot(e);
+      if (!is_add(en)) return;
+      // round 0: x sits behind y in the operand of an endomorphism image
+      const uint32_t* xa = addr_a(en) + ((FIRST && (en.x & REF_ENDO)) ? N : 0);
+      const uint32_t* xb = addr_b(en) + ((FIRST && (en.y & REF_ENDO)) ? N : 0);
+      _Pragma("unroll") for (int c = 0; c < CW; c++) {
+        cp_async16(&stage[ST_A + c][tid], xa + 4 * c);
+        cp_async16(&stage[ST_A + CW + c][tid], xb + 4 * c);
+      }
+    };
+    fetch_ent(0, false);
+    fetch_ent(1, false);
+    cp_async_commit();
+    cp_async_wait_all();
+    issue_x(0);
+    cp_async_commit();
+    fe run = F::one();
+    _Pragma("unroll 1") for (int e = 0; e < E; e++) {
+      cp_async_wait_all();                       // x of pair e, entry e + 1
+      const uint4 cur = *ent_slot(e);
+      const fe xa = stage_fe(ST_A), xb = stage_fe(ST_A + CW);
+      issue_x(e + 1);
+      fetch_ent(e + 2, false);
+      cp_async_commit();
       fe d = F::one();
-      if (s != NO_BUCKET) {
+      if (is_add(cur)) {
         if (!G::prepare_x(xa, xb, d)) {  // rare: an operand is infinity or the x coordinates coincide
-          typename CV::vpoint A, B;
-          if constexpr (FIRST) { A = load_ref<CV>(table, lra[e]); B = load_ref<CV>(table, lrb[e]); }
-          else { A = CV::load_v(V, s); B = CV::load_v(V, s + step); }
+          typename CV::vpoint A = full_a(cur), B = full_b(cur);
           (void)G::add_prepare(A, B, d);
         }
       }
-      pre[e] = run;
-      run = INL ? F::mul_inl(run, d) : F::mul(run, d);
+      _Pragma("unroll") for (int c = 0; c < CW; c++)
+        my_pre[(e * CW + c) * 32] = make_uint4(run.v[4 * c], run.v[4 * c + 1], run.v[4 * c + 2], run.v[4 * c + 3]);
+      run = F::mul(run, d);
     }
-    // warp products: pfx = c_0..c_lane, sfx = c_lane..c_31
+    cp_async_wait_all();
+    __threadfence_block();                         // the prefix products are read back (by this thread) through cp.async
+    fetch_ent(E - 1, true);                        // first entries of the backward pass travel during the warp products
+    fetch_ent(E - 2, true);
+    cp_async_commit();
+    // ---- warp products: pfx = c_0..c_lane, sfx = c_lane..c_31
     fe pfx = run, sfx = run;
     _Pragma("unroll 1") for (int dlt = 1; dlt < 32; dlt <<= 1) {
       fe up = shfl_fe<FP>(pfx, lane - dlt < 0 ? lane : lane - dlt);
@@ -636,76 +682,58 @@ __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ 
       if (lane >= dlt) pfx = np;
       if (lane + dlt <= 31) sfx = ns;
     }
-    fe total = shfl_fe<FP>(pfx, 31);
-    fe inv = total;                                // -> 1 / (this warp's total)
-    if (BLOCK) {
-      if (lane == 0) st_fe<FP>(sm_tot + warp * CV::N, total);
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        fe t0 = ld_fe<FP>(sm_tot), t1 = ld_fe<FP>(sm_tot + CV::N), t2 = ld_fe<FP>(sm_tot + 2 * CV::N), t3 = ld_fe<FP>(sm_tot + 3 * CV::N);
-        fe t01 = F::mul(t0, t1), t23 = F::mul(t2, t3);
-        fe iall = F::inv_divsteps(F::mul(t01, t23));
-        fe i01 = F::mul(iall, t23), i23 = F::mul(iall, t01);
-        st_fe<FP>(sm_tot, F::mul(i01, t1));
-        st_fe<FP>(sm_tot + CV::N, F::mul(i01, t0));
-        st_fe<FP>(sm_tot + 2 * CV::N, F::mul(i23, t3));
-        st_fe<FP>(sm_tot + 3 * CV::N, F::mul(i23, t2));
+    fe inv = shfl_fe<FP>(pfx, 31);                  // -> 1 / (this warp's total)
+    // the backward pass's first inputs travel while lane 0 inverts
+    auto issue_data = [&](int e) {   // operands and prefix product of pair e -> ST_A, ST_B, ST_PRE
+      const uint4 en = *ent_slot(e);
+      if (en.x == REF_EMPTY) return;
+      const uint32_t* pa = addr_a(en);
+      _Pragma("unroll") for (int c = 0; c < CPT; c++) cp_async16(&stage[ST_A + c][tid], pa + 4 * c);
+      if (is_add(en)) {
+        const uint32_t* pb = addr_b(en);
+        _Pragma("unroll") for (int c = 0; c < CPT; c++) cp_async16(&stage[ST_B + c][tid], pb + 4 * c);
       }
-      __syncthreads();
-      inv = ld_fe<FP>(sm_tot + warp * CV::N);
-    } else {
-      if (lane == 0) inv = F::inv_divsteps(total);
-      inv = shfl_fe<FP>(inv, 0);
-    }
+      _Pragma("unroll") for (int c = 0; c < CW; c++) cp_async16(&stage[ST_PRE + c][tid], my_pre + (e * CW + c) * 32);
+    };
+    cp_async_wait_all();
+    issue_data(E - 1);
+    cp_async_commit();
+    if (lane == 0) inv = F::inv_divsteps(inv);
+    inv = shfl_fe<FP>(inv, 0);
     fe left = shfl_fe<FP>(pfx, lane == 0 ? 0 : lane - 1);
     fe right = shfl_fe<FP>(sfx, lane == 31 ? 31 : lane + 1);
     fe u = inv;                                   // -> 1 / (this lane's total)
     if (lane > 0) u = F::mul(u, left);
     if (lane < 31) u = F::mul(u, right);
-    // pair entries two iterations ahead, operands prefetched to L1 one iteration ahead
-    auto ent_at = [&](int e) -> PairEnt {
-      PairEnt x = {NO_BUCKET, 0u};
-      if (e >= 0 && base + (uint32_t)e * 32u < npairs) {
-        if constexpr (FIRST) { x.slot = 2u * (q0 + base + (uint32_t)e * 32u); x.life = life8[q0 + base + (uint32_t)e * 32u]; }
-        else x = pairs[base + (uint32_t)e * 32u];
-      }
-      return x;
-    };
-    PairEnt nxt = ent_at(E - 1), nn = ent_at(E - 2);
+    // ---- backward pass
     _Pragma("unroll 1") for (int e = E - 1; e >= 0; e--) {
-      const PairEnt ent = nxt;
-      const bool valid = ent.slot != NO_BUCKET;
-      nxt = nn;
-      nn = ent_at(e - 2);
-      if (nxt.slot != NO_BUCKET) {
-        if constexpr (FIRST) {
-          prefetch_entry<CV>(table, lra[e - 1]);
-          if (lrb[e - 1] != REF_EMPTY) prefetch_entry<CV>(table, lrb[e - 1]);
-        } else {
-          prefetch_point<CV>(V, nxt.slot);
-          prefetch_point<CV>(V, nxt.slot + step);
-        }
-      }
-      fe inv_den = INL ? F::mul_inl(u, pre[e]) : F::mul(u, pre[e]);
+      cp_async_wait_all();                       // data of pair e, entry e - 1
+      const uint4 cur = *ent_slot(e);
+      const bool valid = cur.x != REF_EMPTY;
+      const bool add = is_add(cur);
+      typename CV::vpoint A = stage_point(ST_A, FIRST && (cur.x & REF_ENDO), FIRST && (cur.x & REF_NEG));
+      typename CV::vpoint B = stage_point(ST_B, FIRST && (cur.y & REF_ENDO), FIRST && (cur.y & REF_NEG));
+      const fe pre = stage_fe(ST_PRE);
+      if (e > 0) issue_data(e - 1);
+      fetch_ent(e - 2, true);
+      cp_async_commit();
+      const fe inv_den = F::mul(u, pre);
+      PairEnt out = {0u, 0u};
       if (valid) {
-        typename CV::vpoint A, B;
-        bool lone = false;
-        if constexpr (FIRST) {
-          A = load_ref<CV>(table, lra[e]);
-          lone = lrb[e] == REF_EMPTY;
-          if (!lone) B = load_ref<CV>(table, lrb[e]);
-        } else { A = CV::load_v(V, ent.slot); B = CV::load_v(V, ent.slot + step); }
-        if (lone) {
-          CV::store_v(V, ent.slot, A);              // no partner: denominator was 1
+        out.slot = FIRST ? 2u * (q0 + base + (uint32_t)e * 32u) : cur.x;
+        out.life = FIRST ? (cur.z >> (8 * ((q0 + base + (uint32_t)e * 32u) & 3))) & 0xffu : cur.y;
+        if (!add) {
+          CV::store_v(V, out.slot, A);              // round 0, no partner: the denominator was 1
         } else {
           fe d;
-          int kind = G::add_prepare(A, B, d);
-          u = INL ? F::mul_inl(u, d) : F::mul(u, d);
-          CV::store_v(V, ent.slot, G::template add_finish<INL>(kind, A, B, inv_den));
+          const int kind = G::add_prepare(A, B, d);
+          u = F::mul(u, d);
+          CV::store_v(V, out.slot, G::template add_finish<false>(kind, A, B, inv_den));
         }
       }
-      emit_pair(valid && (uint32_t)(r + 1) < ent.life, ent, pairs_out, npairs_out);
+      emit_pair(valid && (uint32_t)(r + 1) < out.life, out, pairs_out, npairs_out);
     }
+    cp_async_wait_all();
   }
 }
 
@@ -714,7 +742,7 @@ template <class CV, bool FIRST>
 __global__ void __launch_bounds__(256) k_pair_add(uint32_t* __restrict__ V, const PairEnt* __restrict__ pairs,
                                                   const uint32_t* __restrict__ npairs_ptr, int r,
                                                   PairEnt* __restrict__ pairs_out, uint32_t* __restrict__ npairs_out,
-                                                  const uint32_t* __restrict__ refs, const uint8_t* __restrict__ life8,
+                                                  const uint2* __restrict__ recs, const uint8_t* __restrict__ lifes,
                                                   const uint32_t* __restrict__ table, const uint32_t* __restrict__ offs,
                                                   uint32_t b_begin, uint32_t b_end) {
   const uint32_t q0 = FIRST ? offs[b_begin] >> 1 : 0u;
@@ -726,9 +754,9 @@ __global__ void __launch_bounds__(256) k_pair_add(uint32_t* __restrict__ V, cons
     PairEnt ent = {0u, 0u};
     if (valid) {
       if constexpr (FIRST) {
-        const uint2 rr = reinterpret_cast<const uint2*>(refs)[q0 + idx];
+        const uint2 rr = recs[q0 + idx];
         ent.slot = 2u * (q0 + idx);
-        ent.life = life8[q0 + idx];
+        ent.life = lifes[q0 + idx];
         typename CV::vpoint A = load_ref<CV>(table, rr.x);
         if (rr.y != REF_EMPTY) A = CV::add(A, load_ref<CV>(table, rr.y));
         CV::store_v(V, ent.slot, A);

@@ -30,7 +30,7 @@ struct mgb_ctx {
   cudaStream_t aux[3] = {};          // extra streams: window groups are pipelined against each other
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {};
   cudaEvent_t ev[EV_COUNT] = {};
-  DevBuf table, scalars, ent_bucket, ent_rank, counts, offs, tile_sums, pairs, pairs2, V, refs, life8, redU[2], redW[2], misc, acc_out, out_xy, stage;
+  DevBuf table, scalars, ent_bucket, ent_rank, counts, offs, tile_sums, pairs, pairs2, V, recs, lifes, prebuf, redU[2], redW[2], misc, acc_out, out_xy, stage;
   uint32_t* h_pinned = nullptr;  // [0..31] out xy limbs + flag, [64..] misc readback
   int sm_count = 148;
   std::string err;
@@ -230,9 +230,9 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   // round 0 gathers its operands from the point table (see k_scatter); without a round 0 the sorted
   // points are materialised by the scatter as the reduction expects
   const bool fuse = rounds > 0;
-  if (fuse) { ENS(ctx, ctx->refs, max_slots * 4); ENS(ctx, ctx->life8, max_slots / 2 + 1); }
-  uint32_t* refs = fuse ? (uint32_t*)ctx->refs.p : nullptr;
-  uint8_t* life8 = fuse ? (uint8_t*)ctx->life8.p : nullptr;
+  if (fuse) { ENS(ctx, ctx->recs, (max_slots / 2 + 1) * 8); ENS(ctx, ctx->lifes, max_slots / 2 + 8); }
+  uint32_t* recs = fuse ? (uint32_t*)ctx->recs.p : nullptr;
+  uint8_t* lifes = fuse ? (uint8_t*)ctx->lifes.p : nullptr;
   const uint32_t* table = (const uint32_t*)ctx->table.p;
   const uint32_t* offs = (const uint32_t*)ctx->offs.p;
   const uint32_t* counts = (const uint32_t*)ctx->counts.p;
@@ -258,7 +258,7 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
     uint32_t* cnt = misc + 8 + 64 * g;
     uint32_t* tcnt = misc + 264 + 64 * g;
     k_scatter<CV><<<cdiv(nent_g, 256), 256, 0, sg>>>(pr, w_begin, Kg, (const uint32_t*)ctx->ent_bucket.p, (const uint32_t*)ctx->ent_rank.p,
-                                                    offs, counts, table, fuse ? nullptr : (uint32_t*)ctx->V.p, refs, life8);
+                                                    offs, counts, table, fuse ? nullptr : (uint32_t*)ctx->V.p, recs, lifes);
     launches++;
     if (g == 0) CU(ctx, cudaEventRecord(ctx->ev[EV_SORT], st));
     for (int r = 0; r < rounds; r++) {
@@ -266,7 +266,6 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
       PairEnt* pout = pl[(r & 1) ^ 1];
       if constexpr (CV::BATCH_AFFINE) {
         constexpr int EMAX = 64, MINB = 4;
-        constexpr bool INL = false;
         // additions of this round (exact over all windows, from the scan)
         const uint64_t est = (r < SCAN_ROUNDS ? (uint64_t)round_pairs[r] : 0) * Kg / pr.K;
         const uint64_t warps = (uint64_t)ctx->sm_count * MINB * 4;
@@ -276,24 +275,29 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
         int E = EMAX;
         while (E > 4 && 10 * est < 8 * warps * 32ull * E) E >>= 1;
         uint32_t n_big = (uint32_t)(2 * warps);
-        bool block_tiles = false;
-        if (const char* ev = getenv("MGB_DEBUG_E")) {   // tuning aid: comma-separated E per round, negative = block-level tiles
+        if (const char* ev = getenv("MGB_DEBUG_E")) {   // tuning aid: comma-separated E per round
           int k = 0; const char* q = ev;
           while (k < r && (q = strchr(q, ',')) != nullptr) { q++; k++; }
-          if (q && k == r && atoi(q) != 0) { int v = atoi(q); block_tiles = v < 0; E = std::min(EMAX, std::abs(v)); }
+          if (q && k == r && atoi(q) != 0) E = std::min(EMAX, std::abs(atoi(q)));
         }
         if (const char* ev = getenv("MGB_DEBUG_NBIG")) n_big = (uint32_t)(atof(ev) * warps);
-        if (r == 0)
-          k_batch_add<CV, EMAX, MINB, INL, false, true><<<ctx->sm_count * MINB, 128, 0, sg>>>((uint32_t*)ctx->V.p, nullptr, nullptr, r, E, n_big, pout, cnt + r + 1, tcnt + r,
-                                                                                           refs, life8, table, offs, b_begin, b_end);
-        else if (block_tiles)
-          k_batch_add<CV, EMAX, MINB, INL, true, false><<<ctx->sm_count * MINB, 128, 0, sg>>>((uint32_t*)ctx->V.p, pin, cnt + r, r, E, n_big / 4, pout, cnt + r + 1, tcnt + r,
-                                                                                           nullptr, nullptr, nullptr, nullptr, 0, 0);
-        else
-          k_batch_add<CV, EMAX, MINB, INL, false, false><<<ctx->sm_count * MINB, 128, 0, sg>>>((uint32_t*)ctx->V.p, pin, cnt + r, r, E, n_big, pout, cnt + r + 1, tcnt + r,
-                                                                                            nullptr, nullptr, nullptr, nullptr, 0, 0);
+        // per-warp scratch for the prefix products of a tile (see k_batch_add)
+        const size_t pre_bytes = (size_t)ctx->sm_count * MINB * 4 * EMAX * (CV::N / 4) * 32 * 16;
+        ENS(ctx, ctx->prebuf, pre_bytes * 4);     // one area per window group (at most 4)
+        uint4* scratch = (uint4*)((char*)ctx->prebuf.p + pre_bytes * g);
+        if (r == 0) {
+          auto kern = k_batch_add<CV, EMAX, MINB, true>;
+          cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 75);   // 4 blocks x 36 KB of staging
+          kern<<<ctx->sm_count * MINB, 128, 0, sg>>>((uint32_t*)ctx->V.p, nullptr, nullptr, r, E, n_big, pout, cnt + r + 1, tcnt + r,
+                                                    (const uint2*)recs, lifes, table, offs, b_begin, b_end, scratch);
+        } else {
+          auto kern = k_batch_add<CV, EMAX, MINB, false>;
+          cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 75);
+          kern<<<ctx->sm_count * MINB, 128, 0, sg>>>((uint32_t*)ctx->V.p, pin, cnt + r, r, E, n_big, pout, cnt + r + 1, tcnt + r,
+                                                    nullptr, nullptr, nullptr, nullptr, 0, 0, scratch);
+        }
       } else {
-        if (r == 0) k_pair_add<CV, true><<<ctx->sm_count * 8, 256, 0, sg>>>((uint32_t*)ctx->V.p, nullptr, nullptr, r, pout, cnt + r + 1, refs, life8, table, offs, b_begin, b_end);
+        if (r == 0) k_pair_add<CV, true><<<ctx->sm_count * 8, 256, 0, sg>>>((uint32_t*)ctx->V.p, nullptr, nullptr, r, pout, cnt + r + 1, (const uint2*)recs, lifes, table, offs, b_begin, b_end);
         else k_pair_add<CV, false><<<ctx->sm_count * 8, 256, 0, sg>>>((uint32_t*)ctx->V.p, pin, cnt + r, r, pout, cnt + r + 1, nullptr, nullptr, nullptr, nullptr, 0, 0);
       }
       launches += 1;
@@ -525,7 +529,7 @@ const char* mgb_last_error(const mgb_ctx* ctx) { return ctx ? ctx->err.c_str() :
 void mgb_destroy(mgb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  DevBuf* bufs[] = {&ctx->table, &ctx->scalars, &ctx->ent_bucket, &ctx->ent_rank, &ctx->counts, &ctx->offs, &ctx->tile_sums, &ctx->pairs, &ctx->pairs2, &ctx->V, &ctx->refs, &ctx->life8, &ctx->redU[0], &ctx->redU[1], &ctx->redW[0], &ctx->redW[1], &ctx->misc,
+  DevBuf* bufs[] = {&ctx->table, &ctx->scalars, &ctx->ent_bucket, &ctx->ent_rank, &ctx->counts, &ctx->offs, &ctx->tile_sums, &ctx->pairs, &ctx->pairs2, &ctx->V, &ctx->recs, &ctx->lifes, &ctx->prebuf, &ctx->redU[0], &ctx->redU[1], &ctx->redW[0], &ctx->redW[1], &ctx->misc,
                     &ctx->acc_out, &ctx->out_xy, &ctx->stage};
   for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
