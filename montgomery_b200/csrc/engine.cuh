@@ -60,6 +60,7 @@ struct WeierstrassPolicy {
   typedef typename G::affine vpoint;   // materialised bucket element
   typedef GL Glv;
   typedef CoopWeierstrass<FP> Coop;
+  typedef QuadWeierstrass<FP> Quad;
   static constexpr int N = FP::N;
   static constexpr bool USE_GLV = true;
   static constexpr bool BATCH_AFFINE = true;
@@ -896,6 +897,91 @@ __global__ void __launch_bounds__(192) k_window_sums(MsmParams pr, ReduceGeom gm
     acc = CV::add(acc, CV::ld_acc(sm + 6 * CV::ACC_LIMBS));
     CV::st_acc(Sw + (size_t)w * CV::ACC_LIMBS, acc);
   }
+}
+
+// ---- quad-cooperative variants of the latency-bound reduction stages (Weierstrass, see coop.cuh) ----
+// The last tree levels of one group (<= 32 partial sums left) in one 64-thread block: four lanes per
+// addition, lane k moving coordinate k (N limbs) of the distributed point; block barrier between levels.
+// (The earlier, throughput-bound levels stay with k_tree_round: one thread per addition.)
+template <class CV>
+__global__ void __launch_bounds__(64) k_tree_tail_quad(int NP, int remaining, uint32_t* P) {
+  typedef typename CV::Quad Q;
+  typedef Fe<typename CV::P> fe;
+  constexpr int N = CV::N;
+  const int k = threadIdx.x & 3, qd = threadIdx.x >> 2, wq = (threadIdx.x >> 5) * 8;   // quad of the block, first quad of the warp
+  uint32_t* base = P + (size_t)blockIdx.x * NP * CV::ACC_LIMBS + k * N;
+  for (int half = remaining >> 1; half >= 1; half >>= 1) {
+    if (wq < half) {                                   // warp-uniform
+      const bool act = qd < half;
+      fe a = Q::zero_coord(k), b = a;
+      if (act) { a = ld_fe<typename CV::P>(base + (size_t)qd * CV::ACC_LIMBS); b = ld_fe<typename CV::P>(base + (size_t)(qd + half) * CV::ACC_LIMBS); }
+      const fe r = Q::add(a, b);
+      if (act) st_fe<typename CV::P>(base + (size_t)qd * CV::ACC_LIMBS, r);
+    }
+    __syncthreads();
+  }
+}
+
+// block = (window w, digit d), quad v = digit value: X_d = sum_v v * G_v by an inclusive suffix scan
+// over the values (S_v = sum_{v' >= v} G_v', X = sum_{v >= 1} S_v) through shared memory.
+// out[(w * D + d)] = X_d, out[K * D + w] = sum of all buckets of the window (from digit 0).
+template <class CV>
+__global__ void __launch_bounds__(128) k_digit_sums(MsmParams pr, ReduceGeom gm, int w_begin, const uint32_t* __restrict__ P, uint32_t* __restrict__ out) {
+  typedef typename CV::Quad Q;
+  typedef typename CV::P FP;
+  typedef Fe<FP> fe;
+  constexpr int N = CV::N;
+  __shared__ uint32_t sm[32 * 4 * N];
+  const int k = threadIdx.x & 3, v = threadIdx.x >> 2;
+  const int d = blockIdx.x % gm.D, w = w_begin + blockIdx.x / gm.D;
+  auto lds = [&](int vv) -> fe { fe r; _Pragma("unroll") for (int i = 0; i < N; i++) r.v[i] = sm[(vv * 4 + k) * N + i]; return r; };
+  auto sts = [&](int vv, const fe& a) { _Pragma("unroll") for (int i = 0; i < N; i++) sm[(vv * 4 + k) * N + i] = a.v[i]; };
+  fe S = Q::zero_coord(k);
+  if (v < (1 << gm.width[d])) S = ld_fe<FP>(P + ((size_t)((w * gm.D + d) * 32 + v) * gm.NP) * CV::ACC_LIMBS + k * N);
+  _Pragma("unroll 1") for (int dl = 1; dl < 32; dl <<= 1) {
+    sts(v, S);
+    __syncthreads();
+    const fe o = (v + dl <= 31) ? lds(v + dl) : Q::zero_coord(k);
+    __syncthreads();
+    S = Q::add(S, o);
+  }
+  if (v == 0 && d == 0) st_fe<FP>(out + ((size_t)pr.K * gm.D + w) * CV::ACC_LIMBS + k * N, S);
+  fe X = (v >= 1) ? S : Q::zero_coord(k);
+  _Pragma("unroll 1") for (int dl = 16; dl >= 1; dl >>= 1) {
+    sts(v, X);
+    __syncthreads();
+    const fe o = (v < dl) ? lds(v + dl) : Q::zero_coord(k);
+    __syncthreads();
+    X = Q::add(X, o);
+  }
+  if (v == 0) st_fe<FP>(out + ((size_t)w * gm.D + d) * CV::ACC_LIMBS + k * N, X);
+}
+
+// block = one window: S_w = sum_d 2^(sh_d) X_d + sum_l B_l by Horner over the digits; the four warps
+// share the multiplications of each formula level (coop.cuh), as in k_final.
+template <class CV>
+__global__ void __launch_bounds__(128) k_window_assemble(MsmParams pr, ReduceGeom gm, int w_begin, const uint32_t* __restrict__ in, uint32_t* __restrict__ Sw) {
+  typedef typename CV::P FP;
+  constexpr int N = CV::N;
+  __shared__ uint32_t sm[COOP_SLOTS * N];
+  __shared__ int flag;
+  CoopMem<FP> m{sm};
+  const int w = w_begin + blockIdx.x;
+  auto load_point = [&](int slot0, const uint32_t* src) {
+    if (threadIdx.x < 4 * N) sm[slot0 * N + threadIdx.x] = src[threadIdx.x];
+  };
+  load_point(0, in + ((size_t)w * gm.D + gm.D - 1) * CV::ACC_LIMBS);
+  __syncthreads();
+  for (int dd = gm.D - 2; dd >= 0; dd--) {
+    for (int k = 0; k < gm.width[dd]; k++) CV::Coop::dbl(m, &flag);
+    load_point(4, in + ((size_t)w * gm.D + dd) * CV::ACC_LIMBS);
+    __syncthreads();
+    CV::Coop::add(m, &flag);
+  }
+  load_point(4, in + ((size_t)pr.K * gm.D + w) * CV::ACC_LIMBS);
+  __syncthreads();
+  CV::Coop::add(m, &flag);
+  if (threadIdx.x < 4 * N) Sw[(size_t)w * CV::ACC_LIMBS + threadIdx.x] = sm[threadIdx.x];
 }
 
 // result = sum_w 2^(c*w) S_w by Horner (msm-batched-affine.ts:322-334): (K-1)*c dependent doublings.

@@ -155,7 +155,10 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
       minw = std::min(minw, gm.width[d]);
     }
     const uint32_t gmax = pr.L >> minw;        // largest group
-    gm.CH = 2;
+    // buckets per partial sum: more of the (throughput-bound) first tree level folded into k_group_partial
+    // when there are buckets enough to keep every SM busy anyway (measured at 2^18 / 2^20 / 2^22 points: 2 / 4 / 4 best)
+    gm.CH = pr.nbuckets >= (1u << 18) ? 4 : 2;
+    if (const char* ev = getenv("MGB_DEBUG_CH")) gm.CH = std::max(1, atoi(ev));
     gm.NP = 1;
     while ((uint32_t)gm.NP * gm.CH < gmax) gm.NP <<= 1;
   }
@@ -185,6 +188,7 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   ENS(ctx, ctx->V, max_slots * CV::V_LIMBS * 4);
   ENS(ctx, ctx->redU[0], (size_t)ngroups * gm.NP * CV::ACC_LIMBS * 4);
   ENS(ctx, ctx->redW[0], (size_t)pr.K * CV::ACC_LIMBS * 4);
+  ENS(ctx, ctx->redW[1], (size_t)pr.K * (gm.D + 1) * CV::ACC_LIMBS * 4);
   ENS(ctx, ctx->misc, 1024 * 4);
   // misc: [0] grand total of (padded) slots, [1] max bucket, [512 + r] exact number of additions of tree round r, [8 + 64 g + r] pair count of round r of window group g,
   //       [264 + 64 g + r] tile counter of that round
@@ -321,12 +325,20 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
       k_tree_round<CV><<<cdiv((size_t)ngroups_g * (remaining / 2), 128), 128, 0, sg>>>(ngroups_g, gm.NP, remaining / 2, Pg);
       launches++;
     }
-    if (remaining > 1) {
-      k_tree_tail<CV><<<cdiv((size_t)ngroups_g * 32, 128), 128, 0, sg>>>(ngroups_g, gm.NP, remaining, Pg);
+    if constexpr (CV::BATCH_AFFINE) {
+      // latency-bound stages, four lanes per point addition (coop.cuh): last tree levels, digit sums, per-window assembly
+      if (remaining > 1) { k_tree_tail_quad<CV><<<ngroups_g, 64, 0, sg>>>(gm.NP, remaining, Pg); launches++; }
+      k_digit_sums<CV><<<Kg * gm.D, 128, 0, sg>>>(pr, gm, w_begin, (const uint32_t*)ctx->redU[0].p, (uint32_t*)ctx->redW[1].p);
+      k_window_assemble<CV><<<Kg, 128, 0, sg>>>(pr, gm, w_begin, (const uint32_t*)ctx->redW[1].p, (uint32_t*)ctx->redW[0].p);
+      launches += 2;
+    } else {
+      if (remaining > 1) {
+        k_tree_tail<CV><<<cdiv((size_t)ngroups_g * 32, 128), 128, 0, sg>>>(ngroups_g, gm.NP, remaining, Pg);
+        launches++;
+      }
+      k_window_sums<CV><<<Kg, 192, 0, sg>>>(pr, gm, w_begin, (const uint32_t*)ctx->redU[0].p, (uint32_t*)ctx->redW[0].p);
       launches++;
     }
-    k_window_sums<CV><<<Kg, 192, 0, sg>>>(pr, gm, w_begin, (const uint32_t*)ctx->redU[0].p, (uint32_t*)ctx->redW[0].p);
-    launches++;
     if (g > 0) CU(ctx, cudaEventRecord(ctx->ev_join[g - 1], sg));
   }
   for (int g = 1; g < G; g++) CU(ctx, cudaStreamWaitEvent(st, ctx->ev_join[g - 1], 0));
