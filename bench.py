@@ -173,6 +173,8 @@ def run_b200(args):
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
+        # stdout carries exactly one JSON line: NCCL's own banner (NCCL_DEBUG=VERSION/INFO in the environment) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     curve = m.curves.BY_LABEL[args.curve]
     n = 1 << args.logn

@@ -46,7 +46,8 @@ def build(force=False, verbose=False):
 
     def compile_one(src):
         obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        # MGB_NVCC_EXTRA: extra flags for experiments (e.g. -DMGB_MINB=5)
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("MGB_NVCC_EXTRA", "").split() + ["-c", os.path.join(CSRC, src), "-o", obj]
         res = subprocess.run(cmd, capture_output=True, text=True)
         log = os.path.join(OBJDIR, src + ".ptxas.log")
         with open(log, "w") as fh:

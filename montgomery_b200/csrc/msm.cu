@@ -269,7 +269,13 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
       PairEnt* pin = pl[r & 1];
       PairEnt* pout = pl[(r & 1) ^ 1];
       if constexpr (CV::BATCH_AFFINE) {
-        constexpr int EMAX = 64, MINB = 4;
+#ifndef MGB_MINB
+#define MGB_MINB 4
+#endif
+#ifndef MGB_EMAX
+#define MGB_EMAX 64
+#endif
+        constexpr int EMAX = MGB_EMAX, MINB = MGB_MINB;
         // additions of this round (exact over all windows, from the scan)
         const uint64_t est = (r < SCAN_ROUNDS ? (uint64_t)round_pairs[r] : 0) * Kg / pr.K;
         const uint64_t warps = (uint64_t)ctx->sm_count * MINB * 4;
@@ -291,12 +297,12 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
         uint4* scratch = (uint4*)((char*)ctx->prebuf.p + pre_bytes * g);
         if (r == 0) {
           auto kern = k_batch_add<CV, EMAX, MINB, true>;
-          cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 75);   // 4 blocks x 36 KB of staging
+          cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, MINB > 4 ? 90 : 75);   // MINB blocks x 36 KB of staging
           kern<<<ctx->sm_count * MINB, 128, 0, sg>>>((uint32_t*)ctx->V.p, nullptr, nullptr, r, E, n_big, pout, cnt + r + 1, tcnt + r,
                                                     (const uint2*)recs, lifes, table, offs, b_begin, b_end, scratch);
         } else {
           auto kern = k_batch_add<CV, EMAX, MINB, false>;
-          cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 75);
+          cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, MINB > 4 ? 90 : 75);
           kern<<<ctx->sm_count * MINB, 128, 0, sg>>>((uint32_t*)ctx->V.p, pin, cnt + r, r, E, n_big, pout, cnt + r + 1, tcnt + r,
                                                     nullptr, nullptr, nullptr, nullptr, 0, 0, scratch);
         }
