@@ -93,31 +93,54 @@ struct Field {
 
   // Montgomery product a*b/R mod p, a, b < p.
   // X/Y alternate as E (pairs on limbs 0,1|2,3|...) and O (pairs on limbs 1,2|3,4|...): t = E + O*2^32.
-  MGB_DEV static fe mul_inl(const fe& fa, const fe& fb) {
+  // SQR = true: fb is ignored, the result is fa^2.  Row i then only forms the products with j >= i -- the
+  // diagonal a_i*a_i and a_i*(2 a_{>i})_j for j > i (2a < 2^(32 N) for every modulus here) -- so 66 of the 144
+  // operand products of a 12-limb squaring disappear; the accumulator limbs below the first product
+  // of a row are only shifted, with the carry rippling through plain add-with-carry (ALU pipe).
+  template <bool SQR>
+  MGB_DEV static fe mul_impl(const fe& fa, const fe& fb) {
     const uint32_t* a = fa.v;
-    const uint32_t* b = fb.v;
+    const uint32_t* b = SQR ? fa.v : fb.v;
+    uint32_t a2[N];
+    if constexpr (SQR) {
+      a2[0] = a[0] << 1;
+      _Pragma("unroll") for (int j = 1; j < N; j++) a2[j] = (a[j] << 1) | (a[j - 1] >> 31);
+    }
     uint32_t X[N], Y[N];
     _Pragma("unroll") for (int i = 0; i < N; i++) {
       uint32_t* E = (i & 1) ? Y : X;
       uint32_t* O = (i & 1) ? X : Y;
       const uint32_t bi = b[i];
+      // multiplicand limb j of row i, and whether the product exists at all
+      // (the limb right above the diagonal must not take the top bit of a_i: that bit belongs to 2*a_i, not to 2*(a >> 32(i+1)))
+      auto mc = [&](int j) -> uint32_t { return SQR ? (j > i + 1 ? a2[j] : (j == i + 1 ? a[j] << 1 : a[j])) : a[j]; };
+      auto has = [&](int j) -> bool { return !SQR || j >= i; };
       if (i == 0) {
-        _Pragma("unroll") for (int j = 0; j < N; j += 2) { E[j] = ptx::mul_lo(a[j], bi); E[j + 1] = ptx::mul_hi(a[j], bi); }
-        _Pragma("unroll") for (int j = 0; j < N; j += 2) { O[j] = ptx::mul_lo(a[j + 1], bi); O[j + 1] = ptx::mul_hi(a[j + 1], bi); }
+        _Pragma("unroll") for (int j = 0; j < N; j += 2) { E[j] = ptx::mul_lo(mc(j), bi); E[j + 1] = ptx::mul_hi(mc(j), bi); }
+        _Pragma("unroll") for (int j = 0; j < N; j += 2) { O[j] = ptx::mul_lo(mc(j + 1), bi); O[j + 1] = ptx::mul_hi(mc(j + 1), bi); }
       } else {
         // O is last round's E: its limb 0 was cancelled, its limb 1 now has the weight of E[0];
         // the carry of that add has the weight of O's (shifted) pair 0 and enters the chain.
         E[0] = ptx::add_cc(E[0], O[1]);
         _Pragma("unroll") for (int j = 0; j < N - 2; j += 2) {
-          O[j] = ptx::madc_lo_cc(a[j + 1], bi, O[j + 2]);
-          O[j + 1] = ptx::madc_hi_cc(a[j + 1], bi, O[j + 3]);
+          if (has(j + 1)) {
+            O[j] = ptx::madc_lo_cc(mc(j + 1), bi, O[j + 2]);
+            O[j + 1] = ptx::madc_hi_cc(mc(j + 1), bi, O[j + 3]);
+          } else {
+            O[j] = ptx::addc_cc(O[j + 2], 0);
+            O[j + 1] = ptx::addc_cc(O[j + 3], 0);
+          }
         }
-        O[N - 2] = ptx::madc_lo_cc(a[N - 1], bi, 0);
-        O[N - 1] = ptx::madc_hi(a[N - 1], bi, 0);
+        O[N - 2] = ptx::madc_lo_cc(mc(N - 1), bi, 0);
+        O[N - 1] = ptx::madc_hi(mc(N - 1), bi, 0);
+        bool first = true;
         _Pragma("unroll") for (int j = 0; j < N; j += 2) {
-          E[j] = (j == 0) ? ptx::mad_lo_cc(a[j], bi, E[j]) : ptx::madc_lo_cc(a[j], bi, E[j]);
-          E[j + 1] = ptx::madc_hi_cc(a[j], bi, E[j + 1]);
+          if (!has(j)) continue;
+          E[j] = first ? ptx::mad_lo_cc(mc(j), bi, E[j]) : ptx::madc_lo_cc(mc(j), bi, E[j]);
+          E[j + 1] = ptx::madc_hi_cc(mc(j), bi, E[j + 1]);
+          first = false;
         }
+        if (first) O[N - 1] = ptx::add_cc(O[N - 1], 0);   // (cannot happen: row N-1 still has a product with j >= i)
         O[N - 1] = ptx::addc(O[N - 1], 0);
       }
       const uint32_t m = E[0] * c_mgb_minv[P::ID];
@@ -147,10 +170,11 @@ struct Field {
     t[N - 1] = ptx::addc(O[N - 1], 0);
     return reduce_once(t);
   }
+  MGB_DEV static fe mul_inl(const fe& fa, const fe& fb) { return mul_impl<false>(fa, fb); }
   // Out-of-line copy: one body per kernel keeps the instruction footprint inside the SM's
   // instruction cache (an inlined multiplication is ~5 KB of SASS).
   MGB_NOINLINE_DEV static fe mul(fe a, fe b) { return mul_inl(a, b); }  // by value: register ABI, no stack traffic
-  MGB_DEV static fe sqr(const fe& a) { return mul(a, a); }
+  MGB_NOINLINE_DEV static fe sqr(fe a) { return mul_impl<true>(a, a); }
 
   MGB_DEV static fe to_mont(const fe& a) { fe r2; _Pragma("unroll") for (int i = 0; i < N; i++) r2.v[i] = P::r2(i); return mul(a, r2); }
   MGB_DEV static fe from_mont(const fe& a) { fe o = zero(); o.v[0] = 1; return mul(a, o); }

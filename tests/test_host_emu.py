@@ -66,6 +66,25 @@ def test_field_ops(emu, fid):
         assert I(out, n, 1)[0] == 0
 
 
+@pytest.mark.parametrize("fid", [0, 1, 2, 3])
+def test_dedicated_squaring(emu, fid):
+    """Field::sqr is its own routine (doubled off-diagonal products, skipped low products): operands with
+    all-ones limbs, top bits set in every limb, single limbs, and random ones, against a*a/R mod p."""
+    p, n = FIELDS[fid]
+    R = 1 << (32 * n)
+    Ri = pow(R, -1, p)
+    rnd = random.Random(100 + fid)
+    cases = [p - 1, p - 2, (p - 1) // 2, (p + 1) // 2, R % p, (R - 1) % p]
+    cases += [((1 << (32 * k + 32)) - 1) % p for k in range(n)]                    # low k+1 limbs all ones
+    cases += [sum(0x80000000 << (32 * i) for i in range(n)) % p, sum(0xffffffff << (32 * i) for i in range(0, n, 2)) % p]
+    cases += [(0xffffffff << (32 * k)) % p for k in range(n)] + [(1 << (32 * k + 31)) % p for k in range(n)]
+    cases += [rnd.randrange(p) for _ in range(600)]
+    out = (ctypes.c_uint32 * n)()
+    for a in cases:
+        emu.emu_fe_op(fid, 6, out, L([a], n), L([0], n))
+        assert I(out, n, 1)[0] == a * a * Ri % p, (fid, hex(a))
+
+
 @pytest.mark.parametrize("cid,prm,n", [(0, BLS12_377, 12), (1, PALLAS, 8), (2, BLS12_381, 12)], ids=["bls12-377", "pallas", "bls12-381"])
 def test_weierstrass_ops(emu, cid, prm, n):
     p = prm.p
