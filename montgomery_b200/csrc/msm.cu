@@ -226,7 +226,8 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   int r_full = 0;
   while ((1u << r_full) < maxcount) r_full++;
   int rounds = 0;
-  const uint32_t min_pairs = CV::BATCH_AFFINE ? 100000u : 20000u;   // rounds without an inversion have a much lower floor
+  uint32_t min_pairs = CV::BATCH_AFFINE ? 100000u : 20000u;   // rounds without an inversion have a much lower floor
+  if (const char* ev = getenv("MGB_DEBUG_MINPAIRS")) min_pairs = (uint32_t)atoi(ev);
   while (rounds < r_full && rounds < SCAN_ROUNDS && round_pairs[rounds] >= min_pairs) rounds++;
   rounds = std::max(rounds, r_full - 4);
   if (opts && opts->verbose > 1) rounds = r_full;
@@ -283,7 +284,9 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
         // Measured: the largest E that still gives 0.8 tiles per resident warp -- a batch (warp products
         // + inversion) costs ~25 K issue cycles however small, so fewer, larger tiles win until warps idle.
         int E = EMAX;
-        while (E > 4 && 10 * est < 8 * warps * 32ull * E) E >>= 1;
+        uint64_t fill10 = 8;
+        if (const char* ev = getenv("MGB_DEBUG_FILL")) fill10 = (uint64_t)atoi(ev);
+        while (E > 4 && 10 * est < fill10 * warps * 32ull * E) E >>= 1;
         uint32_t n_big = (uint32_t)(2 * warps);
         if (const char* ev = getenv("MGB_DEBUG_E")) {   // tuning aid: comma-separated E per round
           int k = 0; const char* q = ev;
