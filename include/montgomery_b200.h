@@ -61,7 +61,8 @@ typedef struct mgb_opts {
 /* Per-phase device times in milliseconds (CUDA events on the context's stream); the analogue of
  * the `log` array returned by msm() (src/msm-common.ts:176-213) with the same phase boundaries. */
 typedef struct mgb_timing {
-  float h2d_scalars;        /* host->device copy of the scalars (0 for the device-resident entry)   */
+  float h2d_scalars;        /* host->device copy of the scalars when it is one copy on the main stream (n < 2^16); larger
+                               inputs upload in chunks overlapped with decompose_slice, which then includes the transfer */
   float decompose_slice;    /* "prepare points & scalars" + "slice scalars & count buckets"          */
   float sort;               /* "integrate bucket counts" + "sort points"                             */
   float accumulate;         /* "bucket accumulation"                                                  */

@@ -299,11 +299,12 @@ struct MsmParams {
 // ---------------------------------------------------------------- k_digits
 // One thread per scalar.  Entry e = (h*K + w) of scalar i lives at [e*n + i] (coalesced).
 template <class CV>
-__global__ void __launch_bounds__(256) k_digits(MsmParams pr, const uint32_t* __restrict__ scalars,
+__global__ void __launch_bounds__(256) k_digits(MsmParams pr, uint32_t i_begin, uint32_t i_end, const uint32_t* __restrict__ scalars,
                                                 uint32_t* __restrict__ ent_bucket, uint32_t* __restrict__ ent_rank,
                                                 uint32_t* __restrict__ counts) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= pr.n) return;
+  // scalars [i_begin, i_end): the host path launches one grid per uploaded chunk (see msm_core)
+  uint32_t i = i_begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= i_end) return;
   uint32_t s[8];
   {
     const uint4* q = reinterpret_cast<const uint4*>(scalars + (size_t)i * 8);

@@ -28,7 +28,7 @@ struct mgb_ctx {
   size_t max_points = 0, npoints = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t aux[3] = {};          // extra streams: window groups are pipelined against each other
-  cudaEvent_t ev_fork = nullptr, ev_join[3] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {}, ev_chunk[4] = {};
   cudaEvent_t ev[EV_COUNT] = {};
   DevBuf table, scalars, ent_bucket, ent_rank, counts, offs, tile_sums, pairs, pairs2, V, recs, lifes, prebuf, redU[2], redW[2], misc, acc_out, out_xy, stage;
   uint32_t* h_pinned = nullptr;  // [0..31] out xy limbs + flag, [64..] misc readback
@@ -165,13 +165,26 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   const uint32_t ngroups = (uint32_t)pr.K * gm.D * 32;
   ENS(ctx, ctx->acc_out, CV::ACC_LIMBS * 4);
   CU(ctx, cudaEventRecord(ctx->ev[EV_START], st));
+  // Host scalars travel in chunks on a second stream; the digit kernel of a chunk starts as soon as that chunk has
+  // landed, so only the last chunk's digits are not hidden behind the PCIe transfer.
   const uint32_t* d_scalars;
+  const int n_chunks = (!on_device && n >= (1u << 16)) ? 4 : 1;
   if (on_device) {
     d_scalars = (const uint32_t*)scalars;
   } else {
     ENS(ctx, ctx->scalars, n * 32);
-    CU(ctx, cudaMemcpyAsync(ctx->scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, st));
     d_scalars = (const uint32_t*)ctx->scalars.p;
+    if (n_chunks == 1) {
+      CU(ctx, cudaMemcpyAsync(ctx->scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, st));
+    } else {
+      cudaStream_t cs = ctx->aux[2];
+      CU(ctx, cudaStreamWaitEvent(cs, ctx->ev[EV_START], 0));
+      for (int k = 0; k < n_chunks; k++) {
+        const size_t b = n * (size_t)k / n_chunks, e = n * (size_t)(k + 1) / n_chunks;
+        CU(ctx, cudaMemcpyAsync((char*)ctx->scalars.p + b * 32, (const char*)scalars + b * 32, (e - b) * 32, cudaMemcpyHostToDevice, cs));
+        CU(ctx, cudaEventRecord(ctx->ev_chunk[k], cs));
+      }
+    }
   }
   CU(ctx, cudaEventRecord(ctx->ev[EV_H2D], st));
 
@@ -197,8 +210,12 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   CU(ctx, cudaMemsetAsync(misc, 0, 1024 * 4, st));
 
   // ---- digits + histogram
-  k_digits<CV><<<cdiv(n, 256), 256, 0, st>>>(pr, d_scalars, (uint32_t*)ctx->ent_bucket.p, (uint32_t*)ctx->ent_rank.p, (uint32_t*)ctx->counts.p);
-  launches++;
+  for (int k = 0; k < n_chunks; k++) {
+    const size_t b = n * (size_t)k / n_chunks, e = n * (size_t)(k + 1) / n_chunks;
+    if (n_chunks > 1) CU(ctx, cudaStreamWaitEvent(st, ctx->ev_chunk[k], 0));
+    k_digits<CV><<<cdiv(e - b, 256), 256, 0, st>>>(pr, (uint32_t)b, (uint32_t)e, d_scalars, (uint32_t*)ctx->ent_bucket.p, (uint32_t*)ctx->ent_rank.p, (uint32_t*)ctx->counts.p);
+    launches++;
+  }
   CU(ctx, cudaGetLastError());
   CU(ctx, cudaEventRecord(ctx->ev[EV_DIGITS], st));
 
@@ -482,6 +499,7 @@ int mgb_create(mgb_ctx** out, int curve, int device, size_t max_points) {
     CU(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 3; i++) { CU(ctx, cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking)); CU(ctx, cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming)); }
     CU(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < 4; i++) CU(ctx, cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
     for (int i = 0; i < EV_COUNT; i++) CU(ctx, cudaEventCreate(&ctx->ev[i]));
     CU(ctx, cudaMallocHost((void**)&ctx->h_pinned, 256 * 4));
     return ensure(ctx, ctx->table, max_points * entry_bytes(curve));
@@ -558,6 +576,7 @@ void mgb_destroy(mgb_ctx* ctx) {
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   for (int i = 0; i < 3; i++) { if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]); if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  for (int i = 0; i < 4; i++) if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
   delete ctx;
 }
 
