@@ -597,13 +597,28 @@ __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ 
     return p;
   };
 
-  // tiles are handed out dynamically: warps drift apart (inversion latency varies), and a static
-  // split would leave the tail of every round to a few warps
+  // Tile hand-out.  Every warp first takes ONE statically assigned tile, then tiles are handed out
+  // dynamically (warps drift apart -- inversion latency varies -- and a static split would leave the
+  // tail of every round to a few warps).  The static first tile matters for the late rounds, which
+  // have fewer tiles than warps: with a pure atomic hand-out the winners are random and some SM
+  // sub-partitions run 3-4 tiles while others idle (ncu, round 6: sub-partitions active half of the
+  // kernel's duration).  Blocks b, b + #SM, b + 2 #SM, .. share an SM and warp w of a block sits on
+  // sub-partition w, so tile t goes to block t mod #blocks, warp (t / #blocks + b / #SM) mod 4:
+  // tiles 0 .. #blocks-1 land one per block AND one per sub-partition of every SM.
+  const uint32_t total_warps = gridDim.x * 4u;
+  bool first_tile = true;
   while (true) {
     uint32_t tile = 0;
-    if (lane == 0) tile = atomicAdd(tile_counter, 1u);
-    tile = __shfl_sync(0xffffffffu, tile, 0);
-    if (tile >= ntiles) break;
+    if (first_tile) {
+      const uint32_t k = ((uint32_t)(tid >> 5) + 4u - (blockIdx.x / (gridDim.x / (uint32_t)MINB)) % 4u) % 4u;
+      tile = k * gridDim.x + blockIdx.x;
+      first_tile = false;
+      if (tile >= ntiles) continue;                  // nothing assigned: try the dynamic pool (empty when ntiles <= #warps)
+    } else {
+      if (lane == 0) tile = atomicAdd(tile_counter, 1u) + total_warps;
+      tile = __shfl_sync(0xffffffffu, tile, 0);
+      if (tile >= ntiles) break;
+    }
     const int E = tile < nbig ? E_big : E_small;
     const uint32_t base = (tile < nbig ? tile * TILE_BIG : nbig * TILE_BIG + (tile - nbig) * TILE_SMALL) + lane;
 
