@@ -303,7 +303,9 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
         int E = EMAX;
         uint64_t fill10 = 8;
         if (const char* ev = getenv("MGB_DEBUG_FILL")) fill10 = (uint64_t)atoi(ev);
-        while (E > 4 && 10 * est < fill10 * warps * 32ull * E) E >>= 1;
+        int emin = 4;
+        if (const char* ev = getenv("MGB_DEBUG_EMIN")) emin = std::max(1, atoi(ev));
+        while (E > emin && 10 * est < fill10 * warps * 32ull * E) E >>= 1;
         uint32_t n_big = (uint32_t)(2 * warps);
         if (const char* ev = getenv("MGB_DEBUG_E")) {   // tuning aid: comma-separated E per round
           int k = 0; const char* q = ev;
