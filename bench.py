@@ -173,9 +173,19 @@ def run_b200(args):
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
-        # stdout carries exactly one JSON line: NCCL's own banner (NCCL_DEBUG=VERSION/INFO in the environment) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # stdout carries exactly one JSON line: NCCL prints its version banner with a plain printf when the communicator
+        # is created, so file descriptor 1 points at stderr while that happens (init + one warm-up collective)
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     curve = m.curves.BY_LABEL[args.curve]
     n = 1 << args.logn
     from montgomery_b200.distributed import ShardedMsm
