@@ -11,6 +11,7 @@
 // All three base primes satisfy p = 1 (mod 2^32): the Montgomery quotient digit is m = -t0 and
 // the p[0]*m product is replaced by a carry (same shortcut as multiply-montgomery.ts:324-334).
 #pragma once
+#include <type_traits>
 #include "ptx.cuh"
 #include "constants_gen.cuh"
 
@@ -97,6 +98,20 @@ struct Field {
   // diagonal a_i*a_i and a_i*(2 a_{>i})_j for j > i (2a < 2^(32 N) for every modulus here) -- so 66 of the 144
   // operand products of a 12-limb squaring disappear; the accumulator limbs below the first product
   // of a row are only shifted, with the carry rippling through plain add-with-carry (ALU pipe).
+  // compile-time loop: f(std::integral_constant<int, I>) for I = Begin, Begin + Step, .. < End
+  template <int I, int End, int Step, class Fn>
+  MGB_DEV static void static_for(Fn&& f) {
+    if constexpr (I < End) {
+      f(std::integral_constant<int, I>{});
+      static_for<I + Step, End, Step>(f);
+    }
+  }
+  // compile-time classification of a modulus limb (see mul_impl)
+  // zero or a single bit.  (Two-bit limbs such as BLS12-377's p_2 = 3 << 28 were tried: ptxas turns the second
+  // shifted add back into IMAD.WIDE x, 2^k, so nothing is saved.)
+  MGB_DEV static constexpr bool cheap_limb(uint32_t c) { return (c & (c - 1)) == 0; }
+  MGB_DEV static constexpr int low_bit(uint32_t c) { int b = 0; while (b < 31 && !((c >> b) & 1)) b++; return b; }
+  MGB_DEV static constexpr int high_bit(uint32_t c) { int b = 31; while (b > 0 && !((c >> b) & 1)) b--; return b; }
   template <bool SQR>
   MGB_DEV static fe mul_impl(const fe& fa, const fe& fb) {
     const uint32_t* a = fa.v;
@@ -144,10 +159,33 @@ struct Field {
         O[N - 1] = ptx::addc(O[N - 1], 0);
       }
       const uint32_t m = E[0] * c_mgb_minv[P::ID];
-      _Pragma("unroll") for (int j = 0; j < N; j += 2) {
-        O[j] = (j == 0) ? ptx::mad_lo_cc(P::mod(j + 1), m, O[j]) : ptx::madc_lo_cc(P::mod(j + 1), m, O[j]);
-        O[j + 1] = ptx::madc_hi_cc(P::mod(j + 1), m, O[j + 1]);
-      }
+      // Modulus limbs that are zero or a power of two (Pallas: p_4..p_6 = 0, p_7 = 1 << 30) do not go through the
+      // multiplier: the 64-bit product m * p_j is two shifts on the ALU pipe and enters the carry chain as a plain addend.
+      uint32_t clo[N], chi[N];
+      static_for<1, N, 1>([&](auto J) {
+        constexpr int j = decltype(J)::value;
+        constexpr uint32_t c = P::mod(j);
+        clo[j] = 0; chi[j] = 0;
+        if constexpr (cheap_limb(c) && c != 0) {
+          constexpr int b0 = low_bit(c), b1 = high_bit(c);
+          clo[j] = m << b0;
+          if constexpr (b0 != 0) chi[j] = m >> (32 - b0);
+          if constexpr (b1 != b0) {
+            clo[j] = ptx::add_cc(clo[j], m << b1);
+            chi[j] = ptx::addc(chi[j], m >> (32 - b1));
+          }
+        }
+      });
+      static_for<0, N, 2>([&](auto J) {
+        constexpr int j = decltype(J)::value;
+        if constexpr (cheap_limb(P::mod(j + 1))) {
+          O[j] = (j == 0) ? ptx::add_cc(O[j], clo[j + 1]) : ptx::addc_cc(O[j], clo[j + 1]);
+          O[j + 1] = ptx::addc_cc(O[j + 1], chi[j + 1]);
+        } else {
+          O[j] = (j == 0) ? ptx::mad_lo_cc(P::mod(j + 1), m, O[j]) : ptx::madc_lo_cc(P::mod(j + 1), m, O[j]);
+          O[j + 1] = ptx::madc_hi_cc(P::mod(j + 1), m, O[j + 1]);
+        }
+      });
       if constexpr (P::mod(0) == 1u) {
         // E pair 0 += p[0]*m with p[0] = 1: limb 0 becomes 0, carry (E[0] != 0) goes into limb 1
         (void)ptx::add_cc(E[0], 0xffffffffu);
@@ -156,10 +194,16 @@ struct Field {
         E[0] = ptx::mad_lo_cc(P::mod(0), m, E[0]);      // becomes 0 by the choice of m
         E[1] = ptx::madc_hi_cc(P::mod(0), m, E[1]);
       }
-      _Pragma("unroll") for (int j = 2; j < N; j += 2) {
-        E[j] = ptx::madc_lo_cc(P::mod(j), m, E[j]);
-        E[j + 1] = ptx::madc_hi_cc(P::mod(j), m, E[j + 1]);
-      }
+      static_for<2, N, 2>([&](auto J) {
+        constexpr int j = decltype(J)::value;
+        if constexpr (cheap_limb(P::mod(j))) {
+          E[j] = ptx::addc_cc(E[j], clo[j]);
+          E[j + 1] = ptx::addc_cc(E[j + 1], chi[j]);
+        } else {
+          E[j] = ptx::madc_lo_cc(P::mod(j), m, E[j]);
+          E[j + 1] = ptx::madc_hi_cc(P::mod(j), m, E[j + 1]);
+        }
+      });
       O[N - 1] = ptx::addc(O[N - 1], 0);
     }
     uint32_t* E = ((N - 1) & 1) ? Y : X;
