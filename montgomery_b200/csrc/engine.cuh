@@ -803,9 +803,27 @@ struct ReduceGeom {
   int CH;           // buckets per partial sum
 };
 
+// Bucket sums after the last tree round: one thread per bucket adds whatever the bucket has left (the
+// elements at stride 2^rounds) into an XYZZ accumulator.  Without it every one of the D digit passes of
+// k_group_partial would walk the leftovers again; with it the batched-affine rounds can stop earlier
+// (their late rounds are latency-bound, ~0.2 ms each for ever fewer additions) and hand 4-8 elements
+// per bucket to this throughput-bound kernel instead.
+template <class CV>
+__global__ void __launch_bounds__(128) k_bucket_finish(uint32_t b_begin, uint32_t b_end, int rounds, const uint32_t* __restrict__ V,
+                                                       const uint32_t* __restrict__ offs, const uint32_t* __restrict__ counts, uint32_t* __restrict__ Bsum) {
+  const uint32_t b = b_begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= b_end) return;
+  const uint32_t o = offs[b], n = counts[b], stride = 1u << rounds;
+  if (n == 0) return;                                   // k_group_partial skips empty buckets by their count
+  typename CV::acc acc = CV::acc_zero();
+  for (uint32_t q = 0; q < n; q += stride) acc = CV::add_v(acc, CV::load_v(V, o + q));
+  CV::st_acc(Bsum + (size_t)b * CV::ACC_LIMBS, acc);
+}
+
 template <class CV>
 __global__ void __launch_bounds__(128) k_group_partial(MsmParams pr, ReduceGeom gm, int w_begin, int Kg, int rounds, const uint32_t* __restrict__ V,
-                                                       const uint32_t* __restrict__ offs, const uint32_t* __restrict__ counts, uint32_t* __restrict__ P) {
+                                                       const uint32_t* __restrict__ offs, const uint32_t* __restrict__ counts,
+                                                       const uint32_t* __restrict__ Bsum /* bucket sums of k_bucket_finish, or nullptr */, uint32_t* __restrict__ P) {
   // thread -> (window w, digit d, value v, chunk ch)
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t total = (uint32_t)Kg * gm.D * 32 * gm.NP;
@@ -833,7 +851,11 @@ __global__ void __launch_bounds__(128) k_group_partial(MsmParams pr, ReduceGeom 
       uint32_t idx = (high << (sh + wdt)) | (v << sh) | low;
       uint32_t b = w * pr.L + idx;
       uint32_t o = offs[b], n = counts[b];
-      for (uint32_t q = 0; q < n; q += stride) acc = CV::add_v(acc, CV::load_v(V, o + q));
+      if (Bsum) {
+        if (n) acc = CV::add(acc, CV::ld_acc(Bsum + (size_t)b * CV::ACC_LIMBS));
+      } else {
+        for (uint32_t q = 0; q < n; q += stride) acc = CV::add_v(acc, CV::load_v(V, o + q));
+      }
     }
   }
   CV::st_acc(P + (size_t)t * CV::ACC_LIMBS, acc);

@@ -30,7 +30,7 @@ struct mgb_ctx {
   cudaStream_t aux[3] = {};          // extra streams: window groups are pipelined against each other
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {}, ev_chunk[4] = {};
   cudaEvent_t ev[EV_COUNT] = {};
-  DevBuf table, scalars, ent_bucket, ent_rank, counts, offs, tile_sums, pairs, pairs2, V, recs, lifes, prebuf, redU[2], redW[2], misc, acc_out, out_xy, stage;
+  DevBuf table, scalars, ent_bucket, ent_rank, counts, offs, tile_sums, pairs, pairs2, V, recs, lifes, prebuf, bsum, redU[2], redW[2], misc, acc_out, out_xy, stage;
   uint32_t* h_pinned = nullptr;  // [0..31] out xy limbs + flag, [64..] misc readback
   int sm_count = 148;
   std::string err;
@@ -234,21 +234,27 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   if (ctx->h_pinned[66]) return fail(ctx, MGB_E_INVALID, "internal: a half-scalar exceeded its bound");
   (void)nslots;
 
-  // Depth of the bucket trees.  Full depth is ceil(log2(max bucket)).  A round costs at least one
-  // batch latency (~0.2 ms: prefix products, inversion, back-substitution) however few additions it
-  // holds, while an element left in a bucket costs the reduction ~2 ns; so the rounds stop where
-  // they would hold fewer than ~100 K additions (measured at 2^18 / 2^20 / 2^22: 5 / 7 / 7 rounds),
-  // and the reduction sums whatever a bucket has left.  Buckets far above the typical size (skewed
-  // scalars) force more rounds: at most 16 elements of any bucket are left to the reduction.
+  // Depth of the bucket trees.  Full depth is ceil(log2(max bucket)).  A round costs at least one batch latency
+  // (~0.2 ms: prefix products, inversion, back-substitution) however few additions it holds, and below ~0.3-0.5 M
+  // additions it is cheaper to leave them to k_bucket_finish (mixed XYZZ additions, 10 instead of 6
+  // multiplications each, but throughput-bound): measured best depth at 2^16 / 2^18 / 2^20 points = 2 / 3 / 4-5
+  // rounds.  Buckets far above the typical size (skewed scalars) force more rounds: at most 16 elements of
+  // any bucket are left to the finish kernel.
   int r_full = 0;
   while ((1u << r_full) < maxcount) r_full++;
   int rounds = 0;
-  uint32_t min_pairs = CV::BATCH_AFFINE ? 100000u : 20000u;   // rounds without an inversion have a much lower floor
+  uint32_t min_pairs = CV::BATCH_AFFINE ? 300000u : 20000u;   // rounds without an inversion have a much lower floor
   if (const char* ev = getenv("MGB_DEBUG_MINPAIRS")) min_pairs = (uint32_t)atoi(ev);
   while (rounds < r_full && rounds < SCAN_ROUNDS && round_pairs[rounds] >= min_pairs) rounds++;
   rounds = std::max(rounds, r_full - 4);
   if (opts && opts->verbose > 1) rounds = r_full;
   if (const char* ev = getenv("MGB_DEBUG_NROUNDS")) rounds = std::max(0, std::min(r_full, atoi(ev)));   // tuning aid
+  // Elements a bucket has left after the last round are summed once by k_bucket_finish when there are many of them
+  // (otherwise k_group_partial adds the single leftover directly as a mixed addition, which is cheaper).
+  uint64_t left = 0;
+  for (int r = rounds; r < SCAN_ROUNDS; r++) left += round_pairs[r];
+  bool use_finish = rounds < r_full && 4 * left >= pr.nbuckets;
+  if (const char* ev = getenv("MGB_DEBUG_FINISH")) use_finish = atoi(ev) != 0 && rounds < r_full;
   // round 0 gathers its operands from the point table (see k_scatter); without a round 0 the sorted
   // points are materialised by the scatter as the reduction expects
   const bool fuse = rounds > 0;
@@ -345,7 +351,14 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
     // bucket reduction of the group's windows (digit-decomposed weights, see engine.cuh)
     const uint32_t ngroups_g = (uint32_t)Kg * gm.D * 32;
     uint32_t* Pg = (uint32_t*)ctx->redU[0].p + (size_t)w_begin * gm.D * 32 * gm.NP * CV::ACC_LIMBS;
-    k_group_partial<CV><<<cdiv(ngroups_g * gm.NP, 128), 128, 0, sg>>>(pr, gm, w_begin, Kg, rounds, (const uint32_t*)ctx->V.p, offs, counts,
+    const uint32_t* bsum = nullptr;
+    if (use_finish) {
+      ENS(ctx, ctx->bsum, (size_t)pr.nbuckets * CV::ACC_LIMBS * 4);
+      k_bucket_finish<CV><<<cdiv(b_end - b_begin, 128), 128, 0, sg>>>(b_begin, b_end, rounds, (const uint32_t*)ctx->V.p, offs, counts, (uint32_t*)ctx->bsum.p);
+      launches++;
+      bsum = (const uint32_t*)ctx->bsum.p;
+    }
+    k_group_partial<CV><<<cdiv(ngroups_g * gm.NP, 128), 128, 0, sg>>>(pr, gm, w_begin, Kg, rounds, (const uint32_t*)ctx->V.p, offs, counts, bsum,
                                                                      (uint32_t*)ctx->redU[0].p);
     launches++;
     int remaining = gm.NP;
@@ -570,7 +583,7 @@ const char* mgb_last_error(const mgb_ctx* ctx) { return ctx ? ctx->err.c_str() :
 void mgb_destroy(mgb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  DevBuf* bufs[] = {&ctx->table, &ctx->scalars, &ctx->ent_bucket, &ctx->ent_rank, &ctx->counts, &ctx->offs, &ctx->tile_sums, &ctx->pairs, &ctx->pairs2, &ctx->V, &ctx->recs, &ctx->lifes, &ctx->prebuf, &ctx->redU[0], &ctx->redU[1], &ctx->redW[0], &ctx->redW[1], &ctx->misc,
+  DevBuf* bufs[] = {&ctx->table, &ctx->scalars, &ctx->ent_bucket, &ctx->ent_rank, &ctx->counts, &ctx->offs, &ctx->tile_sums, &ctx->pairs, &ctx->pairs2, &ctx->V, &ctx->recs, &ctx->lifes, &ctx->prebuf, &ctx->bsum, &ctx->redU[0], &ctx->redU[1], &ctx->redW[0], &ctx->redW[1], &ctx->misc,
                     &ctx->acc_out, &ctx->out_xy, &ctx->stage};
   for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);

@@ -182,3 +182,29 @@ def test_compute_msm_bigint_interface():
     xy, _ = points_to_bytes([P for P in pts if P is not None], cv.coord_bytes)
     sc2 = [s for s, P in zip(sc, pts) if P is not None]
     assert compute(xy.tobytes(), scalars_to_bytes(sc2).tobytes()) == got    # byte interface, the infinity point dropped
+
+
+@pytest.mark.parametrize("label", ["bls12-377", "ed-on-bls12-377"])
+def test_tree_depth_and_finish_paths(label, monkeypatch):
+    """The depth of the bucket trees and the choice between k_bucket_finish and direct leftover sums are tuning
+    decisions: every combination (0 rounds = the scatter materialises the points, .., full depth; finish on / off)
+    must give the same canonical point as the default."""
+    cv = CURVES[label]
+    n = 1 << 14
+    eng = m.MsmEngine(cv, 0, n)
+    try:
+        eng.random_points(n, seed=77)
+        sc = inputs.random_scalars(cv.q, n, 9)
+        ref, tm = eng.msm(sc, n=n)
+        for rounds in (0, 1, 2, 3, 6):
+            for finish in ("0", "1"):
+                monkeypatch.setenv("MGB_DEBUG_NROUNDS", str(rounds))
+                monkeypatch.setenv("MGB_DEBUG_FINISH", finish)
+                got, tm2 = eng.msm(sc, n=n)
+                assert got == ref, (label, rounds, finish)
+                assert tm2["rounds"] <= rounds
+        monkeypatch.delenv("MGB_DEBUG_NROUNDS")
+        monkeypatch.delenv("MGB_DEBUG_FINISH")
+        assert eng.msm(sc, n=n)[0] == ref
+    finally:
+        eng.close()
