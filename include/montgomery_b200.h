@@ -66,12 +66,12 @@ typedef struct mgb_timing {
   float decompose_slice;    /* "prepare points & scalars" + "slice scalars & count buckets"          */
   float sort;               /* "integrate bucket counts" + "sort points"                             */
   float accumulate;         /* "bucket accumulation"                                                  */
-  float reduce;             /* "normalize bucket storage" + "bucket reduction"                        */
+  float reduce;             /* "normalize bucket storage" + "bucket reduction" (incl. the sums of the bucket leftovers) */
   float final_sum;          /* "partition sum" + "final sum" + affine normalisation                   */
   float total;              /* whole call on the device, first kernel to result available             */
   int c, K, rounds;         /* window bits, number of windows, accumulation rounds                    */
   uint32_t max_bucket;      /* largest bucket (maxBucketSize, msm-batched-affine.ts:208)             */
-  uint64_t n_pairs;         /* affine / mixed additions performed in the accumulation phase          */
+  uint64_t n_pairs;         /* additions performed by the tree rounds of the accumulation phase      */
   uint32_t n_launches;      /* kernels launched by this call                                          */
 } mgb_timing;
 

@@ -10,6 +10,14 @@
 
 using namespace mgb;
 
+// k_batch_add shape: pairs per lane of the largest tile, resident blocks per SM (build-time knobs for experiments)
+#ifndef MGB_MINB
+#define MGB_MINB 4
+#endif
+#ifndef MGB_EMAX
+#define MGB_EMAX 64
+#endif
+
 namespace {
 
 thread_local std::string g_last_error;
@@ -73,10 +81,9 @@ int ensure(mgb_ctx* ctx, DevBuf& b, size_t bytes) {
 // (measured at 2^16: c = 12 / 14 -> 2.65 / 2.41 ms).  A sparse top window is balanced by sub-bucket
 // spreading (MsmParams::top_sub), not avoided.  The reference's own table (msm-common.ts:25-41) is
 // tuned for 16 CPU threads and is not used here.
-int default_window(int mag_bits, size_t n) {
+int default_window(int /*mag_bits*/, size_t n) {
   int lg = 0;
   while (((size_t)1 << lg) < n) lg++;
-  (void)mag_bits;
   const int c = lg >= 18 ? lg - 4 : lg - 2;
   return std::max(5, std::min(c, 22));
 }
@@ -229,10 +236,9 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   CU(ctx, cudaMemcpyAsync(ctx->h_pinned + 66, (uint32_t*)ctx->counts.p + pr.nbuckets, 4, cudaMemcpyDeviceToHost, st));
   CU(ctx, cudaMemcpyAsync(ctx->h_pinned + 68, misc + 512, SCAN_ROUNDS * 4, cudaMemcpyDeviceToHost, st));
   CU(ctx, cudaStreamSynchronize(st));
-  const uint32_t nslots = ctx->h_pinned[64], maxcount = ctx->h_pinned[65];
+  const uint32_t maxcount = ctx->h_pinned[65];
   const uint32_t* round_pairs = ctx->h_pinned + 68;
   if (ctx->h_pinned[66]) return fail(ctx, MGB_E_INVALID, "internal: a half-scalar exceeded its bound");
-  (void)nslots;
 
   // Depth of the bucket trees.  Full depth is ceil(log2(max bucket)).  A round costs at least one batch latency
   // (~0.2 ms: prefix products, inversion, back-substitution) however few additions it holds, and below ~0.3-0.5 M
@@ -293,12 +299,6 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
       PairEnt* pin = pl[r & 1];
       PairEnt* pout = pl[(r & 1) ^ 1];
       if constexpr (CV::BATCH_AFFINE) {
-#ifndef MGB_MINB
-#define MGB_MINB 4
-#endif
-#ifndef MGB_EMAX
-#define MGB_EMAX 64
-#endif
         constexpr int EMAX = MGB_EMAX, MINB = MGB_MINB;
         // additions of this round (exact over all windows, from the scan)
         const uint64_t est = (r < SCAN_ROUNDS ? (uint64_t)round_pairs[r] : 0) * Kg / pr.K;
@@ -405,14 +405,14 @@ int finish_timing(mgb_ctx* ctx, mgb_timing* tm) {
   tm->reduce = el(EV_ACC, EV_REDUCE);
   tm->final_sum = el(EV_REDUCE, EV_FINAL);
   tm->total = el(EV_START, EV_FINAL);
-  uint32_t h[264];
+  // additions done by the tree rounds: exact per-round counts from the scan (rounds beyond SCAN_ROUNDS -- heavily
+  // skewed inputs only -- from the pair-list counters)
+  uint32_t h[1024];
   CU(ctx, cudaMemcpy(h, (uint32_t*)ctx->misc.p, sizeof(h), cudaMemcpyDeviceToHost));
-  uint64_t s = 0;      // round 0 reads no pair list; its additions are counted by the scan
-  CU(ctx, cudaMemcpy(h, (uint32_t*)ctx->misc.p + 512, 4, cudaMemcpyDeviceToHost));
-  if (tm->rounds > 0) s = h[0];
-  CU(ctx, cudaMemcpy(h, (uint32_t*)ctx->misc.p, sizeof(h), cudaMemcpyDeviceToHost));
+  uint64_t s = 0;
+  for (int r = 0; r < tm->rounds && r < SCAN_ROUNDS; r++) s += h[512 + r];
   for (int g = 0; g < 4; g++)
-    for (int r = 1; r < tm->rounds && r < 63; r++) s += h[8 + 64 * g + r];
+    for (int r = SCAN_ROUNDS; r < tm->rounds && r < 63; r++) s += h[8 + 64 * g + r];
   tm->n_pairs = s;
   return 0;
 }
