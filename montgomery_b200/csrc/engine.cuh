@@ -81,10 +81,6 @@ struct WeierstrassPolicy {
     if (negate) r.y = F::neg(r.y);
     return r;
   }
-  // x coordinate of the point a reference word (index | endo | negate) stands for
-  MGB_DEV static Fe<FP> load_entry_x(const uint32_t* table, uint32_t ref) {
-    return ldg_fe<FP>(table + (size_t)(ref & REF_IDX) * ENTRY_LIMBS + ((ref & REF_ENDO) ? 2 * N : 0));
-  }
   MGB_DEV static vpoint load_v(const uint32_t* V, uint32_t slot) {
     const uint32_t* e = V + (size_t)slot * V_LIMBS;
     vpoint r; r.x = ld_fe<FP>(e); r.y = ld_fe<FP>(e + N); return r;
@@ -435,8 +431,8 @@ static __global__ void __launch_bounds__(SCAN_T) k_scan_add(uint32_t* __restrict
 // sums to V[slot]: one write and one read of every sorted point (192 B per entry, ~1 ms at 2^20) are
 // never done.  Buckets start at even slots (k_scan_tiles), so round 0 pairs slot 2q with 2q+1; the
 // last element of an odd-sized bucket gets REF_EMPTY as its partner and is simply copied by round 0.
-// With V != nullptr (no round follows: every bucket has at most one element) the point is
-// materialised here instead.
+// With V != nullptr (no tree round follows -- tiny inputs: k_bucket_finish / k_group_partial then read V
+// directly) the point is materialised here instead.
 //
 // The in-place bucket tree (msm-batched-affine.ts:243-263): in round r the element at local index j
 // (multiple of 2^(r+1)) absorbs the element at j + 2^r if that is inside the bucket of size n.  The
