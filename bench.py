@@ -50,7 +50,8 @@ def parse_args():
     ap.add_argument("--curve", default="bls12-377")
     ap.add_argument("--c", type=int, default=0, help="window bits (0 = engine default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-logn", type=int, default=18, help="log2 size of the CPU baseline sample")
+    ap.add_argument("--cpu-logn", type=int, default=0,
+                    help="log2 size of the CPU baseline sample (0 = the whole workload when the host has >= 8 cores, else 2^18)")
     return ap.parse_args()
 
 
@@ -111,6 +112,24 @@ def _measured_peak(key):
         return None
 
 
+def cpu_sample_logn(args):
+    """The CPU arm runs the WHOLE per-GPU workload (one 2^20 MSM is ~2 s on 16 cores, ~30 core-seconds) unless the
+    host is too small for that to stay within the bench's time budget."""
+    if args.cpu_logn:
+        return min(args.logn, args.cpu_logn)
+    return args.logn if (os.cpu_count() or 1) >= 8 else min(args.logn, 18)
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json, written by scripts/summarize_ncu.py traffic); None when absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            return json.load(fh)
+    except Exception:
+        return None
+
+
 def dist_setup(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -132,7 +151,8 @@ def run_reference(args):
         return
     from montgomery_b200 import curves, inputs
     curve = curves.BY_LABEL[args.curve]
-    n = 1 << min(args.logn, args.cpu_logn)
+    cl = cpu_sample_logn(args)
+    n = 1 << cl
     # same seeded known-dlog point set as the GPU arm, generated on the CPU (untimed, like the
     # reference's randomPointsFast before its timed loop); no GPU code runs in this arm
     from oracle import cpu_ref
@@ -146,8 +166,8 @@ def run_reference(args):
             times.append(ms)
     ms_step = float(np.mean(times))
     value = n / (ms_step * 1e-3)
-    sample = "one MSM of 2^%d points per step (the first 2^%d of the 2^%d-per-GPU workload), %d threads" % (
-        min(args.logn, args.cpu_logn), min(args.logn, args.cpu_logn), args.logn, threads)
+    sample = ("one MSM of 2^%d points per step (the whole per-GPU workload), %d threads" % (cl, threads)) if cl == args.logn else (
+        "one MSM of 2^%d points per step (the first 2^%d of the 2^%d-per-GPU workload), %d threads" % (cl, cl, args.logn, threads))
     line = {
         "impl": "reference", "metric": "msm_points_per_s", "value": value, "unit": "points/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -255,10 +275,12 @@ def run_b200(args):
     peak_imad_lo = ops.value
     algo_mads = ALGO_FIELD_MULTS_PER_POINT * MADS_PER_FIELD_MULT * n        # per GPU per step (reference op counts)
     acc_ms = phases["accumulate"]
+    traffic = ncu_traffic() if (args.logn == LOGN_DEFAULT and args.curve == "bls12-377") else None
     achieved = algo_mads / (phases["total"] * 1e-3)
     roofline = {
         "bound": "imad", "achieved": achieved / 1e12, "peak": peak_mads / 1e12, "unit": "T 32x32->64 MAD/s",
-        "frac": achieved / peak_mads, "traffic": None,
+        "frac": achieved / peak_mads, "traffic": traffic and traffic.get("bytes_per_launch"),
+        "traffic_note": traffic and traffic.get("note"),
         "note": "integer-multiply roofline of BASELINE.md: algorithmic MADs (108.6 field mults/point x 288) / device time of the whole MSM "
                 "(CUDA events on the engine's stream) / measured rate of carry-chained IMAD.WIDE.U32.X (one full 32x32+64->64 MAD per lane) on this GPU; "
                 "plain IMAD (mad.lo) issues at %.2f T/s, i.e. a full MAD costs two IMAD slots, as SURVEY 8d assumed" % (peak_imad_lo / 1e12),
@@ -286,14 +308,16 @@ def run_b200(args):
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "hbm_phases": hbm,
     }
     if world == 1 and not args.no_cpu_baseline:
-        ncpu = 1 << min(args.logn, args.cpu_logn)
+        cl = cpu_sample_logn(args)
+        ncpu = 1 << cl
         pts, _ = eng.get_points(0, ncpu)
         threads = os.cpu_count() or 1
         sc = host_sets[0].numpy()[:ncpu]
         cres, cms = cpu_reference_msm(args.curve, pts, sc, ncpu, threads)
         gres, _ = eng.msm(sc, n=ncpu)
         line["cpu_baseline"] = {"value": ncpu / (cms * 1e-3), "unit": "points/s", "cores": threads, "kind": "port",
-                                "sample": "one MSM of the first 2^%d points of the workload, %.0f ms" % (min(args.logn, args.cpu_logn), cms),
+                                "sample": ("one MSM of the whole 2^%d-point workload, %.0f ms" if cl == args.logn else
+                                           "one MSM of the first 2^%d points of the workload, %.0f ms") % (cl, cms),
                                 "agrees_with_gpu": cres == gres}
     print(json.dumps(line))
     if dist:

@@ -2,6 +2,7 @@
 
   python scripts/summarize_ncu.py launches gpurun_out/launches_r01.csv > profiles/r01_ncu_launch_summary.csv
   python scripts/summarize_ncu.py full gpurun_out/prof_batch_add_r01.ncu-rep > profiles/r01_ncu_full_k_batch_add.csv
+  python scripts/summarize_ncu.py traffic profiles/r01_ncu_full_k_batch_add.csv "round 2 of 5" > profiles/ncu_traffic.json
 """
 import csv, io, re, subprocess, sys
 from collections import OrderedDict
@@ -70,5 +71,25 @@ def full(path):
             print("stall_%s,%s,warps per issue" % (m.group(1), vals[col[h]]))
 
 
+def traffic(path, which=""):
+    """profiles/*_ncu_full_*.csv -> the small JSON bench.py reads for roofline.traffic (DRAM bytes of that one launch)."""
+    import json
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    vals, kernel = {}, ""
+    for ln in open(path):
+        if ln.startswith("# ncu") and "one launch:" in ln:
+            kernel = ln.split("one launch:")[1].strip()
+        f = ln.strip().split(",")
+        if len(f) == 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum"):
+            vals[f[0]] = float(f[1]) * scale.get(f[2], 1)
+    rd, wr = vals["dram__bytes_read.sum"], vals["dram__bytes_write.sum"]
+    print(json.dumps({
+        "kernel": "k_batch_add", "launch": which, "source": path, "dram_read_bytes": rd, "dram_write_bytes": wr,
+        "bytes_per_launch": rd + wr, "launch_us_under_ncu": vals.get("gpu__time_duration.sum"),
+        "note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE k_batch_add launch (%s) from the committed ncu --set full capture %s; "
+                "roofline.achieved is over the whole MSM (all launches)" % (which, path),
+        "kernel_name": kernel[:120]}, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])
