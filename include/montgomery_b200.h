@@ -121,14 +121,17 @@ int mgb_combine_partials(mgb_ctx* ctx, const void* d_partials, int count,
  * applies op elementwise on the device to n elements given as canonical LE bytes in/out.
  * field: 0 = BLS12-377 Fp, 1 = BLS12-377 Fr (= ed-on-377 base field), 2 = Pallas Fp, 3 = BLS12-381 Fp.
  * op: 0 mul, 1 add, 2 sub, 3 inverse (Fermat), 4 square, 5 inverse (binary gcd), 6 negate,
- * 7 inverse (division steps, the one the MSM uses). */
+ * 7 inverse (division steps, the one the MSM uses), 8 mul by the warp-cooperative routine (one limb per
+ * lane, csrc/warp.cuh; b is the second factor). */
 int mgb_field_op(int device, int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n);
 
 /* Integer-pipe microbenchmarks (roofline denominator).  mode: 0 = mad.lo.u32 (IMAD), 1 = mad.hi.u32,
  * 2 = mad.wide.u32 with 64-bit accumulate, 3 = mad.lo.cc/madc.hi.cc carry chain (IMAD.WIDE.U32.X:
  * the full 32x32+64->64 multiply-accumulate the field multiplication is made of), 4/5 = Fp377 /
  * Fr377 Montgomery multiplications through the out-of-line call, 6/7 = the same inlined, 8/9 = chains
- * of Fp377 division-step inversions on all lanes / on lane 0 of each warp (threads <= 128).  All
+ * of Fp377 division-step inversions on all lanes / on lane 0 of each warp (threads <= 128), 10/11 = a
+ * dependent chain of Fp377 products on a warp running alone: lane 0 with the per-thread routine / all
+ * lanes with the warp-cooperative one (ms / (2 iters) = latency of one product).  All
  * multiplicands change every iteration (a loop-invariant product would be hoisted by ptxas).
  * Returns operations per second (lane operations for modes 0-3, field multiplications for 4-7) in
  * *ops_per_s and the kernel time in *ms. */

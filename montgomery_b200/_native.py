@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmontgomery_b200.so")
+# MGB_LIB: an experiment build of the same library (montgomery_b200.build --variant); never a different backend
+LIB_PATH = os.environ.get("MGB_LIB") or os.path.join(_HERE, "libmontgomery_b200.so")
 
 BLS12_377_G1, PALLAS, ED_ON_BLS12_377, BLS12_381_G1 = 0, 1, 2, 3
 

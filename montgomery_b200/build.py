@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmontgomery_b200.so")
 OBJDIR = os.path.join(HERE, "build")
 SOURCES = ["msm.cu", "tools.cu"]
-HEADERS = ["ptx.cuh", "field.cuh", "ec.cuh", "engine.cuh", "constants_gen.cuh", os.path.join("..", "..", "include", "montgomery_b200.h")]
+HEADERS = ["ptx.cuh", "field.cuh", "ec.cuh", "coop.cuh", "warp.cuh", "engine.cuh", "constants_gen.cuh", os.path.join("..", "..", "include", "montgomery_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",
@@ -38,18 +38,25 @@ def needs_build():
     return False
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, variant=None, extra_flags=()):
+    """variant=None: the product library.  variant="name": an experiment build with extra_flags (e.g.
+    ("-DMGB_COOP_WARP_MUL=1",)) -> libmontgomery_b200_<name>.so, loaded only when MGB_LIB points at it."""
+    lib_path, objdir = LIB, OBJDIR
+    if variant:
+        lib_path = os.path.join(HERE, "libmontgomery_b200_%s.so" % variant)
+        objdir = os.path.join(OBJDIR, variant)
+        force = True
     if not force and not needs_build():
         return LIB
-    os.makedirs(OBJDIR, exist_ok=True)
+    os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
 
     def compile_one(src):
-        obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
         # MGB_NVCC_EXTRA: extra flags for experiments (e.g. -DMGB_MINB=5)
-        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("MGB_NVCC_EXTRA", "").split() + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("MGB_NVCC_EXTRA", "").split() + list(extra_flags) + ["-c", os.path.join(CSRC, src), "-o", obj]
         res = subprocess.run(cmd, capture_output=True, text=True)
-        log = os.path.join(OBJDIR, src + ".ptxas.log")
+        log = os.path.join(objdir, src + ".ptxas.log")
         with open(log, "w") as fh:
             fh.write(res.stdout + res.stderr)
         if res.returncode != 0:
@@ -58,14 +65,19 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
+    cmd = [nvcc, "-shared", "-o", lib_path] + objs + ["-lcudart"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     if verbose:
-        print("built", LIB)
-    return LIB
+        print("built", lib_path)
+    return lib_path
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose=True)
+    # python -m montgomery_b200.build [--force] [--variant NAME -DFLAG ...]
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        build(verbose=True, variant=sys.argv[i + 1], extra_flags=[a for a in sys.argv[i + 2:] if a.startswith("-")])
+    else:
+        build(force="--force" in sys.argv, verbose=True)

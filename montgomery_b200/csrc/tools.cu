@@ -30,6 +30,45 @@ __global__ void __launch_bounds__(128) k_field_op(int op, uint32_t n, const uint
   st_fe<P>(out + (size_t)i * P::N, F::from_mont(r));
 }
 
+// op 8: the warp-cooperative multiplication (warp.cuh), one element per 16-lane group.  The conversions in and
+// out of Montgomery form are products with R^2 and with 1 and go through the same routine.
+template <class P>
+__global__ void __launch_bounds__(128) k_field_op_warp(uint32_t n, const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, uint32_t* __restrict__ out) {
+  typedef WarpField<P> WF;
+  const uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;     // element of this 16-lane group
+  const int l = threadIdx.x & 15;
+  const bool live = e < n && l < P::N;                                   // every lane runs the shuffles, dead ones on zeros
+  uint32_t r2 = 0;
+  _Pragma("unroll") for (int k = 0; k < P::N; k++) r2 = (l == k) ? P::r2(k) : r2;
+  const uint32_t x = WF::mul(live ? a[(size_t)e * P::N + l] : 0u, r2);
+  const uint32_t y = WF::mul(live ? b[(size_t)e * P::N + l] : 0u, r2);
+  const uint32_t r = WF::mul(WF::mul(x, y), l == 0 ? 1u : 0u);
+  if (live) out[(size_t)e * P::N + l] = r;
+}
+
+// latency of a dependent chain of products on one warp: lane 0 alone (Field::mul) or the lanes together (WarpField::mul)
+template <class P, bool COOP>
+__global__ void __launch_bounds__(32) k_mullat(uint32_t* out, uint32_t seed, int iters) {
+  typedef Field<P> F;
+  const int l = threadIdx.x & 31;
+  Fe<P> a = F::one(), b = F::one();
+  a.v[0] ^= seed & 0xffff;
+  b.v[1] ^= blockIdx.x & 0xffff;
+  uint32_t s = 0;
+  if (COOP) {
+    uint32_t x = 0, y = 0;
+    _Pragma("unroll") for (int k = 0; k < P::N; k++) { x = (l == k) ? a.v[k] : x; y = (l == k) ? b.v[k] : y; }
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) { x = WarpField<P>::mul(x, y); y = WarpField<P>::mul(y, x); }
+    s = x ^ y;
+  } else if (l == 0) {
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) { a = F::mul(a, b); b = F::mul(b, a); }
+    _Pragma("unroll") for (int k = 0; k < P::N; k++) s ^= a.v[k] ^ b.v[k];
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // ---- integer pipe microbenchmarks: 8 independent dependency chains per thread
 template <int MODE>
 __global__ void __launch_bounds__(1024) k_imad(uint32_t* out, uint32_t seed, int iters) {
@@ -147,7 +186,14 @@ int mgb_field_op(int device, int field, int op, const uint8_t* a, const uint8_t*
   CUT(cudaMemcpy(da, a, bytes, cudaMemcpyHostToDevice));
   CUT(cudaMemcpy(db, b, bytes, cudaMemcpyHostToDevice));
   unsigned grid = (unsigned)((n + 127) / 128);
-  if (field == 0) k_field_op<Fp377><<<grid, 128>>>(op, (uint32_t)n, da, db, dout);
+  if (op == 8) {
+    grid = (unsigned)((n * 16 + 127) / 128);
+    if (field == 0) k_field_op_warp<Fp377><<<grid, 128>>>((uint32_t)n, da, db, dout);
+    else if (field == 1) k_field_op_warp<Fr377><<<grid, 128>>>((uint32_t)n, da, db, dout);
+    else if (field == 2) k_field_op_warp<FpPallas><<<grid, 128>>>((uint32_t)n, da, db, dout);
+    else k_field_op_warp<Fp381><<<grid, 128>>>((uint32_t)n, da, db, dout);
+  }
+  else if (field == 0) k_field_op<Fp377><<<grid, 128>>>(op, (uint32_t)n, da, db, dout);
   else if (field == 1) k_field_op<Fr377><<<grid, 128>>>(op, (uint32_t)n, da, db, dout);
   else if (field == 2) k_field_op<FpPallas><<<grid, 128>>>(op, (uint32_t)n, da, db, dout);
   else k_field_op<Fp381><<<grid, 128>>>(op, (uint32_t)n, da, db, dout);
@@ -179,11 +225,14 @@ int mgb_microbench(int device, int mode, int blocks_per_sm, int threads, int ite
       case 7: k_mulbench<Fr377, true><<<grid, threads>>>(d, 12345u, it); break;
       case 8: k_invbench<Fp377, false><<<grid, threads>>>(d, 12345u, it); break;
       case 9: k_invbench<Fp377, true><<<grid, threads>>>(d, 12345u, it); break;
+      case 10: k_mullat<Fp377, false><<<grid, 32>>>(d, 12345u, it); break;
+      case 11: k_mullat<Fp377, true><<<grid, 32>>>(d, 12345u, it); break;
       default: break;
     }
   };
-  if (mode < 0 || mode > 9) return MGB_E_INVALID;
+  if (mode < 0 || mode > 11) return MGB_E_INVALID;
   if (mode >= 8 && threads > 128) return MGB_E_INVALID;
+  if (mode >= 10) threads = 32;                         // one warp per block: the chain runs alone on its scheduler
   launch(iters / 8 + 1);  // warm-up
   CUT(cudaDeviceSynchronize());
   CUT(cudaEventRecord(e0));
@@ -196,6 +245,7 @@ int mgb_microbench(int device, int mode, int blocks_per_sm, int threads, int ite
   double per_thread;
   if (mode <= 2) per_thread = 16.0 * 8 * iters;        // instructions per thread
   else if (mode == 3) per_thread = 16.0 * 8 * iters;   // wide MADs per thread
+  else if (mode >= 10) per_thread = 2.0 * iters / 32;   // products per WARP (one chain per warp)
   else if (mode >= 8) per_thread = (mode == 9 ? 1.0 / 32 : 1.0) * iters;   // inversions per thread
   else per_thread = 2.0 * iters;                        // field multiplications per thread
   *ops_per_s = per_thread * (double)grid * threads / (ms * 1e-3);

@@ -2,7 +2,9 @@
 // carry flag, so the formulas can be checked against the oracle without a GPU.  Not shipped, not
 // linked into the product library.
 #define MGB_HOST_EMU 1
+#include "simt_emu.h"
 #include "../../montgomery_b200/csrc/ec.cuh"
+#include "../../montgomery_b200/csrc/warp.cuh"
 #include <cstring>
 using namespace mgb;
 
@@ -67,7 +69,42 @@ template <class P, class C> static void te_op(int op, uint32_t* out, const uint3
   }
 }
 
+// n products through the warp-cooperative multiplication (warp.cuh), two at a time: lanes 0-15 take pair 2j,
+// lanes 16-31 pair 2j+1 (a zero pair when n is odd); operands and results are Montgomery-form limbs.
+template <class P> static void warp_mul(uint32_t* out, const uint32_t* a, const uint32_t* b, int n) {
+  constexpr int N = P::N;
+  simt::run_warp([&](int lane) {
+    const int g = lane >> 4, l = lane & 15;
+    for (int j = 0; j < n; j += 2) {
+      const int e = j + g;
+      const bool live = e < n && l < N;
+      // lanes above the top limb pass garbage on purpose: the routine must ignore it
+      const uint32_t x = live ? a[e * N + l] : (e < n ? 0xdeadbeefu : 0u), y = live ? b[e * N + l] : 0x12345678u;
+      const uint32_t r = WarpField<P>::mul(x, y);
+      if (live) out[e * N + l] = r;
+      else if (e < n && r != 0) out[e * N] ^= 0xffffffffu;   // poison: spare lanes must return 0
+    }
+  });
+}
+
+// the carry / borrow resolution alone: lane l of group g gets t[g*16 + l] and c[g*16 + l] (c as 64-bit)
+template <class P> static void warp_finish(uint32_t* out, const uint32_t* t, const uint64_t* c) {
+  simt::run_warp([&](int lane) { out[lane] = WarpField<P>::finish(t[lane], c[lane]); });
+}
+
 extern "C" {
+void emu_warp_finish(int field, uint32_t* out, const uint32_t* t, const uint64_t* c) {
+  if (field == 0) warp_finish<Fp377>(out, t, c);
+  else if (field == 1) warp_finish<Fr377>(out, t, c);
+  else if (field == 2) warp_finish<FpPallas>(out, t, c);
+  else warp_finish<Fp381>(out, t, c);
+}
+void emu_warp_mul(int field, uint32_t* out, const uint32_t* a, const uint32_t* b, int n) {
+  if (field == 0) warp_mul<Fp377>(out, a, b, n);
+  else if (field == 1) warp_mul<Fr377>(out, a, b, n);
+  else if (field == 2) warp_mul<FpPallas>(out, a, b, n);
+  else warp_mul<Fp381>(out, a, b, n);
+}
 void emu_fe_op(int field, int op, uint32_t* out, const uint32_t* a, const uint32_t* b) {
   if (field == 0) fe_op<Fp377>(op, out, a, b);
   else if (field == 1) fe_op<Fr377>(op, out, a, b);

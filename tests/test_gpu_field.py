@@ -42,3 +42,20 @@ def test_field_ops_gpu(fid):
     assert _run(lib, fid, 5, a[:512], b[:512], n) == inv_exp     # binary gcd
     inv_all = [pow(x, -1, p) if x else 0 for x in a]
     assert _run(lib, fid, 7, a, b, n) == inv_all                  # division steps (used by the MSM)
+
+
+@pytest.mark.parametrize("fid", [0, 1, 2, 3])
+def test_warp_cooperative_mul_gpu(fid):
+    """csrc/warp.cuh (one limb per lane, used by the Horner kernels) == a*b mod p, including an element count
+    that leaves half a warp and most of the last block idle (the shuffles still run on every lane)."""
+    from montgomery_b200 import _native
+    lib = _native.lib()
+    p, n = FIELDS[fid]
+    rnd = random.Random(500 + fid)
+    R = 1 << (32 * n)
+    edge = [0, 1, 2, p - 1, p - 2, (p - 1) // 2, R % p, (R - 1) % p, (1 << 32) - 1, sum(0xffffffff << (32 * i) for i in range(n - 1))]
+    a = [x for x in edge for _ in edge] + [rnd.randrange(p) for _ in range(4001)]
+    b = [y for _ in edge for y in edge] + [rnd.randrange(p) for _ in range(4001)]
+    assert _run(lib, fid, 8, a, b, n) == [x * y % p for x, y in zip(a, b)]
+    assert _run(lib, fid, 8, a[:1], b[:1], n) == [a[0] * b[0] % p]
+    assert _run(lib, fid, 8, a[100:103], b[100:103], n) == [x * y % p for x, y in zip(a[100:103], b[100:103])]

@@ -19,7 +19,7 @@ FIELDS = [(BLS12_377.p, 12), (BLS12_377.q, 8), (PALLAS.p, 8), (BLS12_381.p, 12)]
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
     so = str(tmp_path_factory.mktemp("emu") / "emu.so")
-    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-x", "c++", "-o", so,
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-pthread", "-Wno-unknown-pragmas", "-x", "c++", "-o", so,
                            os.path.join(ROOT, "tests", "host_emu", "emu_lib.cpp")])
     return ctypes.CDLL(so)
 
@@ -157,3 +157,76 @@ def test_twisted_edwards_ops(emu):
         emu.emu_te_op(2, out, L(enc_a(P), n), L(enc_a(Q), n)); assert dec_e(I(out, n, 4)) == exp
         emu.emu_te_op(3, out, L(enc_e(P), n), L(enc_e(Q), n)); assert dec_e(I(out, n, 4)) == T.to_affine(T.double(P))
         emu.emu_te_op(4, out, L(enc_e(P), n), L(enc_e(Q), n)); assert tuple(t * Ri % p for t in I(out, n, 2)) == T.to_affine(P)
+
+
+# ---- warp-cooperative multiplication (csrc/warp.cuh): one limb per lane, run on a 32-thread lockstep
+# emulation of a warp (tests/host_emu/simt_emu.h) -- the same source the Horner kernels compile for the GPU
+
+@pytest.mark.parametrize("fid", [0, 1, 2, 3])
+def test_warp_cooperative_mul(emu, fid):
+    p, n = FIELDS[fid]
+    R = 1 << (32 * n)
+    Ri = pow(R, -1, p)
+    rnd = random.Random(200 + fid)
+    edge = [0, 1, p - 1, p - 2, (p - 1) // 2, R % p, (R - 1) % p, (1 << 32) - 1,
+            sum(0xffffffff << (32 * i) for i in range(n)) % p, sum(0xffffffff << (32 * i) for i in range(n - 1))]
+    A = [x for x in edge for _ in edge] + [rnd.randrange(p) for _ in range(501)]      # odd count: the second half-warp idles once
+    B = [y for _ in edge for y in edge] + [rnd.randrange(p) for _ in range(501)]
+    out = (ctypes.c_uint32 * (n * len(A)))()
+    emu.emu_warp_mul(fid, out, L(A, n), L(B, n), len(A))
+    got = I(out, n, len(A))
+    for a, b, g in zip(A, B, got):
+        assert g == a * b * Ri % p, (fid, hex(a), hex(b))
+
+
+@pytest.mark.parametrize("fid", [0, 1, 2, 3])
+def test_warp_carry_and_borrow_lookahead(emu, fid):
+    """WarpField::finish alone, on inputs a random product practically never produces: carries that ripple through
+    runs of 0xffffffff limbs, borrows that ripple through limbs equal to the modulus's, pending carries at their maximum."""
+    p, n = FIELDS[fid]
+    rnd = random.Random(300 + fid)
+    plimbs = [(p >> (32 * i)) & 0xFFFFFFFF for i in range(n)]
+    cases = []   # (t limbs, c limbs) with sum (t_i + c_i) 2^(32 i) < 2p
+
+    def val(t, c):
+        return sum((ti + ci) << (32 * i) for i, (ti, ci) in enumerate(zip(t, c)))
+
+    for lo_run in range(0, n - 1):                       # carry generated below a run of all-ones limbs
+        for hi_run in range(lo_run, n - 1):
+            t = [rnd.getrandbits(32) for _ in range(n)]
+            c = [0] * n
+            for i in range(lo_run, hi_run + 1):
+                t[i] = 0xFFFFFFFF
+            t[n - 1] = rnd.randrange(plimbs[n - 1])      # keeps the value below 2p
+            c[lo_run] = rnd.choice([1, 2, (1 << 32) + 1, (1 << 33) + 8])
+            if lo_run > 0:
+                t[lo_run - 1], c[lo_run - 1] = 0xFFFFFFFF, rnd.choice([1, 1 << 32])    # ...and a carry arriving through the shuffle
+            cases.append((t, c))
+    for k in range(1, n):                                # value = p + 2^(32k) - 1 - (anything below limb 0..): borrows through equal limbs
+        v = p + (1 << (32 * k)) - 1 - rnd.randrange(2)
+        if v < 2 * p:
+            cases.append(([(v >> (32 * i)) & 0xFFFFFFFF for i in range(n)], [0] * n))
+    for v in (p, p - 1, p + 1, 2 * p - 1, 0, 1):
+        cases.append(([(v >> (32 * i)) & 0xFFFFFFFF for i in range(n)], [0] * n))
+    for _ in range(60):                                  # random split of a random value into limbs and pending carries
+        c = [rnd.randrange((1 << 33) + 9) for _ in range(n - 2)] + [rnd.randrange(4), 0]
+        v = rnd.randrange(sum(ci << (32 * i) for i, ci in enumerate(c)), 2 * p)
+        rest = v - sum(ci << (32 * i) for i, ci in enumerate(c))
+        cases.append(([(rest >> (32 * i)) & 0xFFFFFFFF for i in range(n)], c))
+    if len(cases) % 2:
+        cases.append(cases[0])
+    for j in range(0, len(cases), 2):                    # two elements per warp (lanes 0-15, 16-31)
+        t = (ctypes.c_uint32 * 32)()
+        c = (ctypes.c_uint64 * 32)()
+        for g in range(2):
+            for i in range(n):
+                t[16 * g + i] = cases[j + g][0][i]
+                c[16 * g + i] = cases[j + g][1][i]
+        out = (ctypes.c_uint32 * 32)()
+        emu.emu_warp_finish(fid, out, t, c)
+        for g in range(2):
+            v = val(*cases[j + g])
+            assert v < 2 * p
+            got = sum(int(out[16 * g + i]) << (32 * i) for i in range(n))
+            assert got == (v - p if v >= p else v), (fid, j + g, hex(v))
+            assert all(out[16 * g + i] == 0 for i in range(n, 16))
