@@ -75,3 +75,19 @@ def test_seeded_inputs():
         z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & (2**64 - 1)
         return z ^ (z >> 31)
     assert [int(v) for v in a] == [sm(1, i) for i in range(8)]
+
+
+def test_c99_host_builds_and_links(tmp_path):
+    """bindings/c/example_msm.c -- a plain C99 host of the ABI -- compiles with -pedantic against the header, links
+    against the library, and (no GPU here) exits with the documented 'no CUDA device' code instead of computing."""
+    import shutil
+    import subprocess
+    from montgomery_b200 import _native
+    lib_dir = os.path.dirname(_native.LIB_PATH)
+    exe = str(tmp_path / "example_msm")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "bindings", "c", "example_msm.c"), "-L", lib_dir, "-lmontgomery_b200",
+                           "-Wl,-rpath," + lib_dir, "-o", exe])
+    if shutil.which("nvidia-smi") is None:
+        res = subprocess.run([exe, "8"], capture_output=True, text=True)
+        assert res.returncode == 3 and "mgb_create: -2" in res.stderr
