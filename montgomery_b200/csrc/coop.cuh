@@ -16,7 +16,7 @@
 #include "warp.cuh"
 
 #ifndef MGB_COOP_WARP_MUL
-#define MGB_COOP_WARP_MUL 0
+#define MGB_COOP_WARP_MUL 1
 #endif
 
 namespace mgb {

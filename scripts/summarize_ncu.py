@@ -74,7 +74,7 @@ def full(path):
 def traffic(path, which=""):
     """profiles/*_ncu_full_*.csv -> the small JSON bench.py reads for roofline.traffic (DRAM bytes of that one launch)."""
     import json
-    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1, "ms": 1e3, "s": 1e6}
     vals, kernel = {}, ""
     for ln in open(path):
         if ln.startswith("# ncu") and "one launch:" in ln:
