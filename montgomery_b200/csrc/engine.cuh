@@ -508,8 +508,11 @@ __global__ void __launch_bounds__(256) k_scatter(MsmParams pr, int w_begin, int 
 // kernel's own streaming traffic (ncu: 29 % of the warp samples stalled on a long scoreboard).  So
 // every global input of an iteration -- pair entry, operands, stored prefix product -- is copied
 // asynchronously (cp.async, L2 -> shared memory, no registers, no L1) one iteration ahead (entries:
-// two ahead, their content gives the operand addresses) into a per-thread staging slot; an
-// iteration starts with cp.async.wait_group 0 and conflict-free 16-byte shared-memory reads.
+// two ahead, their content gives the operand addresses) into per-thread staging slots read back
+// with conflict-free 16-byte shared-memory loads.  The backward pass goes further and keeps the
+// coordinates IN those slots for the whole iteration, re-reading them where a formula needs them:
+// Field::mul is an out-of-line call, and holding both points across its five calls does not fit
+// in 128 registers (see the comment at the backward pass).
 template <class P>
 MGB_DEV Fe<P> shfl_fe(const Fe<P>& a, int src) {
   Fe<P> r;
@@ -531,6 +534,7 @@ MGB_DEV void cp_async8(void* smem, const void* gmem) {
 }
 MGB_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 MGB_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+MGB_DEV void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }   // all but the most recent group
 
 template <class CV>
 MGB_DEV typename CV::vpoint load_ref(const uint32_t* table, uint32_t ref) {
@@ -557,8 +561,10 @@ __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ 
   typedef Fe<FP> fe;
   constexpr int N = CV::N;
   constexpr int CW = N / 4;             // 16-byte chunks per coordinate
-  constexpr int CPT = 2 * CW;           // per point (x | y contiguous)
-  constexpr int ST_A = 0, ST_B = CPT, ST_PRE = 2 * CPT, ST_ENT = 2 * CPT + CW, ST_TOTAL = ST_ENT + 3;
+  // staging slots, in chunks: A.x | B.x (pairs of even e; the forward pass uses these too) | A.y | B.y | prefix
+  // product | 3 pair entries | A.x | B.x (pairs of odd e in the backward pass)
+  constexpr int ST_A = 0, ST_PRE = 4 * CW, ST_ENT = 5 * CW;
+  constexpr int ST_X1 = ST_ENT + 3, ST_TOTAL = ST_X1 + 2 * CW;
   __shared__ uint4 stage[ST_TOTAL][128];   // [chunk][thread]: conflict-free 16-byte accesses
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -583,16 +589,6 @@ __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ 
     }
     return x;
   };
-  // a staged point: x | y as stored in V, or (round 0, endomorphism image) y | beta*x from the table entry
-  auto stage_point = [&](int c0, bool swapped, bool negate) -> typename CV::vpoint {
-    const fe lo = stage_fe(c0), hi = stage_fe(c0 + CW);
-    typename CV::vpoint p;
-    p.x = swapped ? hi : lo;
-    p.y = swapped ? lo : hi;
-    if (negate) p.y = F::neg(p.y);
-    return p;
-  };
-
   // Tile hand-out.  Every warp first takes ONE statically assigned tile, then tiles are handed out
   // dynamically (warps drift apart -- inversion latency varies -- and a static split would leave the
   // tail of every round to a few warps).  The static first tile matters for the late rounds, which
@@ -632,7 +628,8 @@ __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ 
       }
     };
     auto is_add = [&](const uint4& en) -> bool { return en.x != REF_EMPTY && !(FIRST && en.y == REF_EMPTY); };
-    // global address of operand A / B of an entry (2N contiguous limbs; round 0: see stage_point)
+    // global address of operand A / B of an entry (2N contiguous limbs: x | y as stored in V; round 0: a table
+    // entry's x | y, or y | beta*x for an endomorphism image)
     auto addr_a = [&](const uint4& en) -> const uint32_t* {
       if (FIRST) return table + (size_t)(en.x & REF_IDX) * CV::ENTRY_LIMBS + ((en.x & REF_ENDO) ? N : 0);
       return V + (size_t)en.x * CV::V_LIMBS;
@@ -696,56 +693,137 @@ __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ 
       if (lane + dlt <= 31) sfx = ns;
     }
     fe inv = shfl_fe<FP>(pfx, 31);                  // -> 1 / (this warp's total)
-    // the backward pass's first inputs travel while lane 0 inverts
-    auto issue_data = [&](int e) {   // operands and prefix product of pair e -> ST_A, ST_B, ST_PRE
+    // Backward pass that keeps its operands in SHARED MEMORY instead of registers.  Field::mul is an out-of-line
+    // call that needs ~70 registers of its own; with 128 per thread the caller can keep ~55 values across a call,
+    // and the one-piece version below holds both points, the running inverse and the inverted denominator (72) --
+    // it spills, and every iteration waits for the reloads (ncu: 5 % of the samples of round 0).  Here only the
+    // running inverse and one intermediate live across a call; coordinates are re-read from the staging slots
+    // when a formula needs them:
+    //   * x halves of pair e sit in one of TWO slot pairs (parity of e), so the prefetch of pair e - 1, issued at
+    //     the top of iteration e (group X, with the prefix product and entry e - 2), does not overwrite them;
+    //   * y halves are needed only after two products: they are prefetched at the END of the previous iteration
+    //     (group Y) into a single slot pair.
+    // An iteration waits for "all but the most recent group" twice: X_e at the top (Y_e may still be in flight),
+    // Y_e before the slope (X_(e-1) may still be in flight).
+    constexpr int ST_AY = ST_A + 2 * CW, ST_BY = ST_A + 3 * CW;
+    auto xslot = [&](int e) -> int { return (e & 1) ? ST_X1 : ST_A; };      // A.x at xslot, B.x at xslot + CW
+    auto issue_xpart = [&](int e) {   // x of both operands and the prefix product of pair e
       const uint4 en = *ent_slot(e);
       if (en.x == REF_EMPTY) return;
-      const uint32_t* pa = addr_a(en);
-      _Pragma("unroll") for (int c = 0; c < CPT; c++) cp_async16(&stage[ST_A + c][tid], pa + 4 * c);
+      const int xs = xslot(e);
+      const uint32_t* pa = addr_a(en) + ((FIRST && (en.x & REF_ENDO)) ? N : 0);
+      _Pragma("unroll") for (int c = 0; c < CW; c++) cp_async16(&stage[xs + c][tid], pa + 4 * c);
       if (is_add(en)) {
-        const uint32_t* pb = addr_b(en);
-        _Pragma("unroll") for (int c = 0; c < CPT; c++) cp_async16(&stage[ST_B + c][tid], pb + 4 * c);
+        const uint32_t* pb = addr_b(en) + ((FIRST && (en.y & REF_ENDO)) ? N : 0);
+        _Pragma("unroll") for (int c = 0; c < CW; c++) cp_async16(&stage[xs + CW + c][tid], pb + 4 * c);
       }
       _Pragma("unroll") for (int c = 0; c < CW; c++) cp_async16(&stage[ST_PRE + c][tid], my_pre + (e * CW + c) * 32);
     };
+    auto issue_ypart = [&](int e) {   // y of both operands (it comes first in the operand of an endomorphism image)
+      const uint4 en = *ent_slot(e);
+      if (en.x == REF_EMPTY) return;
+      const uint32_t* pa = addr_a(en) + ((FIRST && (en.x & REF_ENDO)) ? 0 : N);
+      _Pragma("unroll") for (int c = 0; c < CW; c++) cp_async16(&stage[ST_AY + c][tid], pa + 4 * c);
+      if (is_add(en)) {
+        const uint32_t* pb = addr_b(en) + ((FIRST && (en.y & REF_ENDO)) ? 0 : N);
+        _Pragma("unroll") for (int c = 0; c < CW; c++) cp_async16(&stage[ST_BY + c][tid], pb + 4 * c);
+      }
+    };
     cp_async_wait_all();
-    issue_data(E - 1);
+    issue_xpart(E - 1);
+    cp_async_commit();
+    issue_ypart(E - 1);
     cp_async_commit();
     if (lane == 0) inv = F::inv_divsteps(inv);
     inv = shfl_fe<FP>(inv, 0);
-    fe left = shfl_fe<FP>(pfx, lane == 0 ? 0 : lane - 1);
-    fe right = shfl_fe<FP>(sfx, lane == 31 ? 31 : lane + 1);
     fe u = inv;                                   // -> 1 / (this lane's total)
-    if (lane > 0) u = F::mul(u, left);
-    if (lane < 31) u = F::mul(u, right);
-    // ---- backward pass
+    {
+      const fe left = shfl_fe<FP>(pfx, lane == 0 ? 0 : lane - 1);
+      if (lane > 0) u = F::mul(u, left);
+      const fe right = shfl_fe<FP>(sfx, lane == 31 ? 31 : lane + 1);
+      if (lane < 31) u = F::mul(u, right);
+    }
+    // The slot reservation of an emitted pair -- one atomicAdd per warp and iteration -- is consumed one iteration
+    // later, so its round trip to L2 overlaps the next addition instead of ending the current one.
+    uint32_t pe_mask = 0, pe_base = 0;            // pending emission: lanes, reserved base (valid on the leader), entry
+    PairEnt pe_ent = {0u, 0u};
+    auto flush_emit = [&]() {
+      if (pe_mask) {                              // warp-uniform
+        const uint32_t b = __shfl_sync(0xffffffffu, pe_base, __ffs(pe_mask) - 1);
+        if ((pe_mask >> lane) & 1u) pairs_out[b + __popc(pe_mask & ((1u << lane) - 1u))] = pe_ent;
+      }
+    };
     _Pragma("unroll 1") for (int e = E - 1; e >= 0; e--) {
-      cp_async_wait_all();                       // data of pair e, entry e - 1
+      cp_async_wait_but_one();                   // X_e: x halves and prefix product of pair e, entry e - 1
       const uint4 cur = *ent_slot(e);
       const bool valid = cur.x != REF_EMPTY;
       const bool add = is_add(cur);
-      typename CV::vpoint A = stage_point(ST_A, FIRST && (cur.x & REF_ENDO), FIRST && (cur.x & REF_NEG));
-      typename CV::vpoint B = stage_point(ST_B, FIRST && (cur.y & REF_ENDO), FIRST && (cur.y & REF_NEG));
+      const int xs = xslot(e);
       const fe pre = stage_fe(ST_PRE);
-      if (e > 0) issue_data(e - 1);
+      if (e > 0) issue_xpart(e - 1);
       fetch_ent(e - 2, true);
-      cp_async_commit();
+      cp_async_commit();                         // group X_(e-1)
       const fe inv_den = F::mul(u, pre);
       PairEnt out = {0u, 0u};
       if (valid) {
         out.slot = FIRST ? 2u * (q0 + base + (uint32_t)e * 32u) : cur.x;
         out.life = FIRST ? (cur.z >> (8 * ((q0 + base + (uint32_t)e * 32u) & 3))) & 0xffu : cur.y;
-        if (!add) {
-          CV::store_v(V, out.slot, A);              // round 0, no partner: the denominator was 1
-        } else {
-          fe d;
-          const int kind = G::add_prepare(A, B, d);
-          u = F::mul(u, d);
-          CV::store_v(V, out.slot, G::template add_finish<false>(kind, A, B, inv_den));
-        }
       }
-      emit_pair(valid && (uint32_t)(r + 1) < out.life, out, pairs_out, npairs_out);
+      // kind of the addition (Weierstrass::add_prepare): 0 = generic, 1 = doubling, 2 / 3 = B / A is infinity,
+      // 4 = P + (-P).  The generic case is decided from the x coordinates alone; in the rare other cases the
+      // complete operands are fetched and written back into the staging slots, so that one straight-line formula
+      // below serves both (the flow has no second copy of the products).
+      int kind = 0;
+      bool y_ready = false;                      // rare path: staged y already carries its sign
+      if (add) {
+        fe d;
+        if (!G::prepare_x(stage_fe(xs), stage_fe(xs + CW), d)) {
+          const typename CV::vpoint A = full_a(cur), B = full_b(cur);
+          kind = G::add_prepare(A, B, d);
+          cp_async_wait_but_one();               // Y_e has landed: the slots can be overwritten
+          _Pragma("unroll") for (int c = 0; c < CW; c++) {
+            stage[xs + c][tid] = make_uint4(A.x.v[4 * c], A.x.v[4 * c + 1], A.x.v[4 * c + 2], A.x.v[4 * c + 3]);
+            stage[xs + CW + c][tid] = make_uint4(B.x.v[4 * c], B.x.v[4 * c + 1], B.x.v[4 * c + 2], B.x.v[4 * c + 3]);
+            stage[ST_AY + c][tid] = make_uint4(A.y.v[4 * c], A.y.v[4 * c + 1], A.y.v[4 * c + 2], A.y.v[4 * c + 3]);
+            stage[ST_BY + c][tid] = make_uint4(B.y.v[4 * c], B.y.v[4 * c + 1], B.y.v[4 * c + 2], B.y.v[4 * c + 3]);
+          }
+          y_ready = true;
+        }
+        u = F::mul(u, d);
+      }
+      cp_async_wait_but_one();                   // Y_e
+      auto stage_y = [&](int c0, uint32_t ref) -> fe {
+        const fe y = stage_fe(c0);
+        return (FIRST && !y_ready && (ref & REF_NEG)) ? F::neg(y) : y;
+      };
+      if (valid) {
+        typename CV::vpoint R;
+        if (add && kind < 2) {
+          fe num;
+          if (kind == 1) { const fe xx = F::sqr(stage_fe(xs)); num = F::add(F::dbl(xx), xx); }      // tangent: 3 x^2 / 2 y
+          else num = F::sub(stage_y(ST_BY, cur.y), stage_y(ST_AY, cur.x));
+          const fe m = F::mul(num, inv_den);
+          R.x = F::sqr(m);
+          const fe ax = stage_fe(xs);
+          R.x = F::sub(F::sub(R.x, ax), stage_fe(xs + CW));      // doubling: B = A, so this is m^2 - 2x
+          R.y = F::mul(m, F::sub(ax, R.x));
+          R.y = F::sub(R.y, stage_y(ST_AY, cur.x));
+        } else if (kind == 4) {
+          R = G::affine_inf();
+        } else {                                 // no partner (round 0) or B infinite: A; A infinite: B
+          R.x = stage_fe(kind == 3 ? xs + CW : xs);
+          R.y = stage_y(kind == 3 ? ST_BY : ST_AY, kind == 3 ? cur.y : cur.x);
+        }
+        CV::store_v(V, out.slot, R);
+      }
+      if (e > 0) issue_ypart(e - 1);
+      cp_async_commit();                         // group Y_(e-1)
+      flush_emit();
+      pe_mask = __ballot_sync(0xffffffffu, valid && (uint32_t)(r + 1) < out.life);
+      pe_ent = out;
+      if (pe_mask && lane == __ffs(pe_mask) - 1) pe_base = atomicAdd(npairs_out, (uint32_t)__popc(pe_mask));
     }
+    flush_emit();
     cp_async_wait_all();
   }
 }
