@@ -8,16 +8,12 @@
 // shared memory.  XYZZ doubling = 3 levels instead of 9 sequential products, addition = 4 instead
 // of 14; extended twisted-Edwards addition = 3 instead of 9.
 //
-// MGB_COOP_WARP_MUL = 1: every one of those products is itself spread over the lanes of its warp
-// (warp.cuh: one limb per lane, ~12 dependent steps instead of 277 dependent MADs); the warp's
-// lane 0 still does the additions / subtractions between the products.
+// Every one of those products is itself spread over the lanes of its warp (warp.cuh: one limb per lane, ~12
+// dependent steps instead of 277 dependent MADs; 554 ns instead of 974 ns for a lone 377-bit product); the warp's
+// lane 0 does the additions / subtractions between the products.
 #pragma once
 #include "ec.cuh"
 #include "warp.cuh"
-
-#ifndef MGB_COOP_WARP_MUL
-#define MGB_COOP_WARP_MUL 1
-#endif
 
 namespace mgb {
 
@@ -32,7 +28,6 @@ struct CoopMem {  // slots of N limbs in shared memory
   MGB_DEV void st(int slot, const Fe<P>& a) const {
     _Pragma("unroll") for (int i = 0; i < P::N; i++) base[slot * P::N + i] = a.v[i];
   }
-#ifndef MGB_HOST_EMU
   // slot[out] = slot[a] * slot[b] by ALL lanes of the calling warp (lane l moves limb l); what lane 0 wrote
   // before the call is visible to the others, and the result is visible to lane 0 after it.  Out of line:
   // one copy of the product per kernel, so the Horner loop stays inside the instruction cache.
@@ -45,7 +40,6 @@ struct CoopMem {  // slots of N limbs in shared memory
     __syncwarp();
   }
   MGB_DEV void wmul(int out, int a, int b) const { wmul_impl(base, out, a, b); }
-#endif
 };
 
 // slot map: 0..3 = P (accumulator), 4..7 = Q (second operand), 8.. = temporaries, flags after the slots
@@ -58,70 +52,58 @@ struct CoopWeierstrass {
   typedef Weierstrass<P> G;
   enum { X = 0, Y = 1, ZZ = 2, ZZZ = 3, X2 = 4, Y2 = 5, ZZ2 = 6, ZZZ2 = 7, T = 8 };
 
-  // P <- 2P  (dbl-2008-s-1, a = 0)
-  MGB_DEV static void dbl(CoopMem<P> m, volatile int* flag) {
+  // P <- 2^count P  (dbl-2008-s-1, a = 0).  Per doubling three formula levels and three barriers, nothing else:
+  //  * the infinity / 2-torsion test runs on warp 2 during level 1 (the level's results are only temporaries);
+  //  * X', ZZ', ZZZ' are written straight into the accumulator slots by the level that produces them (no other
+  //    warp reads those slots in that level);
+  //  * Y' = M (S - X') - W Y needs two products of level 3 from different warps: it stays pending as the pair
+  //    (T+10, T+7) and the subtraction is done by the first reader -- lane 0 of warp 0 at the start of the next
+  //    doubling's level 1 (warp 2 repeats it for its test) -- or by the epilogue after the last doubling.
+  MGB_DEV static void dbl_n(CoopMem<P> m, volatile int* flag, int count) {
     const int warp = threadIdx.x >> 5;
     const bool act = (threadIdx.x & 31) == 0;
-    if (threadIdx.x == 0) *flag = F::is_zero(m.ld(ZZ)) || F::is_zero(m.ld(Y)) ? 1 : 0;   // infinity or 2-torsion
-    __syncthreads();
-    if (*flag) {
-      if (threadIdx.x == 0 && !F::is_zero(m.ld(ZZ))) { m.st(X, F::zero()); m.st(Y, F::one()); m.st(ZZ, F::zero()); m.st(ZZZ, F::zero()); }
+    for (int i = 0; i < count; i++) {
+      if (warp == 0) {
+        if (act) {
+          fe y = m.ld(Y);
+          if (i) { y = F::sub(m.ld(T + 10), m.ld(T + 7)); m.st(Y, y); }
+          m.st(T + 0, F::dbl(y));
+        }
+        m.wmul(T + 1, T + 0, T + 0);                                         // U = 2Y, V = U^2
+      }
+      if (warp == 1) { m.wmul(T + 2, X, X); if (act) { fe xx = m.ld(T + 2); m.st(T + 2, F::add(F::dbl(xx), xx)); } }   // M = 3 X^2
+      if (warp == 2 && act) {
+        const fe y = i ? F::sub(m.ld(T + 10), m.ld(T + 7)) : m.ld(Y);
+        *flag = (F::is_zero(m.ld(ZZ)) || F::is_zero(y)) ? 1 : 0;              // infinity or 2-torsion
+      }
       __syncthreads();
-      return;
-    }
-#if MGB_COOP_WARP_MUL
-    if (warp == 0) { if (act) m.st(T + 0, F::dbl(m.ld(Y))); m.wmul(T + 1, T + 0, T + 0); }            // U, V = U^2
-    if (warp == 1) { m.wmul(T + 2, X, X); if (act) { fe xx = m.ld(T + 2); m.st(T + 2, F::add(F::dbl(xx), xx)); } }   // M = 3 X^2
-    __syncthreads();
-    if (warp == 0) m.wmul(T + 3, T + 0, T + 1);                            // W = U*V
-    if (warp == 1) m.wmul(T + 4, X, T + 1);                                // S = X*V
-    if (warp == 2) m.wmul(T + 5, T + 2, T + 2);                            // M^2
-    if (warp == 3) m.wmul(T + 6, T + 1, ZZ);                               // ZZ' = V*ZZ
-    __syncthreads();
-    if (warp == 0) m.wmul(T + 7, T + 3, Y);                                // W*Y
-    if (warp == 1) m.wmul(T + 8, T + 3, ZZZ);                              // ZZZ' = W*ZZZ
-    if (warp == 2) {
-      if (act) {
-        fe S = m.ld(T + 4);
-        fe x3 = F::sub(m.ld(T + 5), F::dbl(S));
-        m.st(T + 9, x3);
-        m.st(T + 11, F::sub(S, x3));
+      if (*flag) {                             // the result of this and of every further doubling is the neutral element
+        if (threadIdx.x == 0) { m.st(X, F::zero()); m.st(Y, F::one()); m.st(ZZ, F::zero()); m.st(ZZZ, F::zero()); }
+        __syncthreads();
+        return;
       }
-      m.wmul(T + 10, T + 2, T + 11);                                       // M*(S - X3)
-    }
-    __syncthreads();
-#else
-    if (act) {
-      if (warp == 0) { fe U = F::dbl(m.ld(Y)); m.st(T + 0, U); m.st(T + 1, F::sqr(U)); }
-      if (warp == 1) { fe xx = F::sqr(m.ld(X)); m.st(T + 2, F::add(F::dbl(xx), xx)); }
-    }
-    __syncthreads();
-    if (act) {
-      if (warp == 0) m.st(T + 3, F::mul(m.ld(T + 0), m.ld(T + 1)));       // W = U*V
-      if (warp == 1) m.st(T + 4, F::mul(m.ld(X), m.ld(T + 1)));           // S = X*V
-      if (warp == 2) m.st(T + 5, F::sqr(m.ld(T + 2)));                    // M^2
-      if (warp == 3) m.st(T + 6, F::mul(m.ld(T + 1), m.ld(ZZ)));          // ZZ' = V*ZZ
-    }
-    __syncthreads();
-    if (act) {
-      if (warp == 0) m.st(T + 7, F::mul(m.ld(T + 3), m.ld(Y)));           // W*Y
-      if (warp == 1) m.st(T + 8, F::mul(m.ld(T + 3), m.ld(ZZZ)));         // ZZZ' = W*ZZZ
+      if (warp == 0) m.wmul(T + 3, T + 0, T + 1);                            // W = U*V
+      if (warp == 1) m.wmul(T + 4, X, T + 1);                                // S = X*V
+      if (warp == 2) m.wmul(T + 5, T + 2, T + 2);                            // M^2
+      if (warp == 3) m.wmul(ZZ, T + 1, ZZ);                                  // ZZ' = V*ZZ, in place
+      __syncthreads();
+      if (warp == 0) m.wmul(T + 7, T + 3, Y);                                // W*Y
+      if (warp == 1) m.wmul(ZZZ, T + 3, ZZZ);                                // ZZZ' = W*ZZZ, in place
       if (warp == 2) {
-        fe S = m.ld(T + 4);
-        fe x3 = F::sub(m.ld(T + 5), F::dbl(S));
-        m.st(T + 9, x3);
-        m.st(T + 10, F::mul(m.ld(T + 2), F::sub(S, x3)));                 // M*(S - X3)
+        if (act) {
+          fe S = m.ld(T + 4);
+          fe x3 = F::sub(m.ld(T + 5), F::dbl(S));
+          m.st(X, x3);                                                       // X', in place
+          m.st(T + 11, F::sub(S, x3));
+        }
+        m.wmul(T + 10, T + 2, T + 11);                                       // M*(S - X')
       }
+      __syncthreads();
     }
-    __syncthreads();
-#endif
-    if (threadIdx.x == 0) {
-      m.st(X, m.ld(T + 9));
-      m.st(Y, F::sub(m.ld(T + 10), m.ld(T + 7)));
-      m.st(ZZ, m.ld(T + 6));
-      m.st(ZZZ, m.ld(T + 8));
+    if (count > 0) {
+      if (threadIdx.x == 0) m.st(Y, F::sub(m.ld(T + 10), m.ld(T + 7)));
+      __syncthreads();
     }
-    __syncthreads();
   }
 
   // P <- P + Q  (add-2008-s; the degenerate cases fall back to the complete serial formula)
@@ -136,19 +118,10 @@ struct CoopWeierstrass {
       __syncthreads();
       return;
     }
-#if MGB_COOP_WARP_MUL
     if (warp == 0) m.wmul(T + 0, X, ZZ2);      // U1
     if (warp == 1) m.wmul(T + 1, X2, ZZ);      // U2
     if (warp == 2) m.wmul(T + 2, Y, ZZZ2);     // S1
     if (warp == 3) m.wmul(T + 3, Y2, ZZZ);     // S2
-#else
-    if (act) {
-      if (warp == 0) m.st(T + 0, F::mul(m.ld(X), m.ld(ZZ2)));     // U1
-      if (warp == 1) m.st(T + 1, F::mul(m.ld(X2), m.ld(ZZ)));     // U2
-      if (warp == 2) m.st(T + 2, F::mul(m.ld(Y), m.ld(ZZZ2)));    // S1
-      if (warp == 3) m.st(T + 3, F::mul(m.ld(Y2), m.ld(ZZZ)));    // S2
-    }
-#endif
     __syncthreads();
     if (threadIdx.x == 0) *flag = F::is_zero(F::sub(m.ld(T + 1), m.ld(T + 0))) ? 1 : 0;
     __syncthreads();
@@ -163,7 +136,6 @@ struct CoopWeierstrass {
       __syncthreads();
       return;
     }
-#if MGB_COOP_WARP_MUL
     if (warp == 0) { if (act) m.st(T + 4, F::sub(m.ld(T + 1), m.ld(T + 0))); m.wmul(T + 5, T + 4, T + 4); }   // P, PP
     if (warp == 1) { if (act) m.st(T + 6, F::sub(m.ld(T + 3), m.ld(T + 2))); m.wmul(T + 7, T + 6, T + 6); }   // R, RR
     if (warp == 2) m.wmul(T + 8, ZZ, ZZ2);
@@ -185,32 +157,6 @@ struct CoopWeierstrass {
     if (warp == 1) m.wmul(T + 15, T + 2, T + 10);   // S1*PPP
     if (warp == 2) m.wmul(T + 4, T + 9, T + 10);    // ZZZ3 (T+4 = P is dead)
     __syncthreads();
-#else
-    if (act) {
-      if (warp == 0) { fe Pd = F::sub(m.ld(T + 1), m.ld(T + 0)); m.st(T + 4, Pd); m.st(T + 5, F::sqr(Pd)); }   // P, PP
-      if (warp == 1) { fe R = F::sub(m.ld(T + 3), m.ld(T + 2)); m.st(T + 6, R); m.st(T + 7, F::sqr(R)); }      // R, RR
-      if (warp == 2) m.st(T + 8, F::mul(m.ld(ZZ), m.ld(ZZ2)));
-      if (warp == 3) m.st(T + 9, F::mul(m.ld(ZZZ), m.ld(ZZZ2)));
-    }
-    __syncthreads();
-    if (act) {
-      if (warp == 0) m.st(T + 10, F::mul(m.ld(T + 4), m.ld(T + 5)));    // PPP
-      if (warp == 1) m.st(T + 11, F::mul(m.ld(T + 0), m.ld(T + 5)));    // Q = U1*PP
-      if (warp == 2) m.st(T + 12, F::mul(m.ld(T + 8), m.ld(T + 5)));    // ZZ3
-    }
-    __syncthreads();
-    if (act) {
-      if (warp == 0) {
-        fe Q = m.ld(T + 11);
-        fe x3 = F::sub(F::sub(m.ld(T + 7), m.ld(T + 10)), F::dbl(Q));
-        m.st(T + 13, x3);
-        m.st(T + 14, F::mul(m.ld(T + 6), F::sub(Q, x3)));               // R*(Q - X3)
-      }
-      if (warp == 1) m.st(T + 15, F::mul(m.ld(T + 2), m.ld(T + 10)));   // S1*PPP
-      if (warp == 2) m.st(T + 4, F::mul(m.ld(T + 9), m.ld(T + 10)));    // ZZZ3 (T+4 = P is dead)
-    }
-    __syncthreads();
-#endif
     if (threadIdx.x == 0) {
       m.st(X, m.ld(T + 13));
       m.st(Y, F::sub(m.ld(T + 14), m.ld(T + 15)));
@@ -297,7 +243,6 @@ struct CoopTwistedEdwards {
   MGB_DEV static void add_from(CoopMem<P> m, int qb) {
     const int warp = threadIdx.x >> 5;
     const bool act = (threadIdx.x & 31) == 0;
-#if MGB_COOP_WARP_MUL
     const int t0 = T + 4 + 2 * warp, t1 = t0 + 1;       // two private operand slots per warp
     if (act) {
       if (warp == 0) { m.st(t0, F::sub(m.ld(Y), m.ld(X))); m.st(t1, F::sub(m.ld(qb + Y), m.ld(qb + X))); }
@@ -319,26 +264,8 @@ struct CoopTwistedEdwards {
     }
     m.wmul(warp == 0 ? X : (warp == 1 ? Y : (warp == 2 ? Tt : Z)), t0, t1);
     __syncthreads();
-#else
-    if (act) {
-      if (warp == 0) m.st(T + 0, F::mul(F::sub(m.ld(Y), m.ld(X)), F::sub(m.ld(qb + Y), m.ld(qb + X))));   // A
-      if (warp == 1) m.st(T + 1, F::mul(F::add(m.ld(Y), m.ld(X)), F::add(m.ld(qb + Y), m.ld(qb + X))));   // B
-      if (warp == 2) m.st(T + 2, F::mul(F::mul(m.ld(Tt), m.ld(qb + Tt)), G::k2d()));                       // C
-      if (warp == 3) m.st(T + 3, F::dbl(F::mul(m.ld(Z), m.ld(qb + Z))));                                   // D
-    }
-    __syncthreads();
-    if (act) {
-      fe A = m.ld(T + 0), B = m.ld(T + 1), Cc = m.ld(T + 2), D = m.ld(T + 3);
-      fe E = F::sub(B, A), Ff = F::sub(D, Cc), Gg = F::add(D, Cc), H = F::add(B, A);
-      if (warp == 0) m.st(X, F::mul(E, Ff));
-      if (warp == 1) m.st(Y, F::mul(Gg, H));
-      if (warp == 2) m.st(Tt, F::mul(E, H));
-      if (warp == 3) m.st(Z, F::mul(Ff, Gg));
-    }
-    __syncthreads();
-#endif
   }
-  MGB_DEV static void dbl(CoopMem<P> m, volatile int*) { add_from(m, 0); }
+  MGB_DEV static void dbl_n(CoopMem<P> m, volatile int*, int count) { for (int i = 0; i < count; i++) add_from(m, 0); }
   MGB_DEV static void add(CoopMem<P> m, volatile int*) { add_from(m, 4); }
 };
 

@@ -1085,7 +1085,7 @@ __global__ void __launch_bounds__(128) k_window_assemble(MsmParams pr, ReduceGeo
   load_point(0, in + ((size_t)w * gm.D + gm.D - 1) * CV::ACC_LIMBS);
   __syncthreads();
   for (int dd = gm.D - 2; dd >= 0; dd--) {
-    for (int k = 0; k < gm.width[dd]; k++) CV::Coop::dbl(m, &flag);
+    CV::Coop::dbl_n(m, &flag, gm.width[dd]);
     load_point(4, in + ((size_t)w * gm.D + dd) * CV::ACC_LIMBS);
     __syncthreads();
     CV::Coop::add(m, &flag);
@@ -1112,7 +1112,7 @@ __global__ void __launch_bounds__(128) k_final(int K, int c, const uint32_t* __r
   load_point(0, Sw + (size_t)(K - 1) * CV::ACC_LIMBS);
   __syncthreads();
   for (int w = K - 2; w >= 0; w--) {
-    for (int d = 0; d < c; d++) CV::Coop::dbl(m, &flag);
+    CV::Coop::dbl_n(m, &flag, c);
     load_point(4, Sw + (size_t)w * CV::ACC_LIMBS);
     __syncthreads();
     CV::Coop::add(m, &flag);
