@@ -616,13 +616,13 @@ __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ 
 
     // pair entry e -> staging slot (e mod 3); x = REF_EMPTY marks "no pair"
     auto ent_slot = [&](int e) -> uint4* { return &stage[ST_ENT + (e + 3) % 3][tid]; };
-    auto fetch_ent = [&](int e, bool with_life) {
+    auto fetch_ent = [&](int e) {
       uint4* dst = ent_slot(e);
       const uint32_t idx = base + (uint32_t)e * 32u;
       if (e < 0 || e >= E || idx >= npairs) { dst->x = REF_EMPTY; return; }
       if (FIRST) {
         cp_async8(dst, recs + q0 + idx);
-        if (with_life) cp_async4(&dst->z, reinterpret_cast<const uint32_t*>(lifes) + ((q0 + idx) >> 2));   // the word holding the byte
+        cp_async4(&dst->z, reinterpret_cast<const uint32_t*>(lifes) + ((q0 + idx) >> 2));   // the word holding the byte
       } else {
         cp_async8(dst, pairs + idx);
       }
@@ -653,20 +653,28 @@ __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ 
         cp_async16(&stage[ST_A + CW + c][tid], xb + 4 * c);
       }
     };
-    fetch_ent(0, false);
-    fetch_ent(1, false);
+    fetch_ent(0);
+    fetch_ent(1);
     cp_async_commit();
     cp_async_wait_all();
     issue_x(0);
     cp_async_commit();
     fe run = F::one();
+    // does the sum written for this entry go on to the next round (is it a left operand there)?
+    auto continues = [&](const uint4& en, int e) -> bool {
+      if (en.x == REF_EMPTY) return false;
+      const uint32_t life = FIRST ? (en.z >> (8 * ((q0 + base + (uint32_t)e * 32u) & 3))) & 0xffu : en.y;
+      return (uint32_t)(r + 1) < life;
+    };
+    uint32_t n_emit = 0;                         // this lane's entries of the next round's pair list
     _Pragma("unroll 1") for (int e = 0; e < E; e++) {
       cp_async_wait_all();                       // x of pair e, entry e + 1
       const uint4 cur = *ent_slot(e);
       const fe xa = stage_fe(ST_A), xb = stage_fe(ST_A + CW);
       issue_x(e + 1);
-      fetch_ent(e + 2, false);
+      fetch_ent(e + 2);
       cp_async_commit();
+      n_emit += continues(cur, e) ? 1u : 0u;
       fe d = F::one();
       if (is_add(cur)) {
         if (!G::prepare_x(xa, xb, d)) {  // rare: an operand is infinity or the x coordinates coincide
@@ -680,8 +688,18 @@ __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ 
     }
     cp_async_wait_all();
     __threadfence_block();                         // the prefix products are read back (by this thread) through cp.async
-    fetch_ent(E - 1, true);                        // first entries of the backward pass travel during the warp products
-    fetch_ent(E - 2, true);
+    // ONE reservation in the next round's pair list per tile (its size is known after the forward pass) instead of
+    // one atomicAdd per warp and iteration of the backward pass: ptxas turns every such atomic into its own
+    // warp-aggregated sequence whose result-distributing shuffle waits for the round trip to L2 on the spot
+    // (ncu: 3.4 % of the samples of round 0), whichever way the source defers the use of the result.
+    uint32_t tile_out = 0;
+    {
+      const uint32_t total = __reduce_add_sync(0xffffffffu, n_emit);
+      if (lane == 0 && total) tile_out = atomicAdd(npairs_out, total);
+      tile_out = __shfl_sync(0xffffffffu, tile_out, 0);
+    }
+    fetch_ent(E - 1);                        // first entries of the backward pass travel during the warp products
+    fetch_ent(E - 2);
     cp_async_commit();
     // ---- warp products: pfx = c_0..c_lane, sfx = c_lane..c_31
     fe pfx = run, sfx = run;
@@ -743,16 +761,6 @@ __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ 
       const fe right = shfl_fe<FP>(sfx, lane == 31 ? 31 : lane + 1);
       if (lane < 31) u = F::mul(u, right);
     }
-    // The slot reservation of an emitted pair -- one atomicAdd per warp and iteration -- is consumed one iteration
-    // later, so its round trip to L2 overlaps the next addition instead of ending the current one.
-    uint32_t pe_mask = 0, pe_base = 0;            // pending emission: lanes, reserved base (valid on the leader), entry
-    PairEnt pe_ent = {0u, 0u};
-    auto flush_emit = [&]() {
-      if (pe_mask) {                              // warp-uniform
-        const uint32_t b = __shfl_sync(0xffffffffu, pe_base, __ffs(pe_mask) - 1);
-        if ((pe_mask >> lane) & 1u) pairs_out[b + __popc(pe_mask & ((1u << lane) - 1u))] = pe_ent;
-      }
-    };
     _Pragma("unroll 1") for (int e = E - 1; e >= 0; e--) {
       cp_async_wait_but_one();                   // X_e: x halves and prefix product of pair e, entry e - 1
       const uint4 cur = *ent_slot(e);
@@ -761,7 +769,7 @@ __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ 
       const int xs = xslot(e);
       const fe pre = stage_fe(ST_PRE);
       if (e > 0) issue_xpart(e - 1);
-      fetch_ent(e - 2, true);
+      fetch_ent(e - 2);
       cp_async_commit();                         // group X_(e-1)
       const fe inv_den = F::mul(u, pre);
       PairEnt out = {0u, 0u};
@@ -818,12 +826,13 @@ __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ 
       }
       if (e > 0) issue_ypart(e - 1);
       cp_async_commit();                         // group Y_(e-1)
-      flush_emit();
-      pe_mask = __ballot_sync(0xffffffffu, valid && (uint32_t)(r + 1) < out.life);
-      pe_ent = out;
-      if (pe_mask && lane == __ffs(pe_mask) - 1) pe_base = atomicAdd(npairs_out, (uint32_t)__popc(pe_mask));
+      {
+        const bool em = valid && (uint32_t)(r + 1) < out.life;      // == continues(cur, e) of the forward pass
+        const uint32_t mk = __ballot_sync(0xffffffffu, em);
+        if (em) pairs_out[tile_out + __popc(mk & ((1u << lane) - 1u))] = out;
+        tile_out += __popc(mk);
+      }
     }
-    flush_emit();
     cp_async_wait_all();
   }
 }

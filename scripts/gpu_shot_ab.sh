@@ -25,6 +25,7 @@ PY
 echo "winner: $WIN" | tee gpurun_out/winner.txt
 if [ "$WIN" != base ]; then export MGB_LIB=$PWD/montgomery_b200/libmontgomery_b200_$WIN.so; fi
 timeout 300 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$WIN.txt 2>&1
+if [ "${QUICK:-0}" = 1 ]; then tail -3 gpurun_out/pytest_gpu_$WIN.txt; cat gpurun_out/ab_*.json; exit 0; fi
 timeout 200 python bench.py --gpus 1 --steps 10 --warmup 3 > gpurun_out/bench_$WIN.json 2> gpurun_out/bench_$WIN.err
 # launch list of the bench command under ncu (shares only: the times are cold-cache and serialised)
 timeout 90 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$WIN.csv \
