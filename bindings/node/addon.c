@@ -12,7 +12,7 @@
  *   msm(ctx, Uint8Array scalars, n, c, projective) -> Promise<{xy: Uint8Array, isZero, log}>
  *                                                            mgb_msm on a libuv worker thread, so the event loop is
  *                                                            never blocked (the reference's msm is async as well)
- *   destroy(ctx)                                             mgb_destroy       (stopThreads)
+ * The context is released by its finaliser (mgb_destroy, the analogue of stopThreads) when the handle is collected.
  * Errors become JS exceptions / rejected promises carrying mgb_last_error's text.  One in-flight msm per context.
  */
 #include <node_api.h>
