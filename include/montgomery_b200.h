@@ -122,7 +122,8 @@ int mgb_combine_partials(mgb_ctx* ctx, const void* d_partials, int count,
  * field: 0 = BLS12-377 Fp, 1 = BLS12-377 Fr (= ed-on-377 base field), 2 = Pallas Fp, 3 = BLS12-381 Fp.
  * op: 0 mul, 1 add, 2 sub, 3 inverse (Fermat), 4 square, 5 inverse (binary gcd), 6 negate,
  * 7 inverse (division steps, the one the MSM uses), 8 mul by the warp-cooperative routine (one limb per
- * lane, csrc/warp.cuh; b is the second factor). */
+ * lane, csrc/warp.cuh; b is the second factor), 9 inverse by the lane-parallel division-step routine of
+ * csrc/warp.cuh (an experiment, not used by the MSM yet). */
 int mgb_field_op(int device, int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n);
 
 /* Integer-pipe microbenchmarks (roofline denominator).  mode: 0 = mad.lo.u32 (IMAD), 1 = mad.hi.u32,
@@ -131,7 +132,8 @@ int mgb_field_op(int device, int field, int op, const uint8_t* a, const uint8_t*
  * Fr377 Montgomery multiplications through the out-of-line call, 6/7 = the same inlined, 8/9 = chains
  * of Fp377 division-step inversions on all lanes / on lane 0 of each warp (threads <= 128), 10/11 = a
  * dependent chain of Fp377 products on a warp running alone: lane 0 with the per-thread routine / all
- * lanes with the warp-cooperative one (ms / (2 iters) = latency of one product).  All
+ * lanes with the warp-cooperative one (ms / (2 iters) = latency of one product), 12 = like 9 with the
+ * lane-parallel inverse (one inversion per warp, all lanes working).  All
  * multiplicands change every iteration (a loop-invariant product would be hoisted by ptxas).
  * Returns operations per second (lane operations for modes 0-3, field multiplications for 4-7) in
  * *ops_per_s and the kernel time in *ms. */

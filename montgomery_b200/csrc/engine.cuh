@@ -15,6 +15,11 @@
 #include "ec.cuh"
 #include "coop.cuh"
 
+// build-time switch (experiment, off): k_batch_add inverts a tile's total with the lane-parallel inverse of warp.cuh
+#ifndef MGB_WARP_INV
+#define MGB_WARP_INV 0
+#endif
+
 namespace mgb {
 
 // ---------------------------------------------------------------- vector loads / stores
@@ -752,8 +757,12 @@ __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ 
     cp_async_commit();
     issue_ypart(E - 1);
     cp_async_commit();
+#if MGB_WARP_INV
+    inv = WarpField<FP>::inv_call(inv);           // experiment: all lanes share the inversion (warp.cuh)
+#else
     if (lane == 0) inv = F::inv_divsteps(inv);
     inv = shfl_fe<FP>(inv, 0);
+#endif
     fe u = inv;                                   // -> 1 / (this lane's total)
     {
       const fe left = shfl_fe<FP>(pfx, lane == 0 ? 0 : lane - 1);

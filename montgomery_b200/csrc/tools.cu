@@ -46,6 +46,17 @@ __global__ void __launch_bounds__(128) k_field_op_warp(uint32_t n, const uint32_
   if (live) out[(size_t)e * P::N + l] = r;
 }
 
+// op 9: the lane-parallel division-step inverse (warp.cuh), one element per WARP (every lane passes the same value)
+template <class P>
+__global__ void __launch_bounds__(128) k_field_op_warp_inv(uint32_t n, const uint32_t* __restrict__ a, uint32_t* __restrict__ out) {
+  typedef Field<P> F;
+  const uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  Fe<P> x = F::zero();
+  if (e < n) x = F::to_mont(ld_fe<P>(a + (size_t)e * P::N));       // warp-uniform
+  const Fe<P> r = WarpField<P>::inv_call(x);
+  if (e < n && (threadIdx.x & 31) == (e & 31)) st_fe<P>(out + (size_t)e * P::N, F::from_mont(r));   // any lane holds it
+}
+
 // latency of a dependent chain of products on one warp: lane 0 alone (Field::mul) or the lanes together (WarpField::mul)
 template <class P, bool COOP>
 __global__ void __launch_bounds__(32) k_mullat(uint32_t* out, uint32_t seed, int iters) {
@@ -154,12 +165,15 @@ __global__ void __launch_bounds__(1024) k_mulbench(uint32_t* out, uint32_t seed,
 }
 
 // inversion latency: dependent chain of division-step inverses, all lanes or lane 0 only
-template <class P, bool LANE0>
+template <class P, bool LANE0, bool COOP = false>
 __global__ void __launch_bounds__(128) k_invbench(uint32_t* out, uint32_t seed, int iters) {
   typedef Field<P> F;
   Fe<P> a = F::one();
-  a.v[0] ^= (seed ^ threadIdx.x ^ (blockIdx.x << 8)) & 0xffffff;
-  if (!LANE0 || (threadIdx.x & 31) == 0) {
+  a.v[0] ^= (seed ^ (COOP ? threadIdx.x >> 5 : threadIdx.x) ^ (blockIdx.x << 8)) & 0xffffff;
+  if (COOP) {                                            // every lane of a warp holds the same element
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) { a = WarpField<P>::inv_call(a); a.v[0] ^= 5; }
+  } else if (!LANE0 || (threadIdx.x & 31) == 0) {
 #pragma unroll 1
     for (int it = 0; it < iters; it++) { a = F::inv_divsteps(a); a.v[0] ^= 5; }
   }
@@ -186,7 +200,14 @@ int mgb_field_op(int device, int field, int op, const uint8_t* a, const uint8_t*
   CUT(cudaMemcpy(da, a, bytes, cudaMemcpyHostToDevice));
   CUT(cudaMemcpy(db, b, bytes, cudaMemcpyHostToDevice));
   unsigned grid = (unsigned)((n + 127) / 128);
-  if (op == 8) {
+  if (op == 9) {
+    grid = (unsigned)((n * 32 + 127) / 128);
+    if (field == 0) k_field_op_warp_inv<Fp377><<<grid, 128>>>((uint32_t)n, da, dout);
+    else if (field == 1) k_field_op_warp_inv<Fr377><<<grid, 128>>>((uint32_t)n, da, dout);
+    else if (field == 2) k_field_op_warp_inv<FpPallas><<<grid, 128>>>((uint32_t)n, da, dout);
+    else k_field_op_warp_inv<Fp381><<<grid, 128>>>((uint32_t)n, da, dout);
+  }
+  else if (op == 8) {
     grid = (unsigned)((n * 16 + 127) / 128);
     if (field == 0) k_field_op_warp<Fp377><<<grid, 128>>>((uint32_t)n, da, db, dout);
     else if (field == 1) k_field_op_warp<Fr377><<<grid, 128>>>((uint32_t)n, da, db, dout);
@@ -227,12 +248,13 @@ int mgb_microbench(int device, int mode, int blocks_per_sm, int threads, int ite
       case 9: k_invbench<Fp377, true><<<grid, threads>>>(d, 12345u, it); break;
       case 10: k_mullat<Fp377, false><<<grid, 32>>>(d, 12345u, it); break;
       case 11: k_mullat<Fp377, true><<<grid, 32>>>(d, 12345u, it); break;
+      case 12: k_invbench<Fp377, true, true><<<grid, threads>>>(d, 12345u, it); break;
       default: break;
     }
   };
-  if (mode < 0 || mode > 11) return MGB_E_INVALID;
+  if (mode < 0 || mode > 12) return MGB_E_INVALID;
   if (mode >= 8 && threads > 128) return MGB_E_INVALID;
-  if (mode >= 10) threads = 32;                         // one warp per block: the chain runs alone on its scheduler
+  if (mode == 10 || mode == 11) threads = 32;                         // one warp per block: the chain runs alone on its scheduler
   launch(iters / 8 + 1);  // warm-up
   CUT(cudaDeviceSynchronize());
   CUT(cudaEventRecord(e0));
@@ -245,6 +267,7 @@ int mgb_microbench(int device, int mode, int blocks_per_sm, int threads, int ite
   double per_thread;
   if (mode <= 2) per_thread = 16.0 * 8 * iters;        // instructions per thread
   else if (mode == 3) per_thread = 16.0 * 8 * iters;   // wide MADs per thread
+  else if (mode == 12) per_thread = 1.0 / 32 * iters;   // inversions per WARP
   else if (mode >= 10) per_thread = 2.0 * iters / 32;   // products per WARP (one chain per warp)
   else if (mode >= 8) per_thread = (mode == 9 ? 1.0 / 32 : 1.0) * iters;   // inversions per thread
   else per_thread = 2.0 * iters;                        // field multiplications per thread

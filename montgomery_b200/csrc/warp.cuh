@@ -1,5 +1,6 @@
-// Warp-cooperative multi-limb Montgomery multiplication: ONE field element spread over the lanes
-// of a 16-lane group, one 32-bit limb per lane.
+// Warp-cooperative multi-limb field arithmetic: ONE field element spread over the lanes of a
+// 16-lane group, one limb per lane -- the Montgomery product (used by the Horner kernels) and a
+// lane-parallel division-step inverse (experiment, see WarpField::inv).
 //
 // Field::mul (field.cuh) keeps a whole element in one thread: 277 carry-dependent IMAD.WIDE for a
 // 377-bit product, ~1.2 us when the warp runs alone.  That is the right shape for the throughput
@@ -115,6 +116,134 @@ struct WarpField {
     const uint32_t d = lo - p - ((bw >> l) & 1u);
     return ((bw >> N) & 1u) ? lo : d;
   }
+
+  // ---------------------------------------------------------------------------------------------
+  // Lane-parallel division-step inverse (experiment for the next round; Field::inv_divsteps is the
+  // one in use).  Field::inv_divsteps runs on ONE lane: per batch of 30 division steps it finds the
+  // 2x2 transition matrix from the low words (inherently serial) and then applies it to the four
+  // L-limb numbers f, g, d, e -- two thirds of its instructions, and 10 % of all instructions the
+  // batched-addition kernel issues, with 1 of 32 lanes active.  Here the matrix is found by every
+  // lane redundantly (uniform control flow), and the application is spread over the warp: lane k of
+  // the first half-warp holds limb k of (f, g), lane 16 + k limb k of (d, e).  Limbs are signed and
+  // LAZY: after u*x + v*y (+ p_k*m) each lane keeps the low 30 bits, hands them one lane down
+  // (= division by 2^30) and the high part stays; a second one-lane-up hop of the small overflow
+  // leaves every limb in [-6, 2^30 + 5] (the top limb carries the sign).  Values are exact, only
+  // their representation is not canonical -- so "g == 0" is tested on the low words first (exact
+  // mod 2^32) and, when those vanish, by one sequential carry walk over the lanes.
+  // All 32 lanes call with the SAME a (Montgomery form); every lane returns a^-1.  a = 0 -> 0.
+  MGB_DEV static Fe<P> inv(const Fe<P>& a) {
+    typedef Field<P> F;
+    constexpr int L = P::N30;
+    constexpr int32_t M30 = 0x3fffffff;
+    static_assert(L < W, "one spare lane above the top limb");
+    if (F::is_zero(a)) return a;
+    const int ln = warp::lane();
+    const int k = ln & (W - 1);
+    const bool de = (ln & W) != 0;                 // second half-warp: (d, e); first: (f, g)
+    int32_t x = 0, y = 0, pk = 0;                  // this lane's limb of (f | d) and (g | e); modulus limb for the d, e lanes
+    _Pragma("unroll") for (int i = 0; i < L; i++) {
+      const int bit = 30 * i, w = bit >> 5, sh = bit & 31;
+      const uint32_t lo = a.v[w], hi = (w + 1 < N) ? a.v[w + 1] : 0u;
+      const uint32_t gi = (sh ? ((lo >> sh) | (sh > 2 ? (hi << (32 - sh)) : 0u)) : lo) & (uint32_t)M30;
+      if (k == i) {
+        x = de ? 0 : P::mod30(i);
+        y = de ? (i == 0 ? 1 : 0) : (int32_t)gi;
+        pk = de ? P::mod30(i) : 0;
+      }
+    }
+    int32_t eta = -1;
+    for (int iter = 0; iter < 64; iter++) {
+      // low words of f, g (exact mod 2^32 whatever the representation), low and top limbs of d, e
+      const uint32_t f0 = warp::shfl((uint32_t)x, 0, 32) + (warp::shfl((uint32_t)x, 1, 32) << 30);
+      const uint32_t g0 = warp::shfl((uint32_t)y, 0, 32) + (warp::shfl((uint32_t)y, 1, 32) << 30);
+      if (g0 == 0) {                               // g == 0?  one exact carry walk over the limbs (uniform branch)
+        int32_t carry = 0, nz = 0;
+        for (int i = 0; i < L; i++) {
+          const int32_t v = (int32_t)warp::shfl((uint32_t)y, i, 32) + carry;
+          nz |= (i < L - 1) ? (v & M30) : v;
+          carry = v >> 30;
+        }
+        if (nz == 0) break;
+      }
+      uint32_t ff = f0, gg = g0;
+      int32_t u = 1, v = 0, q = 0, r = 1;
+      int i = 30;
+      auto neg_inv = [](uint32_t fo) -> uint32_t { uint32_t t = fo; t *= 2u - fo * t; t *= 2u - fo * t; return 0u - t; };
+      uint32_t ninv = neg_inv(ff);
+      while (true) {                               // 30 division steps on the low words (as Field::inv_divsteps)
+        const uint32_t lim = gg | (0xffffffffu << i);
+        const int zeros = MGB_CTZ(lim);
+        gg >>= zeros; u <<= zeros; v <<= zeros; eta -= zeros; i -= zeros;
+        if (i == 0) break;
+        if (eta < 0) {
+          eta = -eta;
+          const uint32_t tf = ff; ff = gg; gg = 0u - tf;
+          const int32_t tu = u; u = q; q = -tu;
+          const int32_t tv = v; v = r; r = -tv;
+          ninv = neg_inv(ff);
+        }
+        const int limit = (eta + 1 < i) ? eta + 1 : i;
+        const uint32_t m = (0xffffffffu >> (32 - limit)) & 255u;
+        const uint32_t w = (gg * ninv) & m;
+        gg += ff * w; q += u * (int32_t)w; r += v * (int32_t)w;
+      }
+      // multiples of p that make the low 30 bits of the new d, e vanish (zero for the f, g lanes through pk = 0)
+      const int32_t d0 = (int32_t)warp::shfl((uint32_t)x, W, 32), e0 = (int32_t)warp::shfl((uint32_t)y, W, 32);
+      const int32_t dt = (int32_t)warp::shfl((uint32_t)x, W + L - 1, 32), et = (int32_t)warp::shfl((uint32_t)y, W + L - 1, 32);
+      const int32_t sd = dt >> 31, se = et >> 31;
+      int32_t md = (u & sd) + (v & se), me = (q & sd) + (r & se);
+      const int64_t cd = (int64_t)u * d0 + (int64_t)v * e0, ce = (int64_t)q * d0 + (int64_t)r * e0;
+      md -= (int32_t)((P::MINV30 * (uint32_t)cd + (uint32_t)md) & (uint32_t)M30);
+      me -= (int32_t)((P::MINV30 * (uint32_t)ce + (uint32_t)me) & (uint32_t)M30);
+      // this lane's limb of both numbers, then / 2^30: low parts one lane down, small overflow one lane up
+      const int64_t tx = (int64_t)u * x + (int64_t)v * y + (int64_t)pk * md;
+      const int64_t ty = (int64_t)q * x + (int64_t)r * y + (int64_t)pk * me;
+      const uint32_t lx = warp::shfl_down((uint32_t)tx & (uint32_t)M30, 1, W);      // lane W-1 gets its own 0 back
+      const uint32_t ly = warp::shfl_down((uint32_t)ty & (uint32_t)M30, 1, W);
+      const int64_t wx = (tx >> 30) + (int64_t)lx, wy = (ty >> 30) + (int64_t)ly;
+      const bool top = k >= L - 1;                 // the top limb is not split: it carries the sign
+      int32_t cx = (int32_t)warp::shfl_up((uint32_t)(top ? 0 : (int32_t)(wx >> 30)), 1, W);
+      int32_t cy = (int32_t)warp::shfl_up((uint32_t)(top ? 0 : (int32_t)(wy >> 30)), 1, W);
+      if (k == 0) { cx = 0; cy = 0; }
+      x = (top ? (int32_t)wx : (int32_t)((uint32_t)wx & (uint32_t)M30)) + cx;
+      y = (top ? (int32_t)wy : (int32_t)((uint32_t)wy & (uint32_t)M30)) + cy;
+    }
+    // f = +-1 (its low word tells which); inverse = sign(f) * d, gathered to every lane and brought to [0, p)
+    const bool fneg = (warp::shfl((uint32_t)x, 0, 32) + (warp::shfl((uint32_t)x, 1, 32) << 30)) != 1u;
+    int32_t d[L];
+    _Pragma("unroll") for (int i = 0; i < L; i++) d[i] = (int32_t)warp::shfl((uint32_t)x, W + i, 32);
+    int64_t c = 0;
+    _Pragma("unroll") for (int i = 0; i < L; i++) {
+      c += fneg ? -(int64_t)d[i] : (int64_t)d[i];
+      d[i] = (i < L - 1) ? ((int32_t)c & M30) : (int32_t)c;
+      c >>= 30;
+    }
+    _Pragma("unroll 1") for (int rep = 0; rep < 6; rep++) {   // d in (-3p, 3p) -> [0, p)
+      const bool neg = d[L - 1] < 0;
+      int32_t t[L];
+      int64_t cc = 0;
+      _Pragma("unroll") for (int i = 0; i < L; i++) {
+        cc += (int64_t)d[i] + (neg ? (int64_t)P::mod30(i) : -(int64_t)P::mod30(i));
+        t[i] = (i < L - 1) ? ((int32_t)cc & M30) : (int32_t)cc;
+        cc >>= 30;
+      }
+      if (!(neg || t[L - 1] >= 0)) break;          // negative: add p; non-negative and >= p: subtract p
+      _Pragma("unroll") for (int i = 0; i < L; i++) d[i] = t[i];
+    }
+    Fe<P> out;
+    _Pragma("unroll") for (int w = 0; w < N; w++) {
+      const int bit = 32 * w, j = bit / 30, sh = bit - 30 * j;
+      uint32_t val = (uint32_t)d[j] >> sh;
+      if (j + 1 < L) val |= (uint32_t)d[j + 1] << (30 - sh);
+      if (sh > 28 && j + 2 < L) val |= (uint32_t)d[j + 2] << (60 - sh);
+      out.v[w] = val;
+    }
+    Fe<P> r3;
+    _Pragma("unroll") for (int i = 0; i < N; i++) r3.v[i] = P::r3(i);
+    return F::mul(out, r3);                        // (aR)^-1 * R^3 / R = a^-1 R
+  }
+  // out-of-line copy for kernels that are short of registers and instruction cache
+  MGB_NOINLINE_DEV static Fe<P> inv_call(Fe<P> a) { return inv(a); }
 };
 
 }  // namespace mgb

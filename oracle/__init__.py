@@ -14,5 +14,8 @@ The oracle is pinned against everything the reference does hold for this path:
   * the algebraic MSM identities of `src/bigint/msm.test.ts`,
   * the GLV identity `s0 + s1*lambda = s (mod q)` of `src/scalar-glv.ts:92-103`,
 and cross-checked by an independent C restatement (`oracle/msm_cpu.cpp`).
-Beyond that (random inputs at N > 2) parity is UNPINNED by the reference itself.
+For random inputs the reference holds no outputs at all (its tests compare two of its own
+implementations at run time), so there the repository pins itself: oracle-generated golden
+vectors (`tests/golden/`, Pippenger == defining sum) and the closed form
+[(sum s_i a_i) mod q] G for known-dlog points at every size.
 """

@@ -31,6 +31,15 @@ for mode in (10, 11):
     ops = ctypes.c_double(); ms = ctypes.c_float()
     L.mgb_microbench(0, mode, 1, 32, 2000, ctypes.byref(ops), ctypes.byref(ms))
     out["ns_per_product_mode%d" % mode] = round(ms.value * 1e6 / 4000, 1)
+# --- lane-parallel inverse (op 9; experiment): parity + latency against the one-lane routine (modes 9 / 12, one warp per SM)
+O2 = np.zeros_like(A)
+rc = L.mgb_field_op(0, 0, 9, A.ctypes.data_as(vp), B.ctypes.data_as(vp), O2.ctypes.data_as(vp), len(a))
+got = [int.from_bytes(O2[i * 48:(i + 1) * 48].tobytes(), "little") for i in range(len(a))]
+out["warp_inv_ok"] = rc == 0 and got == [pow(x, -1, p) if x else 0 for x in a]
+for mode in (9, 12):
+    ops = ctypes.c_double(); ms = ctypes.c_float()
+    L.mgb_microbench(0, mode, 1, 32, 200, ctypes.byref(ops), ctypes.byref(ms))
+    out["us_per_inversion_mode%d" % mode] = round(ms.value * 1e3 / 200, 2)
 # --- MSM parity (closed form) + timing
 from tests.helpers import OracleCurve
 

@@ -92,7 +92,24 @@ template <class P> static void warp_finish(uint32_t* out, const uint32_t* t, con
   simt::run_warp([&](int lane) { out[lane] = WarpField<P>::finish(t[lane], c[lane]); });
 }
 
+// n inversions through the lane-parallel division-step inverse: every lane passes the same element
+template <class P> static void warp_inv(uint32_t* out, const uint32_t* a, int n) {
+  constexpr int N = P::N;
+  simt::run_warp([&](int lane) {
+    for (int j = 0; j < n; j++) {
+      const Fe<P> r = WarpField<P>::inv(ld<P>(a + j * N));
+      if (lane == (j & 31)) st<P>(out + j * N, r);                 // every lane holds the result: take a different one each time
+    }
+  });
+}
+
 extern "C" {
+void emu_warp_inv(int field, uint32_t* out, const uint32_t* a, int n) {
+  if (field == 0) warp_inv<Fp377>(out, a, n);
+  else if (field == 1) warp_inv<Fr377>(out, a, n);
+  else if (field == 2) warp_inv<FpPallas>(out, a, n);
+  else warp_inv<Fp381>(out, a, n);
+}
 void emu_warp_finish(int field, uint32_t* out, const uint32_t* t, const uint64_t* c) {
   if (field == 0) warp_finish<Fp377>(out, t, c);
   else if (field == 1) warp_finish<Fr377>(out, t, c);
