@@ -5,6 +5,7 @@
 #include "simt_emu.h"
 #include "../../montgomery_b200/csrc/ec.cuh"
 #include "../../montgomery_b200/csrc/warp.cuh"
+#include "../../montgomery_b200/csrc/coop.cuh"
 #include <cstring>
 using namespace mgb;
 
@@ -103,7 +104,45 @@ template <class P> static void warp_inv(uint32_t* out, const uint32_t* a, int n)
   });
 }
 
+// ---- the block-cooperative point arithmetic of the Horner kernels (coop.cuh) on an emulated 128-thread block,
+// driven the way k_final drives it: operands in the shared slots 0..3 (accumulator) and 4..7, result in 0..3.
+// op 0: P <- 2^count P (dbl_n), op 1: P <- P + Q, op 2: P <- 2^count P + Q (what one Horner step does)
+template <class COOP, class P> static void coop_op(int op, int count, uint32_t* out, const uint32_t* a, const uint32_t* b) {
+  constexpr int N = P::N;
+  static uint32_t sm[COOP_SLOTS * N];
+  static volatile int flag;
+  simt::run_block(128, [&](int t) {
+    CoopMem<P> m{sm};
+    if (t < 4 * N) { sm[t] = a[t]; sm[4 * N + t] = b[t]; }
+    __syncthreads();
+    if (op == 0 || op == 2) COOP::dbl_n(m, &flag, count);
+    if (op == 1 || op == 2) COOP::add(m, &flag);
+    if (t < 4 * N) out[t] = sm[t];
+  });
+}
+// quad-cooperative XYZZ addition: lane 4j + k holds coordinate k of the j-th of 8 independent additions
+template <class P> static void quad_add(uint32_t* out, const uint32_t* a, const uint32_t* b) {
+  constexpr int N = P::N;
+  simt::run_warp([&](int lane) {
+    const Fe<P> x = ld<P>(a + lane * N), y = ld<P>(b + lane * N);
+    st<P>(out + lane * N, QuadWeierstrass<P>::add(x, y));
+  });
+}
+
 extern "C" {
+void emu_coop_w(int curve, int op, int count, uint32_t* out, const uint32_t* a, const uint32_t* b) {
+  if (curve == 0) coop_op<CoopWeierstrass<Fp377>, Fp377>(op, count, out, a, b);
+  else if (curve == 1) coop_op<CoopWeierstrass<FpPallas>, FpPallas>(op, count, out, a, b);
+  else coop_op<CoopWeierstrass<Fp381>, Fp381>(op, count, out, a, b);
+}
+void emu_coop_te(int op, int count, uint32_t* out, const uint32_t* a, const uint32_t* b) {
+  coop_op<CoopTwistedEdwards<Fr377, Ed377Consts>, Fr377>(op, count, out, a, b);
+}
+void emu_quad_add(int curve, uint32_t* out, const uint32_t* a, const uint32_t* b) {
+  if (curve == 0) quad_add<Fp377>(out, a, b);
+  else if (curve == 1) quad_add<FpPallas>(out, a, b);
+  else quad_add<Fp381>(out, a, b);
+}
 void emu_warp_inv(int field, uint32_t* out, const uint32_t* a, int n) {
   if (field == 0) warp_inv<Fp377>(out, a, n);
   else if (field == 1) warp_inv<Fr377>(out, a, n);

@@ -245,3 +245,113 @@ def test_warp_parallel_inverse(emu, fid):
     emu.emu_warp_inv(fid, out, L(A, n), len(A))
     for a, g in zip(A, I(out, n, len(A))):
         assert g == (pow(a * Ri, -1, p) * R % p if a else 0), (fid, hex(a))
+
+
+# ---- block-cooperative point arithmetic of the Horner kernels (csrc/coop.cuh: four warps share the products of a
+# formula level, the lanes of a warp share each product, runs of doublings are fused) on an emulated 128-thread block
+
+@pytest.mark.parametrize("cid,prm,n", [(0, BLS12_377, 12), (1, PALLAS, 8), (2, BLS12_381, 12)])
+def test_coop_weierstrass_horner_steps(emu, cid, prm, n):
+    p = prm.p
+    R = 1 << (32 * n)
+    Ri = pow(R, -1, p)
+    A = AffineCurve(prm)
+    rnd = random.Random(40 + cid)
+    M = lambda x: x * R % p
+
+    def enc_x(P):
+        if P is None:
+            return [0, M(1), 0, 0]
+        z = rnd.randrange(1, p)
+        return [M(P[0] * z * z % p), M(P[1] * z * z * z % p), M(z * z % p), M(z * z * z % p)]
+
+    def dec_x(v):
+        X, Y, ZZ, ZZZ = [t * Ri % p for t in v]
+        return None if ZZ == 0 else (X * pow(ZZ, -1, p) % p, Y * pow(ZZZ, -1, p) % p)
+
+    def dbl_k(P, k):
+        for _ in range(k):
+            P = A.double(P)
+        return P
+
+    P, Q = (A.scale(rnd.randrange(1, prm.q), prm.G) for _ in range(2))
+    out = (ctypes.c_uint32 * (4 * n))()
+    for count in (0, 1, 2, 5):                       # runs of doublings: Y stays pending between them
+        emu.emu_coop_w(cid, 0, count, out, L(enc_x(P), n), L(enc_x(Q), n))
+        assert dec_x(I(out, n, 4)) == dbl_k(P, count), count
+    emu.emu_coop_w(cid, 0, 3, out, L(enc_x(None), n), L(enc_x(Q), n))      # doubling the neutral element
+    assert dec_x(I(out, n, 4)) is None
+    for X, Y in [(P, Q), (P, P), (P, A.negate(P)), (None, Q), (P, None), (None, None)]:
+        emu.emu_coop_w(cid, 1, 0, out, L(enc_x(X), n), L(enc_x(Y), n))
+        assert dec_x(I(out, n, 4)) == A.add(X, Y)
+    emu.emu_coop_w(cid, 2, 4, out, L(enc_x(P), n), L(enc_x(Q), n))         # one Horner step: 2^4 P + Q
+    assert dec_x(I(out, n, 4)) == A.add(dbl_k(P, 4), Q)
+    emu.emu_coop_w(cid, 2, 3, out, L(enc_x(None), n), L(enc_x(Q), n))      # empty top window
+    assert dec_x(I(out, n, 4)) == Q
+
+
+def test_coop_twisted_edwards_horner_steps(emu):
+    prm, n = ED_ON_BLS12_377, 8
+    p = prm.p
+    R = 1 << (32 * n)
+    Ri = pow(R, -1, p)
+    T = TwistedEdwardsCurve(prm)
+    rnd = random.Random(51)
+    M = lambda x: x * R % p
+
+    def enc_e(P):
+        z = rnd.randrange(1, p)
+        x, y = T.to_affine(P)
+        return [M(x * z % p), M(y * z % p), M(z), M(x * y * z % p)]
+
+    def dec_e(v):
+        X, Y, Z, Tt = [t * Ri % p for t in v]
+        assert (X * Y - Tt * Z) % p == 0
+        zi = pow(Z, -1, p)
+        return (X * zi % p, Y * zi % p)
+
+    P, Q = (T.scale(rnd.randrange(1, prm.q), T.one) for _ in range(2))
+    out = (ctypes.c_uint32 * (4 * n))()
+    D = P
+    for _ in range(3):
+        D = T.double(D)
+    emu.emu_coop_te(0, 3, out, L(enc_e(P), n), L(enc_e(Q), n))
+    assert dec_e(I(out, n, 4)) == T.to_affine(D)
+    for X, Y in [(P, Q), (P, P), (P, T.negate(P)), (T.zero, Q), (P, T.zero)]:
+        emu.emu_coop_te(1, 0, out, L(enc_e(X), n), L(enc_e(Y), n))
+        assert dec_e(I(out, n, 4)) == T.to_affine(T.add(X, Y))
+    emu.emu_coop_te(2, 3, out, L(enc_e(P), n), L(enc_e(Q), n))
+    assert dec_e(I(out, n, 4)) == T.to_affine(T.add(D, Q))
+
+
+@pytest.mark.parametrize("cid,prm,n", [(0, BLS12_377, 12), (1, PALLAS, 8)])
+def test_quad_cooperative_addition(emu, cid, prm, n):
+    """QuadWeierstrass::add: four lanes hold X, Y, ZZ, ZZZ of one point; eight additions per warp, among them the
+    rare cases (doubling, cancellation, neutral operands) next to generic ones in the same warp."""
+    p = prm.p
+    R = 1 << (32 * n)
+    Ri = pow(R, -1, p)
+    A = AffineCurve(prm)
+    rnd = random.Random(60 + cid)
+    M = lambda x: x * R % p
+
+    def enc_x(P):
+        if P is None:
+            return [0, M(1), 0, 0]
+        z = rnd.randrange(1, p)
+        return [M(P[0] * z * z % p), M(P[1] * z * z * z % p), M(z * z % p), M(z * z * z % p)]
+
+    def dec_x(v):
+        X, Y, ZZ, ZZZ = [t * Ri % p for t in v]
+        return None if ZZ == 0 else (X * pow(ZZ, -1, p) % p, Y * pow(ZZZ, -1, p) % p)
+
+    pts = [A.scale(rnd.randrange(1, prm.q), prm.G) for _ in range(8)]
+    pairs = [(pts[0], pts[1]), (pts[2], pts[2]), (pts[3], A.negate(pts[3])), (None, pts[4]), (pts[5], None), (None, None),
+             (pts[6], pts[7]), (pts[7], pts[0])]
+    a = [c for X, _ in pairs for c in enc_x(X)]
+    b = [c for _, Y in pairs for c in enc_x(Y)]
+    out = (ctypes.c_uint32 * (32 * n))()
+    emu.emu_quad_add(cid, out, L(a, n), L(b, n))
+    got = I(out, n, 32)
+    for j, (X, Y) in enumerate(pairs):
+        assert dec_x(got[4 * j:4 * j + 4]) == A.add(X, Y), j
