@@ -499,13 +499,16 @@ __global__ void __launch_bounds__(256) k_scatter(MsmParams pr, int w_begin, int 
 // (reference: batchAddNew / batchAddUnsafeNew, src/curve-affine.ts:376-522, and the Montgomery
 // trick of src/wasm/inverse.ts:220-271).  Warps are fully independent (no block barrier):
 //   1. every lane walks E pairs, needing only the x coordinates, and keeps the running product of
-//      the denominators; the prefix products go to a per-warp scratch area in global memory;
+//      the denominators; the prefix products go to a per-warp scratch area in global memory.  It
+//      also counts the pairs whose sum goes on to the next round: one atomicAdd per TILE then
+//      reserves their range in the next round's pair list;
 //   2. warp-wide inclusive prefix and suffix products of the 32 lane totals by shuffles;
 //   3. lane 0 inverts the grand total with the division-step inverse (the other warps of the
 //      SM keep the multiplier pipe busy meanwhile);
 //   4. every lane gets the inverse of its own total (2 multiplications), then walks its pairs
 //      backwards: recompute the denominator, peel off its inverse, finish the addition, store.
-// 6 multiplications per addition + 13/E for the warp products.  Emits the next round's pair list.
+//      Continuing sums are appended to the reserved range (ballot + running offset, no atomic).
+// 6 multiplications per addition + 13/E for the warp products.
 //
 // Operand staging.  The operands of a pair are two random 96-byte reads (a gather from the point
 // table in round 0, from V later) that miss L1 and mostly L2; a warp has no registers to spare for
