@@ -246,4 +246,99 @@ struct WarpField {
   MGB_NOINLINE_DEV static Fe<P> inv_call(Fe<P> a) { return inv(a); }
 };
 
+// ---------------------------------------------------------------------------------------------
+// The same product with TWO limbs (one 64-bit digit) per lane: an element occupies an 8-lane group,
+// so FOUR independent products fit in one warp -- all the products of a formula level of a point
+// doubling / addition, which would let the Horner chain run inside one warp without block barriers
+// (experiment for the next round; the Horner kernels use WarpField).  Half as many steps (N/2,
+// each with its two shuffles on the dependent path), more arithmetic per step: 64x64->128 products
+// and a pending carry that needs 66 bits (64-bit word + a small count).
+template <class P>
+struct WarpField2 {
+  typedef unsigned long long u64;
+  static constexpr int N = P::N, D = P::N / 2;     // limbs, 64-bit digits
+  static constexpr int W = 8;                      // lanes per element (lanes D..W-1 carry zeros)
+  static_assert(D < W, "one spare lane above the top digit");
+
+  MGB_DEV static u64 mod_digit(int l) {
+    u64 r = 0;
+    _Pragma("unroll") for (int k = 0; k < D; k++) r = (l == k) ? (((u64)P::mod(2 * k + 1) << 32) | P::mod(2 * k)) : r;
+    return r;
+  }
+  MGB_DEV static u64 shfl64(u64 v, int src) {
+    return ((u64)warp::shfl((uint32_t)(v >> 32), src, W) << 32) | warp::shfl((uint32_t)v, src, W);
+  }
+  MGB_DEV static void mul128(u64 a, u64 b, u64& lo, u64& hi) {
+#ifdef MGB_HOST_EMU
+    const unsigned __int128 t = (unsigned __int128)a * b;
+    lo = (u64)t; hi = (u64)(t >> 64);
+#else
+    lo = a * b; hi = __umul64hi(a, b);
+#endif
+  }
+  MGB_DEV static uint32_t lookahead(uint32_t gen, uint32_t prop) {   // as WarpField::lookahead
+    const uint32_t A = gen | prop, B = gen;
+    return (A + B) ^ A ^ B;
+  }
+
+  // All 32 lanes call.  Lane l of an 8-lane group passes digit l of a and b (ignored for l >= D) and receives
+  // digit l of a*b/R mod p, canonical (0 for l >= D).  a, b < p.
+  MGB_DEV static u64 mul(u64 a, u64 b) {
+    const int ln = warp::lane();
+    const int l = ln & (W - 1);
+    const int gsh = ln & ~(W - 1);
+    if (l >= D) a = 0;
+    const u64 p = mod_digit(l);
+    const u64 p0 = ((u64)P::mod(1) << 32) | P::mod(0);
+    u64 y = (u64)(0u - c_mgb_minv[P::ID]);           // p^-1 mod 2^32 -> one Newton step -> mod 2^64
+    y *= 2ull - p0 * y;
+    const u64 minv = 0ull - y;
+    u64 bk[D];
+    _Pragma("unroll") for (int k = 0; k < D; k++) bk[k] = shfl64(b, k);
+    u64 t = 0, clo = 0;
+    uint32_t chi = 0;                                // pending carry clo + chi 2^64, one digit above t
+    _Pragma("unroll") for (int k = 0; k < D; k++) {
+      u64 p1l, p1h, p2l, p2h;
+      mul128(a, bk[k], p1l, p1h);
+      u64 s = t + p1l;
+      uint32_t sc = s < t;
+      const u64 s1 = s + clo;
+      sc += s1 < s;
+      const u64 m = shfl64(s1 * minv, 0);
+      mul128(m, p, p2l, p2h);
+      const u64 s2 = s1 + p2l;                       // digit 0: 0 by the choice of m
+      sc += s2 < s1;
+      u64 c = p1h + p2h;
+      uint32_t ch = c < p1h;
+      const u64 c2 = c + sc + chi;
+      ch += c2 < c;
+      clo = c2; chi = ch;
+      const uint32_t dl = warp::shfl_down((uint32_t)s2, 1, W), dh = warp::shfl_down((uint32_t)(s2 >> 32), 1, W);
+      t = ((u64)dh << 32) | dl;                      // lane W-1 keeps its own value, which is 0
+    }
+    return finish(t, clo, chi);
+  }
+
+  // sum (t_i + clo_i + chi_i 2^64) 2^(64 i) < 2p spread over the lanes as in mul -> canonical digits:
+  // high parts one lane up, then single-bit carries by lookahead, then the conditional subtraction of p
+  MGB_DEV static u64 finish(u64 t, u64 clo, uint32_t chi) {
+    const int ln = warp::lane();
+    const int l = ln & (W - 1);
+    const int gsh = ln & ~(W - 1);
+    const u64 p = mod_digit(l);
+    const u64 s = t + clo;
+    uint32_t up = warp::shfl_up(chi + (uint32_t)(s < t), 1, W);
+    if (l == 0) up = 0;
+    u64 lo = s + up;
+    const uint32_t gen = (warp::ballot(lo < s) >> gsh) & 0xffu;
+    const uint32_t prop = (warp::ballot(lo == ~0ull) >> gsh) & 0xffu;
+    lo += (lookahead(gen, prop) >> l) & 1u;
+    const uint32_t lt = (warp::ballot(lo < p) >> gsh) & 0xffu;
+    const uint32_t eq = (warp::ballot(lo == p) >> gsh) & 0xffu;
+    const uint32_t bw = lookahead(lt, eq);
+    const u64 d = lo - p - ((bw >> l) & 1u);
+    return ((bw >> D) & 1u) ? lo : d;
+  }
+};
+
 }  // namespace mgb

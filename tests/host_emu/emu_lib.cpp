@@ -88,6 +88,28 @@ template <class P> static void warp_mul(uint32_t* out, const uint32_t* a, const 
   });
 }
 
+// n products through the two-limbs-per-lane variant, four at a time (8-lane groups)
+template <class P> static void warp_mul2(uint32_t* out, const uint32_t* a, const uint32_t* b, int n) {
+  constexpr int N = P::N, D = N / 2;
+  typedef unsigned long long u64;
+  simt::run_warp([&](int lane) {
+    const int g = lane >> 3, l = lane & 7;
+    for (int j = 0; j < n; j += 4) {
+      const int e = j + g;
+      const bool live = e < n && l < D;
+      const u64 x = live ? (((u64)a[e * N + 2 * l + 1] << 32) | a[e * N + 2 * l]) : (e < n ? 0xdeadbeefcafef00dull : 0ull);
+      const u64 y = live ? (((u64)b[e * N + 2 * l + 1] << 32) | b[e * N + 2 * l]) : 0x123456789abcdef0ull;
+      const u64 r = WarpField2<P>::mul(x, y);
+      if (live) { out[e * N + 2 * l] = (uint32_t)r; out[e * N + 2 * l + 1] = (uint32_t)(r >> 32); }
+      else if (e < n && r != 0) out[e * N] ^= 0xffffffffu;   // poison: spare lanes must return 0
+    }
+  });
+}
+
+template <class P> static void warp_finish2(uint64_t* out, const uint64_t* t, const uint64_t* clo, const uint32_t* chi) {
+  simt::run_warp([&](int lane) { out[lane] = WarpField2<P>::finish(t[lane], clo[lane], chi[lane]); });
+}
+
 // the carry / borrow resolution alone: lane l of group g gets t[g*16 + l] and c[g*16 + l] (c as 64-bit)
 template <class P> static void warp_finish(uint32_t* out, const uint32_t* t, const uint64_t* c) {
   simt::run_warp([&](int lane) { out[lane] = WarpField<P>::finish(t[lane], c[lane]); });
@@ -148,6 +170,18 @@ void emu_warp_inv(int field, uint32_t* out, const uint32_t* a, int n) {
   else if (field == 1) warp_inv<Fr377>(out, a, n);
   else if (field == 2) warp_inv<FpPallas>(out, a, n);
   else warp_inv<Fp381>(out, a, n);
+}
+void emu_warp_mul2(int field, uint32_t* out, const uint32_t* a, const uint32_t* b, int n) {
+  if (field == 0) warp_mul2<Fp377>(out, a, b, n);
+  else if (field == 1) warp_mul2<Fr377>(out, a, b, n);
+  else if (field == 2) warp_mul2<FpPallas>(out, a, b, n);
+  else warp_mul2<Fp381>(out, a, b, n);
+}
+void emu_warp_finish2(int field, uint64_t* out, const uint64_t* t, const uint64_t* clo, const uint32_t* chi) {
+  if (field == 0) warp_finish2<Fp377>(out, t, clo, chi);
+  else if (field == 1) warp_finish2<Fr377>(out, t, clo, chi);
+  else if (field == 2) warp_finish2<FpPallas>(out, t, clo, chi);
+  else warp_finish2<Fp381>(out, t, clo, chi);
 }
 void emu_warp_finish(int field, uint32_t* out, const uint32_t* t, const uint64_t* c) {
   if (field == 0) warp_finish<Fp377>(out, t, c);

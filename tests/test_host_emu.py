@@ -355,3 +355,79 @@ def test_quad_cooperative_addition(emu, cid, prm, n):
     got = I(out, n, 32)
     for j, (X, Y) in enumerate(pairs):
         assert dec_x(got[4 * j:4 * j + 4]) == A.add(X, Y), j
+
+
+# ---- two limbs (one 64-bit digit) per lane: four products per warp (csrc/warp.cuh WarpField2; an experiment)
+
+@pytest.mark.parametrize("fid", [0, 1, 2, 3])
+def test_warp_cooperative_mul_two_limbs_per_lane(emu, fid):
+    p, n = FIELDS[fid]
+    R = 1 << (32 * n)
+    Ri = pow(R, -1, p)
+    rnd = random.Random(600 + fid)
+    edge = [0, 1, p - 1, p - 2, (p - 1) // 2, R % p, (R - 1) % p, (1 << 64) - 1,
+            sum(0xffffffff << (32 * i) for i in range(n)) % p, sum(0xffffffff << (32 * i) for i in range(n - 2))]
+    A = [x for x in edge for _ in edge] + [rnd.randrange(p) for _ in range(1001)]      # 1101: the last warp runs one product
+    B = [y for _ in edge for y in edge] + [rnd.randrange(p) for _ in range(1001)]
+    out = (ctypes.c_uint32 * (n * len(A)))()
+    emu.emu_warp_mul2(fid, out, L(A, n), L(B, n), len(A))
+    for a, b, g in zip(A, B, I(out, n, len(A))):
+        assert g == a * b * Ri % p, (fid, hex(a), hex(b))
+
+
+@pytest.mark.parametrize("fid", [0, 1, 2, 3])
+def test_warp_carry_and_borrow_lookahead_two_limbs_per_lane(emu, fid):
+    """WarpField2::finish on carries rippling through runs of all-ones DIGITS and borrows rippling through digits
+    equal to the modulus's (a random product never gets there), four elements per warp."""
+    p, n = FIELDS[fid]
+    D = n // 2
+    rnd = random.Random(700 + fid)
+    W64 = (1 << 64) - 1
+    pd = [(p >> (64 * i)) & W64 for i in range(D)]
+    cases = []        # (t digits, clo digits, chi digits): sum (t + clo + chi 2^64) 2^(64 i) < 2p
+
+    def val(t, clo, chi):
+        return sum((a + b + (c << 64)) << (64 * i) for i, (a, b, c) in enumerate(zip(t, clo, chi)))
+
+    for lo_run in range(0, D - 1):
+        for hi_run in range(lo_run, D - 1):
+            t = [rnd.getrandbits(64) for _ in range(D)]
+            clo, chi = [0] * D, [0] * D
+            for i in range(lo_run, hi_run + 1):
+                t[i] = W64
+            t[D - 1] = rnd.randrange(pd[D - 1])
+            clo[lo_run] = rnd.choice([1, 2, W64])
+            if lo_run > 0:
+                t[lo_run - 1], chi[lo_run - 1] = W64, rnd.choice([1, 2])         # a carry arriving through the shuffle
+            if val(t, clo, chi) < 2 * p:
+                cases.append((t, clo, chi))
+    for k in range(1, D):
+        v = p + (1 << (64 * k)) - 1 - rnd.randrange(2)
+        if v < 2 * p:
+            cases.append(([(v >> (64 * i)) & W64 for i in range(D)], [0] * D, [0] * D))
+    for v in (p, p - 1, p + 1, 2 * p - 1, 0, 1):
+        cases.append(([(v >> (64 * i)) & W64 for i in range(D)], [0] * D, [0] * D))
+    for _ in range(40):
+        clo = [rnd.getrandbits(64) for _ in range(D - 2)] + [rnd.randrange(4), 0]
+        chi = [rnd.randrange(3) for _ in range(D - 2)] + [0, 0]
+        low = val([0] * D, clo, chi)
+        v = rnd.randrange(low, 2 * p)
+        rest = v - low
+        cases.append(([(rest >> (64 * i)) & W64 for i in range(D)], clo, chi))
+    while len(cases) % 4:
+        cases.append(cases[0])
+    for j in range(0, len(cases), 4):
+        t = (ctypes.c_uint64 * 32)()
+        clo = (ctypes.c_uint64 * 32)()
+        chi = (ctypes.c_uint32 * 32)()
+        for g in range(4):
+            for i in range(D):
+                t[8 * g + i], clo[8 * g + i], chi[8 * g + i] = cases[j + g][0][i], cases[j + g][1][i], cases[j + g][2][i]
+        out = (ctypes.c_uint64 * 32)()
+        emu.emu_warp_finish2(fid, out, t, clo, chi)
+        for g in range(4):
+            v = val(*cases[j + g])
+            assert v < 2 * p
+            got = sum(int(out[8 * g + i]) << (64 * i) for i in range(D))
+            assert got == (v - p if v >= p else v), (fid, j + g, hex(v))
+            assert all(out[8 * g + i] == 0 for i in range(D, 8))
