@@ -339,6 +339,34 @@ struct WarpField2 {
     const u64 d = lo - p - ((bw >> l) & 1u);
     return ((bw >> D) & 1u) ? lo : d;
   }
+
+  // ---- additions on distributed elements (all four groups of a warp at once); canonical in, canonical out
+  MGB_DEV static uint32_t group_ballot(bool pred) { return (warp::ballot(pred) >> (warp::lane() & ~(W - 1))) & 0xffu; }
+  // a - b mod p
+  MGB_DEV static u64 sub(u64 a, u64 b) {
+    const int l = warp::lane() & (W - 1);
+    const u64 p = mod_digit(l);
+    const uint32_t bw = lookahead(group_ballot(a < b), group_ballot(a == b));
+    const u64 d = a - b - ((bw >> l) & 1u);
+    // a < b (borrow out of the top digit): add p back; its carry out of the top digit cancels the borrow.  No branch:
+    // the four groups of a warp decide differently and the ballots below need all 32 lanes.
+    const u64 s = d + p;
+    const u64 r = s + ((lookahead(group_ballot(s < d), group_ballot(s == ~0ull)) >> l) & 1u);
+    return ((bw >> D) & 1u) ? r : d;
+  }
+  // a + b mod p
+  MGB_DEV static u64 add(u64 a, u64 b) {
+    const int l = warp::lane() & (W - 1);
+    const u64 p = mod_digit(l);
+    u64 s = a + b;                                   // 2p < 2^(64 D): no carry out of the top digit
+    s += (lookahead(group_ballot(s < a), group_ballot(s == ~0ull)) >> l) & 1u;
+    const uint32_t bw = lookahead(group_ballot(s < p), group_ballot(s == p));
+    const u64 d = s - p - ((bw >> l) & 1u);
+    return ((bw >> D) & 1u) ? s : d;
+  }
+  MGB_DEV static u64 dbl(u64 a) { return add(a, a); }
+  // is the element of this lane's group zero?  (same answer on the 8 lanes of a group)
+  MGB_DEV static bool is_zero(u64 a) { return group_ballot(a != 0) == 0; }
 };
 
 }  // namespace mgb

@@ -106,6 +106,24 @@ template <class P> static void warp_mul2(uint32_t* out, const uint32_t* a, const
   });
 }
 
+// op 0: a + b, 1: a - b, 2: 2a, 3: (a == 0) on distributed elements, four at a time
+template <class P> static void warp_addsub2(int op, uint32_t* out, const uint32_t* a, const uint32_t* b, int n) {
+  constexpr int N = P::N, D = N / 2;
+  typedef unsigned long long u64;
+  typedef WarpField2<P> WF;
+  simt::run_warp([&](int lane) {
+    const int g = lane >> 3, l = lane & 7;
+    for (int j = 0; j < n; j += 4) {
+      const int e = j + g;
+      const bool live = e < n && l < D;
+      const u64 x = live ? (((u64)a[e * N + 2 * l + 1] << 32) | a[e * N + 2 * l]) : 0ull;
+      const u64 y = live ? (((u64)b[e * N + 2 * l + 1] << 32) | b[e * N + 2 * l]) : 0ull;
+      const u64 r = op == 0 ? WF::add(x, y) : op == 1 ? WF::sub(x, y) : op == 2 ? WF::dbl(x) : (u64)WF::is_zero(x);
+      if (live) { out[e * N + 2 * l] = (uint32_t)r; out[e * N + 2 * l + 1] = (uint32_t)(r >> 32); }
+    }
+  });
+}
+
 template <class P> static void warp_finish2(uint64_t* out, const uint64_t* t, const uint64_t* clo, const uint32_t* chi) {
   simt::run_warp([&](int lane) { out[lane] = WarpField2<P>::finish(t[lane], clo[lane], chi[lane]); });
 }
@@ -176,6 +194,12 @@ void emu_warp_mul2(int field, uint32_t* out, const uint32_t* a, const uint32_t* 
   else if (field == 1) warp_mul2<Fr377>(out, a, b, n);
   else if (field == 2) warp_mul2<FpPallas>(out, a, b, n);
   else warp_mul2<Fp381>(out, a, b, n);
+}
+void emu_warp_addsub2(int field, int op, uint32_t* out, const uint32_t* a, const uint32_t* b, int n) {
+  if (field == 0) warp_addsub2<Fp377>(op, out, a, b, n);
+  else if (field == 1) warp_addsub2<Fr377>(op, out, a, b, n);
+  else if (field == 2) warp_addsub2<FpPallas>(op, out, a, b, n);
+  else warp_addsub2<Fp381>(op, out, a, b, n);
 }
 void emu_warp_finish2(int field, uint64_t* out, const uint64_t* t, const uint64_t* clo, const uint32_t* chi) {
   if (field == 0) warp_finish2<Fp377>(out, t, clo, chi);

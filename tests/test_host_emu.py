@@ -13,6 +13,8 @@ from oracle.twisted_edwards import TwistedEdwardsCurve
 from oracle.weierstrass import AffineCurve
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# the warp emulation deadlocks (like the GPU would misbehave) if lanes diverge around a shuffle / ballot: fail, don't hang
+pytestmark = pytest.mark.timeout(300)
 FIELDS = [(BLS12_377.p, 12), (BLS12_377.q, 8), (PALLAS.p, 8), (BLS12_381.p, 12)]
 
 
@@ -431,3 +433,30 @@ def test_warp_carry_and_borrow_lookahead_two_limbs_per_lane(emu, fid):
             got = sum(int(out[8 * g + i]) << (64 * i) for i in range(D))
             assert got == (v - p if v >= p else v), (fid, j + g, hex(v))
             assert all(out[8 * g + i] == 0 for i in range(D, 8))
+
+
+@pytest.mark.parametrize("fid", [0, 1, 2, 3])
+def test_warp_distributed_add_sub(emu, fid):
+    """WarpField2::add / sub / dbl / is_zero on elements spread over 8-lane groups: carries and borrows cross the
+    lanes by lookahead, so the operands are chosen to make them ripple (all-ones digits, digits equal to p's)."""
+    p, n = FIELDS[fid]
+    rnd = random.Random(800 + fid)
+    W64 = (1 << 64) - 1
+    D = n // 2
+    special = [0, 1, p - 1, p - 2, (p - 1) // 2, (p + 1) // 2, W64, (1 << 64), (1 << (64 * (D - 1))) - 1, (1 << (64 * (D - 1))),
+               p - (1 << 64), p - W64, sum(W64 << (64 * i) for i in range(D - 1))]
+    special = [x % p for x in special]
+    A = [x for x in special for _ in special] + [rnd.randrange(p) for _ in range(400)]
+    B = [y for _ in special for y in special] + [rnd.randrange(p) for _ in range(400)]
+    A += [x for x in special]                           # a - a, a + (p - a)
+    B += [x for x in special]
+    A += [x for x in special]
+    B += [(p - x) % p for x in special]
+    out = (ctypes.c_uint32 * (n * len(A)))()
+    for op, f in ((0, lambda a, b: (a + b) % p), (1, lambda a, b: (a - b) % p), (2, lambda a, b: 2 * a % p), (3, lambda a, b: int(a == 0))):
+        emu.emu_warp_addsub2(fid, op, out, L(A, n), L(B, n), len(A))
+        got = I(out, n, len(A))
+        for a, b, g in zip(A, B, got):
+            if op == 3:
+                g &= W64                               # the flag comes back in every digit of the group
+            assert g == f(a, b), (fid, op, hex(a), hex(b))
