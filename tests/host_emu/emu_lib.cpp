@@ -6,6 +6,7 @@
 #include "../../montgomery_b200/csrc/ec.cuh"
 #include "../../montgomery_b200/csrc/warp.cuh"
 #include "../../montgomery_b200/csrc/coop.cuh"
+#include "../../montgomery_b200/csrc/onewarp.cuh"
 #include <cstring>
 using namespace mgb;
 
@@ -160,6 +161,22 @@ template <class COOP, class P> static void coop_op(int op, int count, uint32_t* 
     if (t < 4 * N) out[t] = sm[t];
   });
 }
+// the same three operations on ONE emulated warp (onewarp.cuh): the point distributed over the lanes
+template <class P> static void onewarp_op(int op, int count, uint32_t* out, const uint32_t* a, const uint32_t* b) {
+  typedef OneWarpWeierstrass<P> OW;
+  typedef Weierstrass<P> W;
+  constexpr int N = P::N;
+  auto ldx = [&](const uint32_t* p) { typename W::acc r; r.X = ld<P>(p); r.Y = ld<P>(p + N); r.ZZ = ld<P>(p + 2 * N); r.ZZZ = ld<P>(p + 3 * N); return r; };
+  simt::run_warp([&](int lane) {
+    auto v = OW::spread(ldx(a));
+    const auto q = OW::spread(ldx(b));
+    if (op == 0 || op == 2) for (int i = 0; i < count; i++) v = OW::dbl(v);
+    if (op == 1 || op == 2) v = OW::add(v, q);
+    const typename W::acc r = OW::gather(v);
+    if (lane == 7) { st<P>(out, r.X); st<P>(out + N, r.Y); st<P>(out + 2 * N, r.ZZ); st<P>(out + 3 * N, r.ZZZ); }
+  });
+}
+
 // quad-cooperative XYZZ addition: lane 4j + k holds coordinate k of the j-th of 8 independent additions
 template <class P> static void quad_add(uint32_t* out, const uint32_t* a, const uint32_t* b) {
   constexpr int N = P::N;
@@ -174,6 +191,11 @@ void emu_coop_w(int curve, int op, int count, uint32_t* out, const uint32_t* a, 
   if (curve == 0) coop_op<CoopWeierstrass<Fp377>, Fp377>(op, count, out, a, b);
   else if (curve == 1) coop_op<CoopWeierstrass<FpPallas>, FpPallas>(op, count, out, a, b);
   else coop_op<CoopWeierstrass<Fp381>, Fp381>(op, count, out, a, b);
+}
+void emu_onewarp_w(int curve, int op, int count, uint32_t* out, const uint32_t* a, const uint32_t* b) {
+  if (curve == 0) onewarp_op<Fp377>(op, count, out, a, b);
+  else if (curve == 1) onewarp_op<FpPallas>(op, count, out, a, b);
+  else onewarp_op<Fp381>(op, count, out, a, b);
 }
 void emu_coop_te(int op, int count, uint32_t* out, const uint32_t* a, const uint32_t* b) {
   coop_op<CoopTwistedEdwards<Fr377, Ed377Consts>, Fr377>(op, count, out, a, b);

@@ -252,8 +252,12 @@ def test_warp_parallel_inverse(emu, fid):
 # ---- block-cooperative point arithmetic of the Horner kernels (csrc/coop.cuh: four warps share the products of a
 # formula level, the lanes of a warp share each product, runs of doublings are fused) on an emulated 128-thread block
 
+@pytest.mark.parametrize("impl", ["block", "onewarp"])
 @pytest.mark.parametrize("cid,prm,n", [(0, BLS12_377, 12), (1, PALLAS, 8), (2, BLS12_381, 12)])
-def test_coop_weierstrass_horner_steps(emu, cid, prm, n):
+def test_coop_weierstrass_horner_steps(emu, cid, prm, n, impl):
+    """impl = block: coop.cuh on a 128-thread block (what k_final runs); onewarp: onewarp.cuh, the whole point in one warp
+    (an experiment: no shared memory, no barriers)."""
+    run = emu.emu_coop_w if impl == "block" else emu.emu_onewarp_w
     p = prm.p
     R = 1 << (32 * n)
     Ri = pow(R, -1, p)
@@ -279,16 +283,16 @@ def test_coop_weierstrass_horner_steps(emu, cid, prm, n):
     P, Q = (A.scale(rnd.randrange(1, prm.q), prm.G) for _ in range(2))
     out = (ctypes.c_uint32 * (4 * n))()
     for count in (0, 1, 2, 5):                       # runs of doublings: Y stays pending between them
-        emu.emu_coop_w(cid, 0, count, out, L(enc_x(P), n), L(enc_x(Q), n))
+        run(cid, 0, count, out, L(enc_x(P), n), L(enc_x(Q), n))
         assert dec_x(I(out, n, 4)) == dbl_k(P, count), count
-    emu.emu_coop_w(cid, 0, 3, out, L(enc_x(None), n), L(enc_x(Q), n))      # doubling the neutral element
+    run(cid, 0, 3, out, L(enc_x(None), n), L(enc_x(Q), n))      # doubling the neutral element
     assert dec_x(I(out, n, 4)) is None
     for X, Y in [(P, Q), (P, P), (P, A.negate(P)), (None, Q), (P, None), (None, None)]:
-        emu.emu_coop_w(cid, 1, 0, out, L(enc_x(X), n), L(enc_x(Y), n))
+        run(cid, 1, 0, out, L(enc_x(X), n), L(enc_x(Y), n))
         assert dec_x(I(out, n, 4)) == A.add(X, Y)
-    emu.emu_coop_w(cid, 2, 4, out, L(enc_x(P), n), L(enc_x(Q), n))         # one Horner step: 2^4 P + Q
+    run(cid, 2, 4, out, L(enc_x(P), n), L(enc_x(Q), n))         # one Horner step: 2^4 P + Q
     assert dec_x(I(out, n, 4)) == A.add(dbl_k(P, 4), Q)
-    emu.emu_coop_w(cid, 2, 3, out, L(enc_x(None), n), L(enc_x(Q), n))      # empty top window
+    run(cid, 2, 3, out, L(enc_x(None), n), L(enc_x(Q), n))      # empty top window
     assert dec_x(I(out, n, 4)) == Q
 
 
