@@ -14,7 +14,12 @@
 #include <cuda_runtime.h>
 #include "ec.cuh"
 #include "coop.cuh"
+#include "onewarp.cuh"
 
+// build-time switch (experiment, off): the Horner kernels of the Weierstrass curves run on one warp (onewarp.cuh)
+#ifndef MGB_ONEWARP_HORNER
+#define MGB_ONEWARP_HORNER 0
+#endif
 // build-time switch (experiment, off): k_batch_add inverts a tile's total with the lane-parallel inverse of warp.cuh
 #ifndef MGB_WARP_INV
 #define MGB_WARP_INV 0
@@ -1090,6 +1095,18 @@ __global__ void __launch_bounds__(128) k_digit_sums(MsmParams pr, ReduceGeom gm,
   if (v == 0) st_fe<FP>(out + ((size_t)w * gm.D + d) * CV::ACC_LIMBS + k * N, X);
 }
 
+// one-warp Horner (MGB_ONEWARP_HORNER): lane 8g + l holds 64-bit digit l of coordinate g of an XYZZ accumulator
+template <class FP>
+MGB_DEV unsigned long long ow_load(const uint32_t* src) {
+  const int g = (threadIdx.x & 31) >> 3, l = threadIdx.x & 7;
+  return l < FP::N / 2 ? (((unsigned long long)src[g * FP::N + 2 * l + 1] << 32) | src[g * FP::N + 2 * l]) : 0ull;
+}
+template <class FP>
+MGB_DEV void ow_store(uint32_t* dst, unsigned long long v) {
+  const int g = (threadIdx.x & 31) >> 3, l = threadIdx.x & 7;
+  if (l < FP::N / 2) { dst[g * FP::N + 2 * l] = (uint32_t)v; dst[g * FP::N + 2 * l + 1] = (uint32_t)(v >> 32); }
+}
+
 // block = one window: S_w = sum_d 2^(sh_d) X_d + sum_l B_l by Horner over the digits; the four warps
 // share the multiplications of each formula level (coop.cuh), as in k_final.
 template <class CV>
@@ -1100,6 +1117,20 @@ __global__ void __launch_bounds__(128) k_window_assemble(MsmParams pr, ReduceGeo
   __shared__ int flag;
   CoopMem<FP> m{sm};
   const int w = w_begin + blockIdx.x;
+#if MGB_ONEWARP_HORNER
+  if constexpr (std::is_same<typename CV::Coop, CoopWeierstrass<FP>>::value) {
+    if (threadIdx.x >= 32) return;
+    typedef OneWarpWeierstrass<FP> OW;
+    unsigned long long v = ow_load<FP>(in + ((size_t)w * gm.D + gm.D - 1) * CV::ACC_LIMBS);
+    for (int dd = gm.D - 2; dd >= 0; dd--) {
+      for (int k = 0; k < gm.width[dd]; k++) v = OW::dbl(v);
+      v = OW::add(v, ow_load<FP>(in + ((size_t)w * gm.D + dd) * CV::ACC_LIMBS));
+    }
+    v = OW::add(v, ow_load<FP>(in + ((size_t)pr.K * gm.D + w) * CV::ACC_LIMBS));
+    ow_store<FP>(Sw + (size_t)w * CV::ACC_LIMBS, v);
+    return;
+  }
+#endif
   auto load_point = [&](int slot0, const uint32_t* src) {
     if (threadIdx.x < 4 * N) sm[slot0 * N + threadIdx.x] = src[threadIdx.x];
   };
@@ -1126,6 +1157,19 @@ __global__ void __launch_bounds__(128) k_final(int K, int c, const uint32_t* __r
   __shared__ uint32_t sm[COOP_SLOTS * N];
   __shared__ int flag;
   CoopMem<FP> m{sm};
+#if MGB_ONEWARP_HORNER
+  if constexpr (std::is_same<typename CV::Coop, CoopWeierstrass<FP>>::value) {
+    if (threadIdx.x >= 32) return;
+    typedef OneWarpWeierstrass<FP> OW;
+    unsigned long long v = ow_load<FP>(Sw + (size_t)(K - 1) * CV::ACC_LIMBS);
+    for (int w = K - 2; w >= 0; w--) {
+      for (int d = 0; d < c; d++) v = OW::dbl(v);
+      v = OW::add(v, ow_load<FP>(Sw + (size_t)w * CV::ACC_LIMBS));
+    }
+    ow_store<FP>(out_acc, v);
+    return;
+  }
+#endif
   // accumulator slots 0..3 and operand slots 4..7 hold the 4 coordinates of CV::acc in order
   auto load_point = [&](int slot0, const uint32_t* src) {
     if (threadIdx.x < 4 * N) sm[slot0 * N + threadIdx.x] = src[threadIdx.x];
