@@ -11,7 +11,14 @@
 //   k_reduce_*    bucket running sums per window chunk, then segment combination [:556-583]
 //   k_final       Horner over windows + affine normalisation                 [:311-334, curve-projective.ts:335-349]
 #pragma once
+#ifdef MGB_HOST_EMU
+// host emulation (tests only): tests/host_emu/cuda_emu.h, included first, stands in for the CUDA built-ins used below
+#ifndef MGB_CUDA_EMU
+#error "MGB_HOST_EMU: include tests/host_emu/cuda_emu.h before engine.cuh"
+#endif
+#else
 #include <cuda_runtime.h>
+#endif
 #include "ec.cuh"
 #include "coop.cuh"
 #include "onewarp.cuh"
@@ -533,6 +540,15 @@ MGB_DEV Fe<P> shfl_fe(const Fe<P>& a, int src) {
   return r;
 }
 
+#ifdef MGB_HOST_EMU
+// emulation: the copy completes at once, so the group bookkeeping has nothing to wait for
+MGB_DEV void cp_async16(void* smem, const void* gmem) { memcpy(smem, gmem, 16); }
+MGB_DEV void cp_async4(void* smem, const void* gmem) { memcpy(smem, gmem, 4); }
+MGB_DEV void cp_async8(void* smem, const void* gmem) { memcpy(smem, gmem, 8); }
+MGB_DEV void cp_async_commit() {}
+MGB_DEV void cp_async_wait_all() {}
+MGB_DEV void cp_async_wait_but_one() {}
+#else
 MGB_DEV void cp_async16(void* smem, const void* gmem) {
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
@@ -548,6 +564,7 @@ MGB_DEV void cp_async8(void* smem, const void* gmem) {
 MGB_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 MGB_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 MGB_DEV void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }   // all but the most recent group
+#endif
 
 template <class CV>
 MGB_DEV typename CV::vpoint load_ref(const uint32_t* table, uint32_t ref) {

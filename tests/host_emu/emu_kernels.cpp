@@ -1,0 +1,33 @@
+// TEST-ONLY: whole kernels of the engine on the CPU.  engine.cuh is compiled for the host against the CUDA stand-ins of
+// cuda_emu.h; a launch becomes simt::run_grid (blocks one after the other, each as 128 lockstep host threads with real
+// shuffles / ballots / barriers / atomics).  Not shipped, not linked into the product library.
+#define MGB_HOST_EMU 1
+#include "cuda_emu.h"
+#include "../../montgomery_b200/csrc/engine.cuh"
+using namespace mgb;
+
+// k_batch_add<curve, EMAX = 8, MINB = 4, FIRST>: one round of batched-affine additions (see engine.cuh).  All buffers are
+// the caller's; `blocks` must be a multiple of 4 (the static first tile of a warp assumes MINB blocks per SM).
+template <class CV, bool FIRST>
+static void batch_add(uint32_t* V, const PairEnt* pairs, const uint32_t* npairs_ptr, int r, int E_big, uint32_t n_big, PairEnt* pairs_out,
+                      uint32_t* npairs_out, uint32_t* tile_counter, const uint2* recs, const uint8_t* lifes, const uint32_t* table,
+                      const uint32_t* offs, uint32_t b_begin, uint32_t b_end, uint4* scratch, int blocks) {
+  simt::run_grid((unsigned)blocks, 128, [&] {
+    k_batch_add<CV, 8, 4, FIRST>(V, pairs, npairs_ptr, r, E_big, n_big, pairs_out, npairs_out, tile_counter, recs, lifes, table, offs, b_begin, b_end, scratch);
+  });
+}
+
+extern "C" void emu_batch_add(int curve, int first, uint32_t* V, const uint32_t* pairs, const uint32_t* npairs_ptr, int r, int E_big, uint32_t n_big,
+                              uint32_t* pairs_out, uint32_t* npairs_out, uint32_t* tile_counter, const uint32_t* recs, const uint8_t* lifes,
+                              const uint32_t* table, const uint32_t* offs, uint32_t b_begin, uint32_t b_end, uint32_t* scratch, int blocks) {
+  auto P = reinterpret_cast<const PairEnt*>(pairs);
+  auto PO = reinterpret_cast<PairEnt*>(pairs_out);
+  auto RC = reinterpret_cast<const uint2*>(recs);
+  auto SC = reinterpret_cast<uint4*>(scratch);
+#define GO(CV) (first ? batch_add<CV, true>(V, P, npairs_ptr, r, E_big, n_big, PO, npairs_out, tile_counter, RC, lifes, table, offs, b_begin, b_end, SC, blocks) \
+                      : batch_add<CV, false>(V, P, npairs_ptr, r, E_big, n_big, PO, npairs_out, tile_counter, RC, lifes, table, offs, b_begin, b_end, SC, blocks))
+  if (curve == 0) GO(CurveBls377);
+  else if (curve == 1) GO(CurvePallas);
+  else GO(CurveBls381);
+#undef GO
+}

@@ -1,0 +1,127 @@
+"""CPU test of a whole KERNEL: k_batch_add (batched-affine bucket accumulation, csrc/engine.cuh) compiled for the host
+against the CUDA stand-ins of tests/host_emu/cuda_emu.h and run as 4 blocks x 128 lockstep host threads -- shuffles,
+ballots, atomics, shared-memory staging, dynamic tile hand-out and the per-tile pair-list reservation included.  Two tree
+rounds over synthetic buckets of 1..4 points, with endomorphism / negation references, a doubling and a cancellation,
+against the oracle's affine arithmetic.  (The GPU versions of this check are the MSM parity tests of test_gpu_msm.py.)"""
+import ctypes
+import os
+import random
+import subprocess
+
+import pytest
+
+from oracle.params import BLS12_377, PALLAS
+from oracle.weierstrass import AffineCurve
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.timeout(600)
+REF_NEG, REF_ENDO, REF_EMPTY = 0x80000000, 0x40000000, 0xFFFFFFFF
+U32 = ctypes.c_uint32
+
+
+@pytest.fixture(scope="module")
+def emu_k(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("emu_k") / "emu_k.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-Wno-unknown-pragmas", "-o", so,
+                           os.path.join(ROOT, "tests", "host_emu", "emu_kernels.cpp")])
+    return ctypes.CDLL(so)
+
+
+@pytest.mark.parametrize("cid,prm,n,e_big", [(0, BLS12_377, 12, 2), (0, BLS12_377, 12, 8), (1, PALLAS, 8, 4)],
+                         ids=["bls12-377-E2", "bls12-377-E8", "pallas-E4"])
+def test_batch_add_two_rounds(emu_k, cid, prm, n, e_big):
+    p = prm.p
+    R = 1 << (32 * n)
+    Ri = pow(R, -1, p)
+    A = AffineCurve(prm)
+    rnd = random.Random(90 + cid + e_big)
+    limbs = lambda x: [(x >> (32 * i)) & 0xFFFFFFFF for i in range(n)]
+    M = lambda x: x * R % p
+
+    # ---- point table: x | y | beta*x, Montgomery form
+    npts = 64
+    pts = [A.scale(rnd.randrange(1, prm.q), prm.G) for _ in range(npts)]
+    table = []
+    for x, y in pts:
+        table += limbs(M(x)) + limbs(M(y)) + limbs(M(prm.beta * x % p))
+
+    def ref_point(ref):
+        x, y = pts[ref & 0x3FFFFFFF]
+        if ref & REF_ENDO:
+            x = prm.beta * x % p
+        if ref & REF_NEG:
+            y = (-y) % p
+        return (x, y)
+
+    def rand_ref():
+        return rnd.randrange(npts) | rnd.choice([0, REF_NEG]) | rnd.choice([0, REF_ENDO])
+
+    # ---- buckets of 1..4 elements at 4-slot strides; slot pair q = slot / 2
+    nb = 150
+    buckets = []
+    for j in range(nb):
+        k = rnd.choice([1, 2, 3, 4, 4, 4])
+        refs = [rand_ref() for _ in range(k)]
+        if j == 3:                                         # doubling in round 0
+            refs = [refs[0], refs[0]] + [rand_ref(), rand_ref()]
+        if j == 5:                                         # cancellation in round 0, then infinity + point in round 1
+            refs = [refs[0], refs[0] ^ REF_NEG] + [rand_ref(), rand_ref()]
+        if j == 7:                                         # doubling in round 1: the two halves of the bucket are equal
+            a, b = rand_ref(), rand_ref()
+            refs = [a, b, a, b]
+        buckets.append(refs)
+    npairs = 2 * nb
+    recs, lifes = [], []
+    for refs in buckets:
+        k = len(refs)
+        recs += [refs[0], refs[1] if k > 1 else REF_EMPTY]
+        lifes.append(2 if k > 2 else 1)
+        if k > 2:
+            recs += [refs[2], refs[3] if k > 3 else REF_EMPTY]
+        else:
+            recs += [REF_EMPTY, REF_EMPTY]                 # no pair at all
+        lifes.append(1)
+    while len(lifes) % 4:
+        lifes.append(0)
+
+    blocks = 4
+    V = (U32 * (2 * npairs * 2 * n))()
+    pairs_a = (U32 * (2 * npairs))()
+    pairs_b = (U32 * (2 * npairs))()
+    cnt_a, cnt_b, tiles = U32(0), U32(0), U32(0)
+    scratch = (U32 * (blocks * 4 * 8 * (n // 4) * 32 * 4))()
+    offs = (U32 * 2)(0, 2 * npairs)
+    dummy = U32(0)
+    emu_k.emu_batch_add(cid, 1, V, pairs_a, ctypes.byref(dummy), 0, e_big, 1000, pairs_a, ctypes.byref(cnt_a), ctypes.byref(tiles),
+                        (U32 * len(recs))(*recs), (ctypes.c_uint8 * len(lifes))(*lifes), (U32 * len(table))(*table), offs, 0, 1, scratch, blocks)
+
+    def slot(s):
+        w = [int(V[s * 2 * n + i]) for i in range(2 * n)]
+        if w[n - 1] & 0x80000000:
+            return None
+        x = sum(w[i] << (32 * i) for i in range(n)) * Ri % p
+        y = sum(w[n + i] << (32 * i) for i in range(n)) * Ri % p
+        return (x, y)
+
+    def add_all(refs):
+        acc = None
+        for r_ in refs:
+            acc = A.add(acc, ref_point(r_))
+        return acc
+
+    exp_pairs = set()
+    for j, refs in enumerate(buckets):
+        assert slot(4 * j) == add_all(refs[:2]), ("round 0, first half of bucket", j)
+        if len(refs) > 2:
+            assert slot(4 * j + 2) == add_all(refs[2:]), ("round 0, second half of bucket", j)
+            exp_pairs.add((4 * j, 2))
+    got_pairs = {(int(pairs_a[2 * i]), int(pairs_a[2 * i + 1])) for i in range(cnt_a.value)}
+    assert cnt_a.value == len(exp_pairs) and got_pairs == exp_pairs        # the next round's pair list, no duplicates, no holes
+
+    # ---- round 1: V[slot] += V[slot + 2] for the listed slots
+    tiles.value = 0
+    emu_k.emu_batch_add(cid, 0, V, pairs_a, ctypes.byref(cnt_a), 1, e_big, 1000, pairs_b, ctypes.byref(cnt_b), ctypes.byref(tiles),
+                        (U32 * len(recs))(*recs), (ctypes.c_uint8 * len(lifes))(*lifes), (U32 * len(table))(*table), offs, 0, 1, scratch, blocks)
+    for j, refs in enumerate(buckets):
+        assert slot(4 * j) == add_all(refs), ("round 1, bucket", j)
+    assert cnt_b.value == 0                                                 # nobody lives past round 1
