@@ -19,11 +19,14 @@ REF_NEG, REF_ENDO, REF_EMPTY = 0x80000000, 0x40000000, 0xFFFFFFFF
 U32 = ctypes.c_uint32
 
 
-@pytest.fixture(scope="module")
-def emu_k(tmp_path_factory):
+# "product": the kernel as shipped; "warp_inv": the build-time experiment -DMGB_WARP_INV=1 (a tile's total is inverted by the
+# lane-parallel inverse of csrc/warp.cuh instead of lane 0 alone) -- same inputs, same expected sums
+@pytest.fixture(scope="module", params=["product", "warp_inv"])
+def emu_k(request, tmp_path_factory):
     so = str(tmp_path_factory.mktemp("emu_k") / "emu_k.so")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-Wno-unknown-pragmas", "-o", so,
-                           os.path.join(ROOT, "tests", "host_emu", "emu_kernels.cpp")])
+    flags = ["-DMGB_WARP_INV=1"] if request.param == "warp_inv" else []
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-Wno-unknown-pragmas"] + flags +
+                          ["-o", so, os.path.join(ROOT, "tests", "host_emu", "emu_kernels.cpp")])
     return ctypes.CDLL(so)
 
 
