@@ -31,3 +31,13 @@ extern "C" void emu_batch_add(int curve, int first, uint32_t* V, const uint32_t*
   else GO(CurveBls381);
 #undef GO
 }
+
+// k_final: result = sum_w 2^(c w) S_w by Horner, one 128-thread block (one warp with -DMGB_ONEWARP_HORNER=1)
+extern "C" void emu_final(int curve, int K, int c, const uint32_t* Sw, uint32_t* out_acc) {
+  simt::run_grid(1, 128, [&] {
+    if (curve == 0) k_final<CurveBls377>(K, c, Sw, out_acc);
+    else if (curve == 1) k_final<CurvePallas>(K, c, Sw, out_acc);
+    else if (curve == 2) k_final<CurveBls381>(K, c, Sw, out_acc);
+    else k_final<CurveEd377>(K, c, Sw, out_acc);
+  });
+}

@@ -10,7 +10,8 @@ import subprocess
 
 import pytest
 
-from oracle.params import BLS12_377, PALLAS
+from oracle.params import BLS12_377, ED_ON_BLS12_377, PALLAS
+from oracle.twisted_edwards import TwistedEdwardsCurve
 from oracle.weierstrass import AffineCurve
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -21,10 +22,11 @@ U32 = ctypes.c_uint32
 
 # "product": the kernel as shipped; "warp_inv": the build-time experiment -DMGB_WARP_INV=1 (a tile's total is inverted by the
 # lane-parallel inverse of csrc/warp.cuh instead of lane 0 alone) -- same inputs, same expected sums
-@pytest.fixture(scope="module", params=["product", "warp_inv"])
+# "onewarp": -DMGB_ONEWARP_HORNER=1 (the Horner kernels of the Weierstrass curves run in one warp, csrc/onewarp.cuh)
+@pytest.fixture(scope="module", params=["product", "warp_inv", "onewarp"])
 def emu_k(request, tmp_path_factory):
     so = str(tmp_path_factory.mktemp("emu_k") / "emu_k.so")
-    flags = ["-DMGB_WARP_INV=1"] if request.param == "warp_inv" else []
+    flags = {"product": [], "warp_inv": ["-DMGB_WARP_INV=1"], "onewarp": ["-DMGB_ONEWARP_HORNER=1"]}[request.param]
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-Wno-unknown-pragmas"] + flags +
                           ["-o", so, os.path.join(ROOT, "tests", "host_emu", "emu_kernels.cpp")])
     return ctypes.CDLL(so)
@@ -128,3 +130,67 @@ def test_batch_add_two_rounds(emu_k, cid, prm, n, e_big):
     for j, refs in enumerate(buckets):
         assert slot(4 * j) == add_all(refs), ("round 1, bucket", j)
     assert cnt_b.value == 0                                                 # nobody lives past round 1
+
+
+@pytest.mark.parametrize("cid,prm,n", [(0, BLS12_377, 12), (1, PALLAS, 8)], ids=["bls12-377", "pallas"])
+def test_final_horner_kernel(emu_k, cid, prm, n):
+    """k_final: sum_w 2^(c w) S_w over K window sums given as XYZZ accumulators (one of them the neutral element)."""
+    p = prm.p
+    R = 1 << (32 * n)
+    Ri = pow(R, -1, p)
+    A = AffineCurve(prm)
+    rnd = random.Random(70 + cid)
+    M = lambda x: x * R % p
+    limbs = lambda x: [(x >> (32 * i)) & 0xFFFFFFFF for i in range(n)]
+    K, c = 4, 5
+    S = [A.scale(rnd.randrange(1, prm.q), prm.G) for _ in range(K)]
+    S[2] = None
+    words = []
+    for P in S:
+        if P is None:
+            coords = [0, M(1), 0, 0]
+        else:
+            z = rnd.randrange(1, p)
+            coords = [M(P[0] * z * z % p), M(P[1] * z * z * z % p), M(z * z % p), M(z * z * z % p)]
+        for v in coords:
+            words += limbs(v)
+    out = (U32 * (4 * n))()
+    emu_k.emu_final(cid, K, c, (U32 * len(words))(*words), out)
+    X, Y, ZZ, ZZZ = [sum(int(out[k * n + i]) << (32 * i) for i in range(n)) * Ri % p for k in range(4)]
+    got = None if ZZ == 0 else (X * pow(ZZ, -1, p) % p, Y * pow(ZZZ, -1, p) % p)
+    exp = None
+    for w in reversed(range(K)):
+        for _ in range(c):
+            exp = A.double(exp)
+        exp = A.add(exp, S[w])
+    assert got == exp
+
+
+def test_final_horner_kernel_twisted_edwards(emu_k):
+    prm, n = ED_ON_BLS12_377, 8
+    p = prm.p
+    R = 1 << (32 * n)
+    Ri = pow(R, -1, p)
+    T = TwistedEdwardsCurve(prm)
+    rnd = random.Random(77)
+    M = lambda x: x * R % p
+    limbs = lambda x: [(x >> (32 * i)) & 0xFFFFFFFF for i in range(n)]
+    K, c = 3, 4
+    S = [T.scale(rnd.randrange(1, prm.q), T.one) for _ in range(K)]
+    S[1] = T.zero
+    words = []
+    for P in S:
+        x, y = T.to_affine(P)
+        z = rnd.randrange(1, p)
+        for v in (M(x * z % p), M(y * z % p), M(z), M(x * y * z % p)):
+            words += limbs(v)
+    out = (U32 * (4 * n))()
+    emu_k.emu_final(3, K, c, (U32 * len(words))(*words), out)
+    X, Y, Z, Tt = [sum(int(out[k * n + i]) << (32 * i) for i in range(n)) * Ri % p for k in range(4)]
+    zi = pow(Z, -1, p)
+    exp = T.zero
+    for w in reversed(range(K)):
+        for _ in range(c):
+            exp = T.double(exp)
+        exp = T.add(exp, S[w])
+    assert (X * zi % p, Y * zi % p) == T.to_affine(exp) and (X * Y - Tt * Z) % p == 0
