@@ -41,3 +41,16 @@ extern "C" void emu_final(int curve, int K, int c, const uint32_t* Sw, uint32_t*
     else k_final<CurveEd377>(K, c, Sw, out_acc);
   });
 }
+
+// k_pair_add<CurveEd377, FIRST>: one tree round of the twisted-Edwards accumulation (unified additions, no inversion)
+extern "C" void emu_pair_add_te(int first, uint32_t* V, const uint32_t* pairs, const uint32_t* npairs_ptr, int r, uint32_t* pairs_out,
+                                uint32_t* npairs_out, const uint32_t* recs, const uint8_t* lifes, const uint32_t* table, const uint32_t* offs,
+                                uint32_t b_begin, uint32_t b_end, int blocks) {
+  auto P = reinterpret_cast<const PairEnt*>(pairs);
+  auto PO = reinterpret_cast<PairEnt*>(pairs_out);
+  auto RC = reinterpret_cast<const uint2*>(recs);
+  simt::run_grid((unsigned)blocks, 128, [&] {
+    if (first) k_pair_add<CurveEd377, true>(V, P, npairs_ptr, r, PO, npairs_out, RC, lifes, table, offs, b_begin, b_end);
+    else k_pair_add<CurveEd377, false>(V, P, npairs_ptr, r, PO, npairs_out, RC, lifes, table, offs, b_begin, b_end);
+  });
+}

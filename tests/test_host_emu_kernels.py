@@ -29,12 +29,21 @@ def emu_k(request, tmp_path_factory):
     flags = {"product": [], "warp_inv": ["-DMGB_WARP_INV=1"], "onewarp": ["-DMGB_ONEWARP_HORNER=1"]}[request.param]
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-Wno-unknown-pragmas"] + flags +
                           ["-o", so, os.path.join(ROOT, "tests", "host_emu", "emu_kernels.cpp")])
-    return ctypes.CDLL(so)
+    lib = ctypes.CDLL(so)
+    lib.variant = request.param
+    return lib
+
+
+def only(lib, *variants):
+    """an experiment build is exercised by the tests of the kernel it changes; the others would repeat the product run"""
+    if lib.variant not in variants:
+        pytest.skip("kernel not affected by the %s build" % lib.variant)
 
 
 @pytest.mark.parametrize("cid,prm,n,e_big", [(0, BLS12_377, 12, 2), (0, BLS12_377, 12, 8), (1, PALLAS, 8, 4)],
                          ids=["bls12-377-E2", "bls12-377-E8", "pallas-E4"])
 def test_batch_add_two_rounds(emu_k, cid, prm, n, e_big):
+    only(emu_k, "product", "warp_inv")
     p = prm.p
     R = 1 << (32 * n)
     Ri = pow(R, -1, p)
@@ -135,6 +144,7 @@ def test_batch_add_two_rounds(emu_k, cid, prm, n, e_big):
 @pytest.mark.parametrize("cid,prm,n", [(0, BLS12_377, 12), (1, PALLAS, 8)], ids=["bls12-377", "pallas"])
 def test_final_horner_kernel(emu_k, cid, prm, n):
     """k_final: sum_w 2^(c w) S_w over K window sums given as XYZZ accumulators (one of them the neutral element)."""
+    only(emu_k, "product", "onewarp")
     p = prm.p
     R = 1 << (32 * n)
     Ri = pow(R, -1, p)
@@ -167,6 +177,7 @@ def test_final_horner_kernel(emu_k, cid, prm, n):
 
 
 def test_final_horner_kernel_twisted_edwards(emu_k):
+    only(emu_k, "product")
     prm, n = ED_ON_BLS12_377, 8
     p = prm.p
     R = 1 << (32 * n)
@@ -194,3 +205,74 @@ def test_final_horner_kernel_twisted_edwards(emu_k):
             exp = T.double(exp)
         exp = T.add(exp, S[w])
     assert (X * zi % p, Y * zi % p) == T.to_affine(exp) and (X * Y - Tt * Z) % p == 0
+
+
+def test_pair_add_two_rounds_twisted_edwards(emu_k):
+    """k_pair_add (the accumulation kernel of the twisted-Edwards curve): buckets of 2..4 points laid out back to back
+    as the scatter kernel does, negated references, P + P and P + (-P), two tree rounds, next round's pair list."""
+    only(emu_k, "product")
+    prm, n = ED_ON_BLS12_377, 8
+    p = prm.p
+    R = 1 << (32 * n)
+    Ri = pow(R, -1, p)
+    T = TwistedEdwardsCurve(prm)
+    rnd = random.Random(95)
+    M = lambda x: x * R % p
+    limbs = lambda x: [(x >> (32 * i)) & 0xFFFFFFFF for i in range(n)]
+    npts = 48
+    pts = [T.scale(rnd.randrange(1, prm.q), T.one) for _ in range(npts)]
+    table = []
+    for P in pts:
+        x, y = T.to_affine(P)
+        table += limbs(M(x)) + limbs(M(y)) + limbs(M(x * y % p))
+    ref_point = lambda ref: T.negate(pts[ref & 0x3FFFFFFF]) if ref & REF_NEG else pts[ref & 0x3FFFFFFF]
+    rand_ref = lambda: rnd.randrange(npts) | rnd.choice([0, REF_NEG])
+    buckets = []
+    for j in range(100):
+        refs = [rand_ref() for _ in range(rnd.choice([2, 3, 4, 4]))]
+        if j == 2:
+            refs = [refs[0], refs[0], rand_ref(), rand_ref()]                 # doubling (the addition law is unified)
+        if j == 4:
+            refs = [refs[0], refs[0] ^ REF_NEG, rand_ref()]                   # neutral element as an intermediate sum
+        buckets.append(refs)
+    recs, lifes, first_slot = [], [], []
+    for refs in buckets:
+        first_slot.append(len(recs))                                          # = 2 * (index of the bucket's first slot pair)
+        recs += [refs[0], refs[1]]
+        lifes.append(2 if len(refs) > 2 else 1)
+        if len(refs) > 2:
+            recs += [refs[2], refs[3] if len(refs) > 3 else REF_EMPTY]
+            lifes.append(1)
+    npairs = len(lifes)
+    while len(lifes) % 4:
+        lifes.append(0)
+    V = (U32 * (2 * npairs * 4 * n))()
+    pairs_a, pairs_b = (U32 * (2 * npairs))(), (U32 * (2 * npairs))()
+    cnt_a, cnt_b, dummy = U32(0), U32(0), U32(0)
+    offs = (U32 * 2)(0, 2 * npairs)
+    args = ((U32 * len(recs))(*recs), (ctypes.c_uint8 * len(lifes))(*lifes), (U32 * len(table))(*table), offs, 0, 1, 3)
+    emu_k.emu_pair_add_te(1, V, pairs_a, ctypes.byref(dummy), 0, pairs_a, ctypes.byref(cnt_a), *args)
+
+    def slot(s):
+        X, Y, Z, Tt = [sum(int(V[(s * 4 + k) * n + i]) << (32 * i) for i in range(n)) * Ri % p for k in range(4)]
+        assert (X * Y - Tt * Z) % p == 0
+        zi = pow(Z, -1, p)
+        return (X * zi % p, Y * zi % p)
+
+    def add_all(refs):
+        acc = T.zero
+        for r_ in refs:
+            acc = T.add(acc, ref_point(r_))
+        return T.to_affine(acc)
+
+    exp_pairs = set()
+    for refs, s0 in zip(buckets, first_slot):
+        assert slot(s0) == add_all(refs[:2])
+        if len(refs) > 2:
+            assert slot(s0 + 2) == add_all(refs[2:])
+            exp_pairs.add((s0, 2))
+    assert {(int(pairs_a[2 * i]), int(pairs_a[2 * i + 1])) for i in range(cnt_a.value)} == exp_pairs and cnt_a.value == len(exp_pairs)
+    emu_k.emu_pair_add_te(0, V, pairs_a, ctypes.byref(cnt_a), 1, pairs_b, ctypes.byref(cnt_b), *args)
+    for refs, s0 in zip(buckets, first_slot):
+        assert slot(s0) == add_all(refs)
+    assert cnt_b.value == 0
