@@ -54,3 +54,25 @@ extern "C" void emu_pair_add_te(int first, uint32_t* V, const uint32_t* pairs, c
     else k_pair_add<CurveEd377, false>(V, P, npairs_ptr, r, PO, npairs_out, RC, lifes, table, offs, b_begin, b_end);
   });
 }
+
+// byte ingestion and read-back (k_set_points / k_get_points) and the combine + normalise kernel (k_normalize: sums `count`
+// partial accumulators -- the multi-GPU combine -- and returns the canonical affine point)
+template <class CV> static void set_get(uint32_t n, const uint32_t* xy, const uint8_t* is_zero, uint32_t* table, uint32_t* xy_back, uint8_t* zero_back) {
+  const unsigned blocks = (n + 127) / 128;
+  simt::run_grid(blocks, 128, [&] { k_set_points<CV>(n, xy, is_zero, table); });
+  simt::run_grid(blocks, 128, [&] { k_get_points<CV>(0, n, table, xy_back, zero_back); });
+}
+extern "C" void emu_set_get_points(int curve, uint32_t n, const uint32_t* xy, const uint8_t* is_zero, uint32_t* table, uint32_t* xy_back, uint8_t* zero_back) {
+  if (curve == 0) set_get<CurveBls377>(n, xy, is_zero, table, xy_back, zero_back);
+  else if (curve == 1) set_get<CurvePallas>(n, xy, is_zero, table, xy_back, zero_back);
+  else if (curve == 2) set_get<CurveBls381>(n, xy, is_zero, table, xy_back, zero_back);
+  else set_get<CurveEd377>(n, xy, is_zero, table, xy_back, zero_back);
+}
+extern "C" void emu_normalize(int curve, const uint32_t* accs, int count, uint32_t* out_xy, uint32_t* out_flag) {
+  simt::run_grid(1, 32, [&] {
+    if (curve == 0) k_normalize<CurveBls377>(accs, count, out_xy, out_flag);
+    else if (curve == 1) k_normalize<CurvePallas>(accs, count, out_xy, out_flag);
+    else if (curve == 2) k_normalize<CurveBls381>(accs, count, out_xy, out_flag);
+    else k_normalize<CurveEd377>(accs, count, out_xy, out_flag);
+  });
+}

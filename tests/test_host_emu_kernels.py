@@ -10,7 +10,7 @@ import subprocess
 
 import pytest
 
-from oracle.params import BLS12_377, ED_ON_BLS12_377, PALLAS
+from oracle.params import BLS12_377, BLS12_381, ED_ON_BLS12_377, PALLAS
 from oracle.twisted_edwards import TwistedEdwardsCurve
 from oracle.weierstrass import AffineCurve
 
@@ -276,3 +276,48 @@ def test_pair_add_two_rounds_twisted_edwards(emu_k):
     for refs, s0 in zip(buckets, first_slot):
         assert slot(s0) == add_all(refs)
     assert cnt_b.value == 0
+
+
+@pytest.mark.parametrize("cid,prm,n", [(0, BLS12_377, 12), (1, PALLAS, 8), (2, BLS12_381, 12)], ids=["bls12-377", "pallas", "bls12-381"])
+def test_set_get_points_and_combine_weierstrass(emu_k, cid, prm, n):
+    """k_set_points (canonical bytes -> Montgomery table entry x | y | beta x, infinity flag), k_get_points (back), and
+    k_normalize summing three partial accumulators (the multi-GPU combine) into the canonical affine point."""
+    only(emu_k, "product")
+    p = prm.p
+    R = 1 << (32 * n)
+    A = AffineCurve(prm)
+    rnd = random.Random(33 + cid)
+    limbs = lambda x: [(x >> (32 * i)) & 0xFFFFFFFF for i in range(n)]
+    val = lambda w: sum(int(v) << (32 * i) for i, v in enumerate(w))
+    pts = [A.scale(rnd.randrange(1, prm.q), prm.G) for _ in range(130)]          # two blocks, the second one partly idle
+    flags = [1 if i in (5, 129) else 0 for i in range(len(pts))]
+    xy = []
+    for x, y in pts:
+        xy += limbs(x) + limbs(y)
+    table = (U32 * (len(pts) * 3 * n))()
+    back = (U32 * len(xy))()
+    zback = (ctypes.c_uint8 * len(pts))()
+    emu_k.emu_set_get_points(cid, len(pts), (U32 * len(xy))(*xy), (ctypes.c_uint8 * len(pts))(*flags), table, back, zback)
+    for i, (x, y) in enumerate(pts):
+        e = [int(v) for v in table[i * 3 * n:(i + 1) * 3 * n]]
+        if flags[i]:
+            assert e[n - 1] & 0x80000000 and zback[i] == 1 and val(back[i * 2 * n:i * 2 * n + 2 * n]) == 0
+            continue
+        assert (val(e[:n]), val(e[n:2 * n]), val(e[2 * n:])) == (x * R % p, y * R % p, prm.beta * x * R % p)
+        assert (val(back[i * 2 * n:i * 2 * n + n]), val(back[i * 2 * n + n:(i + 1) * 2 * n]), zback[i]) == (x, y, 0)
+    # combine: three XYZZ partial sums (one the neutral element) -> affine
+    parts = [pts[0], None, pts[1]]
+    words = []
+    for P in parts:
+        z = rnd.randrange(1, p)
+        coords = [0, R % p, 0, 0] if P is None else [P[0] * z * z * R % p, P[1] * z * z * z * R % p, z * z * R % p, z * z * z * R % p]
+        for v in coords:
+            words += limbs(v)
+    out, flag = (U32 * (2 * n))(), U32(7)
+    emu_k.emu_normalize(cid, (U32 * len(words))(*words), 3, out, ctypes.byref(flag))
+    assert (val(out[:n]), val(out[n:]), flag.value) == (*A.add(pts[0], pts[1]), 0)
+    words2 = words[:4 * n] + [w for w in words[:4 * n]]
+    neg = A.negate(pts[0])
+    words2[4 * n:] = sum((limbs(v) for v in (neg[0] * R % p, neg[1] * R % p, R % p, R % p)), [])
+    emu_k.emu_normalize(cid, (U32 * len(words2))(*words2), 2, out, ctypes.byref(flag))         # P + (-P): the neutral element
+    assert flag.value == 1 and val(out[:]) == 0
