@@ -11,6 +11,7 @@ buffer of scalars and a `PointSet` handle naming points resident in HBM.  The re
 Node-free runtime in this image, so this layer is Python; INTEGRATION.md shows the N-API shim.
 """
 import ctypes
+import weakref
 
 import numpy as np
 
@@ -93,6 +94,10 @@ class MsmEngine:
         tm = _native.MgbTiming()
         opts = self._opts(c, unsafe, projective)
         if device_ptr is not None:
+            if n is None:
+                raise ValueError("msm(device_ptr=...): n is required (the length of a raw device buffer is unknown)")
+            if int(device_ptr) % 16:
+                raise ValueError("msm(device_ptr=...): the scalar buffer must be 16-byte aligned")
             self._check(self.lib.mgb_msm_device(self._h, ctypes.c_void_p(device_ptr), n, ctypes.byref(opts), _ptr(out),
                                                 ctypes.byref(is_zero), ctypes.byref(tm)))
         else:
@@ -102,6 +107,8 @@ class MsmEngine:
                 raise ValueError("scalars buffer must be a multiple of 32 bytes")
             if n is None:
                 n = sc.size // 32
+            if n < 0 or n * 32 > sc.size:
+                raise ValueError("msm: n = %d exceeds the %d scalars in the buffer" % (n, sc.size // 32))
             self._check(self.lib.mgb_msm(self._h, _ptr(sc), n, ctypes.byref(opts), _ptr(out), ctypes.byref(is_zero), ctypes.byref(tm)))
         cb = self.curve.coord_bytes
         res = {
@@ -150,26 +157,34 @@ class _Parallel:
     def _engine(self, n):
         return self._m._engine_for(n)
 
+    def _new_point_set(self, n):
+        eng = self._m._engine_for(n)
+        ps = PointSet(eng, n)
+        self._m._owner = weakref.ref(ps)
+        return ps
+
     def pointsFromBytes(self, point_bytes, is_zero=None):
         n = len(point_bytes) // self._m.curve.point_bytes
-        eng = self._engine(n)
-        eng.set_points(point_bytes, is_zero)
-        return PointSet(eng, n)
+        ps = self._new_point_set(n)
+        ps.engine.set_points(point_bytes, is_zero)
+        return ps
 
     def scalarsFromBytes(self, scalar_bytes):
         a = np.frombuffer(scalar_bytes, dtype=np.uint8) if not isinstance(scalar_bytes, np.ndarray) else scalar_bytes
         return np.ascontiguousarray(a.reshape(-1, 32))
 
     def randomPointsFast(self, n, seed=0x6D6F6E74):
-        eng = self._engine(n)
-        eng.random_points(n, seed)
-        return PointSet(eng, n)
+        ps = self._new_point_set(n)
+        ps.engine.random_points(n, seed)
+        return ps
 
     def randomScalars(self, n, seed=0x6D6F6E74):
         return inputs.random_scalars(self._m.curve.q, n, seed)
 
     def msm(self, scalars, points, N, verboseTiming=False, options=None):
         options = options or {}
+        if N > points.n:
+            raise ValueError("msm: N = %d exceeds the %d points of the set" % (N, points.n))
         res, tm = points.engine.msm(scalars[:N] if isinstance(scalars, np.ndarray) else scalars, n=N, c=options.get("c"),
                                     unsafe=not options.get("useSafeAdditions", True))
         log = _log_from_timing(tm)
@@ -182,6 +197,8 @@ class _Parallel:
         """msm-basic over projective coordinates, no GLV (src/parallel.ts:69-87); Weierstrass curves only."""
         assert self._m.curve.kind == "weierstrass"
         options = options or {}
+        if N > points.n:
+            raise ValueError("msmProjective: N = %d exceeds the %d points of the set" % (N, points.n))
         res, tm = points.engine.msm(scalars[:N] if isinstance(scalars, np.ndarray) else scalars, n=N, c=options.get("c"), projective=True)
         return {"result": res, "log": _log_from_timing(tm), "timing": tm}
 
@@ -192,11 +209,19 @@ class _Parallel:
 
 
 class PointSet:
-    """Handle to points resident in HBM (the analogue of a `pointPtr` into wasm memory)."""
+    """Handle to points resident in HBM (the analogue of a `pointPtr` into wasm memory).  As in the reference,
+    where every pointPtr is its own memory (src/parallel.ts:97-116), every live PointSet has its own point table:
+    the set keeps its engine (one context) alive, and a curve module hands an engine to a new set only when the
+    set that used it before has been released (`close()` or garbage collection)."""
 
     def __init__(self, engine, n):
         self.engine = engine
         self.n = n
+
+    def close(self):
+        """Release the points: the module may give this set's engine (and its table) to the next set."""
+        self.n = 0
+        self.engine = _ReleasedEngine()
 
     def toBigints(self, first=0, n=None):
         n = self.n - first if n is None else n
@@ -206,21 +231,36 @@ class PointSet:
                 for r, f in zip(xy, z)]
 
 
+class _ReleasedEngine:
+    def __getattr__(self, name):
+        raise MsmError(_native_E_STATE, "this PointSet has been closed")
+
+
+_native_E_STATE = -4   # MGB_E_STATE
+
+
 class _CurveModule:
     def __init__(self, curve, device=0, max_points=None):
         self.curve = curve
         self.params = curve
         self.device = device
         self._engine = None
+        self._owner = None          # weakref to the PointSet whose points sit in self._engine
         self._max_points = max_points
         self.Parallel = _Parallel(self)
 
     def _engine_for(self, n):
+        """An engine whose point table is free for a new set of n points.  The cached engine is reused only when
+        the PointSet that owned it is gone; otherwise that set keeps it and a new engine is created (two live
+        PointSets never share a table), and an engine that is too small is left to its owner, not destroyed."""
         need = max(n, self._max_points or 0, 1)
-        if self._engine is None or self._engine.max_points < need:
-            if self._engine is not None:
-                self._engine.close()
-            self._engine = MsmEngine(self.curve, self.device, need)
+        owner = self._owner() if self._owner is not None else None
+        in_use = owner is not None and owner.engine is self._engine
+        if self._engine is not None and not in_use and self._engine.max_points >= need:
+            return self._engine
+        if self._engine is not None and not in_use:
+            self._engine.close()
+        self._engine = MsmEngine(self.curve, self.device, need)
         return self._engine
 
 

@@ -23,13 +23,18 @@
 #include "coop.cuh"
 #include "onewarp.cuh"
 
-// build-time switch (experiment, off): the Horner kernels of the Weierstrass curves run on one warp (onewarp.cuh)
+// Build-time switches, both ON since round 2 (A/B on a B200, profiles/r02_ab_winv_onewarp.json; =0 rebuilds the
+// round-1 paths for comparison):
+//   MGB_ONEWARP_HORNER  the Horner kernels of the Weierstrass curves run in one warp (onewarp.cuh): final sum
+//                       0.370 -> 0.335 ms at 2^20, 0.414 -> 0.373 ms at 2^16
+//   MGB_WARP_INV        k_batch_add inverts a tile's total with the lane-parallel inverse of warp.cuh (20.6 us
+//                       instead of 35.3 us alone, and all lanes use the issue slots): accumulate 5.01 -> 4.78 ms,
+//                       and 4.39 ms with tile sizes balanced over the resident warps (see msm_core)
 #ifndef MGB_ONEWARP_HORNER
-#define MGB_ONEWARP_HORNER 0
+#define MGB_ONEWARP_HORNER 1
 #endif
-// build-time switch (experiment, off): k_batch_add inverts a tile's total with the lane-parallel inverse of warp.cuh
 #ifndef MGB_WARP_INV
-#define MGB_WARP_INV 0
+#define MGB_WARP_INV 1
 #endif
 
 namespace mgb {
@@ -334,6 +339,15 @@ __global__ void __launch_bounds__(256) k_digits(MsmParams pr, uint32_t i_begin, 
     _Pragma("unroll") for (int k = 0; k < ML; k++) mag[0][k] = s[k];
     mag[0][ML] = 0;
     neg[0] = false;
+    // no reduction mod q on this path: the windows cover bits [0, MAG_BITS - 1) of the raw scalar, so a larger
+    // one would be silently truncated -- flag it instead (msm_core returns MGB_E_INVALID; the reference's
+    // scalars are field elements < q by construction, src/scalar-simple.ts)
+    {
+      constexpr int SB = CV::MAG_BITS - 1;
+      uint32_t over = SB < 256 ? (s[SB >> 5] >> (SB & 31)) : 0u;
+      _Pragma("unroll") for (int k = (SB >> 5) + 1; k < 8; k++) over |= s[k];
+      if (over) atomicOr(&counts[pr.nbuckets], 2u);
+    }
   }
   const int c = pr.c;
   const uint32_t L = pr.L, cmask = (1u << c) - 1;

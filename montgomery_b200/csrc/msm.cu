@@ -238,6 +238,8 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   CU(ctx, cudaStreamSynchronize(st));
   const uint32_t maxcount = ctx->h_pinned[65];
   const uint32_t* round_pairs = ctx->h_pinned + 68;
+  if (ctx->h_pinned[66] & 2u)
+    return fail(ctx, MGB_E_INVALID, "a scalar is out of range: this path takes scalars below 2^" + std::to_string(CV::MAG_BITS - 1) + " (reduce them mod q first)");
   if (ctx->h_pinned[66]) return fail(ctx, MGB_E_INVALID, "internal: a half-scalar exceeded its bound");
 
   // Depth of the bucket trees.  Full depth is ceil(log2(max bucket)).  A round costs at least one batch latency
@@ -303,16 +305,21 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
         // additions of this round (exact over all windows, from the scan)
         const uint64_t est = (r < SCAN_ROUNDS ? (uint64_t)round_pairs[r] : 0) * Kg / pr.K;
         const uint64_t warps = (uint64_t)ctx->sm_count * MINB * 4;
-        // tile shape: big tiles of E pairs per lane, at most 2 per resident warp, then tiles of E/4.
-        // Measured: the largest E that still gives 0.8 tiles per resident warp -- a batch (warp products
-        // + inversion) costs ~25 K issue cycles however small, so fewer, larger tiles win until warps idle.
-        int E = EMAX;
-        uint64_t fill10 = 8;
-        if (const char* ev = getenv("MGB_DEBUG_FILL")) fill10 = (uint64_t)atoi(ev);
+        // Tile shape: every tile holds E pairs per lane, with E chosen so that the round is an (almost) whole number
+        // k of tiles per resident warp:  per lane p = est / (32 * warps) additions, k = ceil(p / EMAX) tiles,
+        // E = ceil(p / k).  A batch (warp products + inversion) costs the same however small, so few, large tiles
+        // win -- but a power-of-two E leaves up to a quarter of the warps without a second tile (or without any
+        // tile) while the others finish.  Measured at 2^20 (profiles/r02_tile_sweep.txt): E = 64/64/32/16/8 ->
+        // 56/28/28/14/7 takes the accumulation from 4.78 to 4.37 ms.  Late rounds (p < 32) get two tiles per warp:
+        // the dynamic hand-out of the second tile evens out the warps that drew an expensive first one.
+        const uint64_t per_lane = std::max<uint64_t>(1, (est + 32 * warps - 1) / (32 * warps));
+        uint64_t ktiles = (per_lane + EMAX - 1) / EMAX;
+        if (per_lane > 16 && per_lane <= (uint64_t)EMAX && r > 0) ktiles = 2;
+        if (const char* ev = getenv("MGB_DEBUG_KTILES")) ktiles = std::max(1, atoi(ev));
         int emin = 4;
         if (const char* ev = getenv("MGB_DEBUG_EMIN")) emin = std::max(1, atoi(ev));
-        while (E > emin && 10 * est < fill10 * warps * 32ull * E) E >>= 1;
-        uint32_t n_big = (uint32_t)(2 * warps);
+        int E = (int)std::min<uint64_t>(EMAX, std::max<uint64_t>((uint64_t)emin, (per_lane + ktiles - 1) / ktiles));
+        uint32_t n_big = 0xffffffffu;            // all tiles have E pairs per lane (the E/4 tail tiles are not needed when balanced)
         if (const char* ev = getenv("MGB_DEBUG_E")) {   // tuning aid: comma-separated E per round
           int k = 0; const char* q = ev;
           while (k < r && (q = strchr(q, ',')) != nullptr) { q++; k++; }

@@ -20,13 +20,13 @@ REF_NEG, REF_ENDO, REF_EMPTY = 0x80000000, 0x40000000, 0xFFFFFFFF
 U32 = ctypes.c_uint32
 
 
-# "product": the kernel as shipped; "warp_inv": the build-time experiment -DMGB_WARP_INV=1 (a tile's total is inverted by the
-# lane-parallel inverse of csrc/warp.cuh instead of lane 0 alone) -- same inputs, same expected sums
-# "onewarp": -DMGB_ONEWARP_HORNER=1 (the Horner kernels of the Weierstrass curves run in one warp, csrc/onewarp.cuh)
-@pytest.fixture(scope="module", params=["product", "warp_inv", "onewarp"])
+# "product": the kernels as shipped (lane-parallel inversion of a tile's total, csrc/warp.cuh; Horner kernels of the Weierstrass
+# curves in one warp, csrc/onewarp.cuh); "lane0_inv": -DMGB_WARP_INV=0, the round-1 kernel whose lane 0 inverts alone;
+# "block_horner": -DMGB_ONEWARP_HORNER=0, the round-1 block-cooperative Horner -- same inputs, same expected sums
+@pytest.fixture(scope="module", params=["product", "lane0_inv", "block_horner"])
 def emu_k(request, tmp_path_factory):
     so = str(tmp_path_factory.mktemp("emu_k") / "emu_k.so")
-    flags = {"product": [], "warp_inv": ["-DMGB_WARP_INV=1"], "onewarp": ["-DMGB_ONEWARP_HORNER=1"]}[request.param]
+    flags = {"product": [], "lane0_inv": ["-DMGB_WARP_INV=0"], "block_horner": ["-DMGB_ONEWARP_HORNER=0"]}[request.param]
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-Wno-unknown-pragmas"] + flags +
                           ["-o", so, os.path.join(ROOT, "tests", "host_emu", "emu_kernels.cpp")])
     lib = ctypes.CDLL(so)
@@ -43,7 +43,7 @@ def only(lib, *variants):
 @pytest.mark.parametrize("cid,prm,n,e_big", [(0, BLS12_377, 12, 2), (0, BLS12_377, 12, 8), (1, PALLAS, 8, 4)],
                          ids=["bls12-377-E2", "bls12-377-E8", "pallas-E4"])
 def test_batch_add_two_rounds(emu_k, cid, prm, n, e_big):
-    only(emu_k, "product", "warp_inv")
+    only(emu_k, "product", "lane0_inv")
     p = prm.p
     R = 1 << (32 * n)
     Ri = pow(R, -1, p)
@@ -144,7 +144,7 @@ def test_batch_add_two_rounds(emu_k, cid, prm, n, e_big):
 @pytest.mark.parametrize("cid,prm,n", [(0, BLS12_377, 12), (1, PALLAS, 8)], ids=["bls12-377", "pallas"])
 def test_final_horner_kernel(emu_k, cid, prm, n):
     """k_final: sum_w 2^(c w) S_w over K window sums given as XYZZ accumulators (one of them the neutral element)."""
-    only(emu_k, "product", "onewarp")
+    only(emu_k, "product", "block_horner")
     p = prm.p
     R = 1 << (32 * n)
     Ri = pow(R, -1, p)
