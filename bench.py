@@ -38,6 +38,22 @@ SEED_POINTS = 0x6D6F6E74
 SEED_SCALARS = 0x6D6F6E74 ^ 3          # "seed xor config index" (config 4 = index 3)
 ALGO_FIELD_MULTS_PER_POINT = 108.6     # SURVEY 8d, BLS12-377 2^20 at the reference's c = 18
 MADS_PER_FIELD_MULT = 288              # 2 * 12^2 32x32->64 multiply-accumulates
+# The other BASELINE.json configs, reported as `extra` blocks beside the headline (field
+# multiplications per input point at the reference's window size, 32x32->64 MADs per multiplication = 2 * limbs^2)
+EXTRA_CONFIGS = {
+    "bls377_2p16": {"curve": "bls12-377", "logn": 16, "mults_per_point": 139.0, "mads_per_mult": 288, "seed_index": 0},
+    "ed377_2p18": {"curve": "ed-on-bls12-377", "logn": 18, "mults_per_point": 188.0, "mads_per_mult": 128, "seed_index": 1},
+    "pallas_2p18": {"curve": "pallas", "logn": 18, "mults_per_point": 142.0, "mads_per_mult": 128, "seed_index": 2},
+}
+STRONG_LOGN = 24                       # BASELINE config 5: 2^24 pairs in total, sharded over the GPUs of the run
+STRONG_MULTS_PER_POINT = 107.5
+
+
+def workload_config(curve, logn, world):
+    """`config` of BOTH arms (the driver compares them): what one step computes."""
+    return {"workload": "%s G1 MSM, 2^%d points per GPU, 4 rotating pre-generated scalar sets (a different one every step), points resident" % (curve, logn),
+            "l2": "inputs larger than L2 (point table %d MB + scalars %d MB per GPU)" % ((1 << logn) * 144 >> 20, (1 << logn) * 32 >> 20),
+            "parallelism": "points sharded x%d, one NCCL all-gather of the partial sums" % world}
 
 
 def parse_args():
@@ -50,6 +66,7 @@ def parse_args():
     ap.add_argument("--curve", default="bls12-377")
     ap.add_argument("--c", type=int, default=0, help="window bits (0 = engine default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the `configs` / `strong_2p24` blocks (the other BASELINE configs)")
     ap.add_argument("--cpu-logn", type=int, default=0,
                     help="log2 size of the CPU baseline sample (0 = the whole workload when the host has >= 8 cores, else 2^18)")
     return ap.parse_args()
@@ -172,7 +189,7 @@ def run_reference(args):
         "impl": "reference", "metric": "msm_points_per_s", "value": value, "unit": "points/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64 limbs (native restatement; the reference computes in 29-bit limbs in i64)", "data": "synthetic",
-        "config": {"workload": "%s MSM, 2^%d points per GPU, fresh scalars per step" % (args.curve, args.logn)},
+        "config": workload_config(args.curve, args.logn, args.gpus),
         "cpu_baseline": {"value": value, "unit": "points/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -190,38 +207,19 @@ def run_b200(args):
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node = --gpus"
     torch.cuda.set_device(local)
     dist = None
+    # stdout carries exactly one JSON line: NCCL prints its version banner with a plain printf when a communicator
+    # is created (torch's and the engine's own), so file descriptor 1 points at stderr until the line is printed
+    sys.stdout.flush()
+    saved_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
-        # stdout carries exactly one JSON line: NCCL prints its version banner with a plain printf when the communicator
-        # is created, so file descriptor 1 points at stderr while that happens (init + one warm-up collective)
-        sys.stdout.flush()
-        saved_fd = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-            dist.barrier()
-            torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved_fd, 1)
-            os.close(saved_fd)
-    curve = m.curves.BY_LABEL[args.curve]
-    n = 1 << args.logn
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+        torch.cuda.synchronize()
     from montgomery_b200.distributed import ShardedMsm
-    sharded = ShardedMsm(curve, local, n)
-    eng = sharded.engine
-    sharded.random_points(n, SEED_POINTS)               # rank r: seed + r -> this rank's shard of the global point set
-    nsets = 4
-    host_sets = [torch.from_numpy(inputs.random_scalars(curve.q, n, SEED_SCALARS + 1000 * rank + i)).pin_memory() for i in range(nsets)]
-    dev_sets = [h.cuda(non_blocking=False) for h in host_sets]
-    torch.cuda.synchronize()
-    opts_c = args.c or None
-
-    def step(i, e2e):
-        """one MSM over this rank's shard (+ all-gather and combine when world > 1)"""
-        k = i % nsets
-        return sharded.msm(host_sets[k] if e2e else dev_sets[k], n, on_device=not e2e, c=opts_c)
+    from tests.helpers import OracleCurve       # the oracle is the checker of `parity_ok`, never the thing timed
 
     def barrier():
         torch.cuda.synchronize()
@@ -229,43 +227,76 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(e2e, sampler=None):
-        for i in range(args.warmup):
-            step(i, e2e)
-        barrier()
-        if sampler:
-            sampler.start()
-        t0 = time.perf_counter()
-        phases = {}
-        launches = 0
-        res = None
-        for i in range(args.steps):
-            res, tm = step(args.warmup + i, e2e)
-            launches += tm["n_launches"]
-            for key in ("h2d_scalars", "decompose_slice", "sort", "accumulate", "reduce", "final_sum", "total"):
-                phases[key] = phases.get(key, 0.0) + tm[key] / args.steps
-        barrier()
-        el = time.perf_counter() - t0
-        clocks = sampler.stop() if sampler else None
-        t = torch.tensor([el], dtype=torch.float64, device="cuda")
-        if dist:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), phases, launches, res, tm, clocks
+    def gather_ints(v):
+        """exact Python ints from every rank -> list on every rank"""
+        if not dist:
+            return [v]
+        out = [None] * world
+        dist.all_gather_object(out, v)
+        return out
+
+    def measure(label, logn_local, seed_points, seed_scalars, steps, warmup, sampler=None, c=None, nsets=4):
+        """Weak-scaling-shaped run of one configuration: 2^logn_local pairs on every rank.  Returns device-resident and
+        end-to-end timings, the phase breakdown, and the parity verdict against the closed form over all shards."""
+        curve = m.curves.BY_LABEL[label]
+        n = 1 << logn_local
+        sharded = ShardedMsm(curve, local, n)
+        sharded.random_points(n, seed_points)       # rank r: seed + r -> this rank's shard of the global point set
+        nsets = min(nsets, steps + warmup)
+        np_sets = [inputs.random_scalars(curve.q, n, seed_scalars + 1000 * rank + i) for i in range(nsets)]
+        host_sets = [torch.from_numpy(a).pin_memory() for a in np_sets]
+        dev_sets = [h.cuda(non_blocking=False) for h in host_sets]
+        torch.cuda.synchronize()
+
+        def step(i, e2e):
+            k = i % nsets
+            return sharded.msm(host_sets[k] if e2e else dev_sets[k], n, on_device=not e2e, c=c)
+
+        def timed(e2e, smp=None):
+            for i in range(warmup):
+                step(i, e2e)
+            barrier()
+            if smp:
+                smp.start()
+            t0 = time.perf_counter()
+            phases, launches, res, tm = {}, 0, None, None
+            for i in range(steps):
+                res, tm = step(warmup + i, e2e)
+                launches += tm["n_launches"]
+                for key in ("h2d_scalars", "decompose_slice", "sort", "accumulate", "reduce", "final_sum", "total"):
+                    phases[key] = phases.get(key, 0.0) + tm[key] / steps
+            barrier()
+            el = time.perf_counter() - t0
+            clocks = smp.stop() if smp else None
+            t = torch.tensor([el, phases["total"]], dtype=torch.float64, device="cuda")
+            if dist:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t[0].item()), float(t[1].item()), phases, launches, res, tm, clocks
+
+        el, dev_ms_max, phases, launches, res, tm, clocks = timed(False, sampler)
+        el_e2e, _, phases_e2e, _, res_e2e, _, _ = timed(True)
+        # parity: the closed form over every rank's shard, for the scalar set of the LAST step of each timed loop
+        last = (warmup + steps - 1) % nsets
+        ks = gather_ints(inputs.dot_known_dlogs(np_sets[last], inputs.known_dlogs(seed_points + rank, n)))
+        O = OracleCurve(label)
+        expect = O.result_of(O.scale(sum(ks) % O.q, O.G))
+        parity_ok = bool(res == expect and res_e2e == expect)
+        out = {"curve": curve, "n": n, "el": el, "el_e2e": el_e2e, "dev_ms_max": dev_ms_max, "phases": phases, "phases_e2e": phases_e2e,
+               "launches": launches, "res": res, "tm": tm, "clocks": clocks, "parity_ok": parity_ok, "sharded": sharded,
+               "host_sets": host_sets}
+        return out
 
     sampler = ClockSampler(local) if rank == 0 else None
-    el, phases, launches, res, tm, clocks = timed(False, sampler)
-    el_e2e, phases_e2e, _, res_e2e, _, _ = timed(True)
-    ms_step = el / args.steps * 1e3
+    head = measure(args.curve, args.logn, SEED_POINTS, SEED_SCALARS, args.steps, args.warmup, sampler, c=args.c or None)
+    curve, n, phases, tm, sharded = head["curve"], head["n"], head["phases"], head["tm"], head["sharded"]
+    eng = sharded.engine
+    parity_ok = head["parity_ok"]
+    ms_step = head["el"] / args.steps * 1e3
     total_points = n * world
-    value = total_points / (el / args.steps)
-    e2e_value = total_points / (el_e2e / args.steps)
+    value = total_points / (head["el"] / args.steps)
+    e2e_value = total_points / (head["el_e2e"] / args.steps)
 
-    if rank != 0:
-        if dist:
-            dist.destroy_process_group()
-        return
-
-    # ---- roofline of the path: integer-multiply pipe.  Peak measured live.
+    # ---- roofline denominator: the integer-multiply pipe, measured live (BASELINE.md section 2)
     lib = _native.lib()
     ops = ctypes.c_double()
     msb = ctypes.c_float()
@@ -273,19 +304,79 @@ def run_b200(args):
     peak_mads = ops.value
     lib.mgb_microbench(local, 0, 2, 1024, 2000, ctypes.byref(ops), ctypes.byref(msb))    # plain IMAD (mad.lo.u32) issue rate
     peak_imad_lo = ops.value
+    lib.mgb_microbench(local, 6, 4, 256, 2000, ctypes.byref(ops), ctypes.byref(msb))     # Fp377 Montgomery products, 8 warps per scheduler
+    peak_fp377_mults = ops.value
+
+    # ---- the other BASELINE configs (single-GPU sizes: measured at N = 1 only) and config 5 (2^24 in total, every N)
+    extra_steps, extra_warm = max(3, min(args.steps, 10)), 3
+    configs = {}
+    cpu_host_threads = os.cpu_count() or 1
+    if world == 1 and args.logn == LOGN_DEFAULT and args.curve == "bls12-377" and not args.no_extras:
+        sharded.close()
+        for name, cfg in EXTRA_CONFIGS.items():
+            r = measure(cfg["curve"], cfg["logn"], SEED_POINTS ^ (cfg["seed_index"] + 1), 0x6D6F6E74 ^ cfg["seed_index"], extra_steps, extra_warm)
+            nn = r["n"]
+            dev_ms = r["phases"]["total"]
+            blk = {"workload": "%s MSM, 2^%d points, 1 GPU" % (cfg["curve"], cfg["logn"]), "ms_device": dev_ms,
+                   "ms_per_step": r["el"] / extra_steps * 1e3, "points_per_s": nn / (r["el"] / extra_steps),
+                   "e2e_ms_per_step": r["el_e2e"] / extra_steps * 1e3, "e2e_points_per_s": nn / (r["el_e2e"] / extra_steps),
+                   "roofline_frac": cfg["mults_per_point"] * cfg["mads_per_mult"] * nn / (dev_ms * 1e-3) / peak_mads,
+                   "window_bits": r["tm"]["c"], "windows": r["tm"]["K"], "tree_rounds": r["tm"]["rounds"], "kernels_per_msm": r["tm"]["n_launches"],
+                   "phases_ms": r["phases"], "parity_ok": r["parity_ok"]}
+            if not args.no_cpu_baseline:
+                pts, _ = r["sharded"].engine.get_points(0, nn)
+                cres, cms = cpu_reference_msm(cfg["curve"], pts, r["host_sets"][0].numpy(), nn, cpu_host_threads)
+                gres, _ = r["sharded"].engine.msm(r["host_sets"][0].numpy(), n=nn)
+                blk["cpu_port_ms"] = cms
+                blk["cpu_port_cores"] = cpu_host_threads
+                blk["cpu_port_agrees_with_gpu"] = bool(cres == gres)
+            r["sharded"].close()
+            configs[name] = blk
+        head_engine_closed = True
+    else:
+        head_engine_closed = False
+    strong = None
+    if args.logn == LOGN_DEFAULT and args.curve == "bls12-377" and not args.no_extras and STRONG_LOGN - (world.bit_length() - 1) >= 10 and (world & (world - 1)) == 0:
+        if not head_engine_closed:
+            sharded.close()
+            head_engine_closed = True
+        ln = STRONG_LOGN - (world.bit_length() - 1)
+        ssteps = max(2, min(args.steps, 5))
+        r = measure("bls12-377", ln, SEED_POINTS ^ 0x5A5A, 0x6D6F6E74 ^ 4, ssteps, 2, nsets=1)
+        tot = (1 << ln) * world
+        strong = {"workload": "bls12-377 G1 MSM, 2^%d points in total = 2^%d per GPU on %d GPU(s) (BASELINE config 5)" % (STRONG_LOGN, ln, world),
+                  "scaling": "strong", "n_gpus": world, "ms_per_step": r["el"] / ssteps * 1e3, "ms_device_max": r["dev_ms_max"],
+                  "points_per_s": tot / (r["el"] / ssteps), "e2e_ms_per_step": r["el_e2e"] / ssteps * 1e3, "e2e_points_per_s": tot / (r["el_e2e"] / ssteps),
+                  "roofline_frac": STRONG_MULTS_PER_POINT * MADS_PER_FIELD_MULT * (1 << ln) / (r["dev_ms_max"] * 1e-3) / peak_mads,
+                  "window_bits": r["tm"]["c"], "windows": r["tm"]["K"], "tree_rounds": r["tm"]["rounds"], "steps": ssteps, "parity_ok": r["parity_ok"]}
+        r["sharded"].close()
+        parity_ok = parity_ok and r["parity_ok"]
+    parity_ok = parity_ok and all(b["parity_ok"] for b in configs.values())
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+
     algo_mads = ALGO_FIELD_MULTS_PER_POINT * MADS_PER_FIELD_MULT * n        # per GPU per step (reference op counts)
     acc_ms = phases["accumulate"]
     traffic = ncu_traffic() if (args.logn == LOGN_DEFAULT and args.curve == "bls12-377") else None
     achieved = algo_mads / (phases["total"] * 1e-3)
+    executed_mults_per_s = 6.0 * tm["n_pairs"] / (acc_ms * 1e-3)
     roofline = {
         "bound": "imad", "achieved": achieved / 1e12, "peak": peak_mads / 1e12, "unit": "T 32x32->64 MAD/s",
         "frac": achieved / peak_mads, "traffic": traffic and traffic.get("bytes_per_launch"),
         "traffic_note": traffic and traffic.get("note"),
-        "note": "integer-multiply roofline of BASELINE.md: algorithmic MADs (108.6 field mults/point x 288) / device time of the whole MSM "
-                "(CUDA events on the engine's stream) / measured rate of carry-chained IMAD.WIDE.U32.X (one full 32x32+64->64 MAD per lane) on this GPU; "
-                "plain IMAD (mad.lo) issues at %.2f T/s, i.e. a full MAD costs two IMAD slots, as SURVEY 8d assumed" % (peak_imad_lo / 1e12),
+        "note": "integer-multiply roofline of BASELINE.md: ALGORITHMIC MADs (the reference's operation count at its own window size: 108.6 field "
+                "mults/point x 288) / device time of the whole MSM (CUDA events on the engine's stream) / measured rate of carry-chained "
+                "IMAD.WIDE.U32.X (one full 32x32+64->64 MAD per lane) on this GPU; plain IMAD (mad.lo) issues at %.2f T/s, i.e. a full MAD costs "
+                "two IMAD slots, as SURVEY 8d assumed.  `dominant_kernel` reports the work the engine actually EXECUTES instead" % (peak_imad_lo / 1e12),
         "dominant_kernel": {"name": "k_batch_add", "phase_ms": acc_ms, "share_of_step": acc_ms / phases["total"],
-                            "pairs_per_step": int(tm["n_pairs"]), "field_mults_per_s": 6.0 * tm["n_pairs"] / (acc_ms * 1e-3)},
+                            "pairs_per_step": int(tm["n_pairs"]), "executed_field_mults_per_s": executed_mults_per_s,
+                            "fp377_mult_peak_per_s": peak_fp377_mults, "frac_of_mult_peak": executed_mults_per_s / peak_fp377_mults,
+                            "executed_mads_frac_of_imad_peak": executed_mults_per_s * MADS_PER_FIELD_MULT / peak_mads,
+                            "note": "6 field multiplications per affine addition executed by the tree rounds (exact pair count from the engine) against the "
+                                    "live-measured throughput of the same Montgomery multiplication with 8 warps per scheduler"},
     }
     # HBM side of the path (north star: "HBM GB/s for the sort and gather phases").  The sort no longer copies points:
     # per sorted entry the scatter reads digit + rank (8 B) and the bucket's offset + count (8 B, L2-resident) and writes
@@ -299,29 +390,42 @@ def run_b200(args):
         "metric": "msm_points_per_s", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32 limbs (12 x 32-bit Montgomery)", "data": "synthetic",
-        "config": {"workload": "%s G1 MSM, 2^%d points per GPU, fresh scalars per step, points resident" % (args.curve, args.logn),
-                   "window_bits": tm["c"], "windows": tm["K"], "l2": "inputs larger than L2 (point table %d MB + scalars %d MB per GPU)" % (
-                       n * 144 >> 20, n * 32 >> 20), "parallelism": "points sharded x%d, NCCL all-gather of partial sums" % world},
-        "msm_ms": ms_step, "phases_ms": phases, "result_x": hex(res["x"]),
-        "e2e": {"value": e2e_value, "unit": "points/s", "ms_per_step": el_e2e / args.steps * 1e3,
-                "h2d_bytes_per_step": n * 32 * world, "d2h_bytes_per_step": (2 * curve.coord_bytes + 4) * world, "phases_ms": phases_e2e},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "hbm_phases": hbm,
+        "config": workload_config(args.curve, args.logn, world),
+        "engine": {"window_bits": tm["c"], "windows": tm["K"], "tree_rounds": tm["rounds"], "kernels_per_msm": tm["n_launches"]},
+        "parity_ok": parity_ok, "parity": "closed form [(sum s_i a_i) mod q] G over every rank's shard (known-dlog points), checked on the "
+                                          "results of the last device-timed and the last end-to-end step of every configuration in this line",
+        "msm_ms": ms_step, "msm_ms_device": phases["total"], "phases_ms": phases, "result_x": hex(head["res"]["x"]),
+        "e2e": {"value": e2e_value, "unit": "points/s", "ms_per_step": head["el_e2e"] / args.steps * 1e3,
+                "h2d_bytes_per_step": n * 32 * world, "d2h_bytes_per_step": (2 * curve.coord_bytes + 4) * world, "phases_ms": head["phases_e2e"]},
+        "gpu_launches": head["launches"], "clocks": head["clocks"], "roofline": roofline, "hbm_phases": hbm,
     }
+    if configs:
+        line["configs"] = configs
+    if strong:
+        line["strong_2p24"] = strong
     if world == 1 and not args.no_cpu_baseline:
         cl = cpu_sample_logn(args)
         ncpu = 1 << cl
-        pts, _ = eng.get_points(0, ncpu)
-        threads = os.cpu_count() or 1
-        sc = host_sets[0].numpy()[:ncpu]
-        cres, cms = cpu_reference_msm(args.curve, pts, sc, ncpu, threads)
-        gres, _ = eng.msm(sc, n=ncpu)
-        line["cpu_baseline"] = {"value": ncpu / (cms * 1e-3), "unit": "points/s", "cores": threads, "kind": "port",
+        ceng = m.MsmEngine(curve, local, ncpu) if head_engine_closed else eng
+        if head_engine_closed:
+            ceng.random_points(ncpu, SEED_POINTS)
+        pts, _ = ceng.get_points(0, ncpu)
+        sc = head["host_sets"][0].numpy()[:ncpu]
+        cres, cms = cpu_reference_msm(args.curve, pts, sc, ncpu, cpu_host_threads)
+        gres, _ = ceng.msm(sc, n=ncpu)
+        line["cpu_baseline"] = {"value": ncpu / (cms * 1e-3), "unit": "points/s", "cores": cpu_host_threads, "kind": "port",
                                 "sample": ("one MSM of the whole 2^%d-point workload, %.0f ms" if cl == args.logn else
                                            "one MSM of the first 2^%d points of the workload, %.0f ms") % (cl, cms),
                                 "agrees_with_gpu": cres == gres}
+        ceng.close()
+    sys.stdout.flush()
+    os.dup2(saved_fd, 1)
+    os.close(saved_fd)
     print(json.dumps(line))
+    sys.stdout.flush()
     if dist:
         dist.destroy_process_group()
+    assert parity_ok, "parity check failed: the engine's result differs from the closed form"
 
 
 def main():

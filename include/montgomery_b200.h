@@ -42,7 +42,9 @@ enum mgb_error {
   MGB_E_CUDA = -2,      /* a CUDA runtime call failed; message has the CUDA error string             */
   MGB_E_NOMEM = -3,     /* device memory exhausted (the reference's "memory overflow" error,
                            src/wasm/memory-helpers.ts:225-236)                                         */
-  MGB_E_STATE = -4      /* msm called before points were set                                          */
+  MGB_E_STATE = -4,     /* msm called before points were set / sharded msm without a communicator     */
+  MGB_E_COMM = -5       /* NCCL: library not found, communicator set-up or collective failed, or an
+                           asynchronous error reported by ncclCommGetAsyncError                        */
 };
 
 /* Per-call options; mirrors `{c?, useSafeAdditions?}` of msm-batched-affine.ts:74-77 and
@@ -88,7 +90,8 @@ int mgb_set_points(mgb_ctx* ctx, const uint8_t* xy_le, const uint8_t* is_zero, s
 
 /* Replaces `Parallel.randomPointsFast(n)` (src/curve-random.ts:24-92): fills the context with n
  * points a_i*G, a_i a seeded 64-bit value (splitmix64 of seed and i), built on the device from
- * window tables of the generator.  Deterministic; used for benchmarks and closed-form checks. */
+ * a 64-step double-and-add of the generator, one thread per point.  Deterministic; used for benchmarks
+ * and closed-form checks. */
 int mgb_random_points(mgb_ctx* ctx, uint64_t seed, size_t n);
 
 /* Reads back points [first, first+n) as canonical x||y LE bytes (`Affine.toBigint`,
@@ -103,19 +106,62 @@ int mgb_get_points(mgb_ctx* ctx, size_t first, size_t n, uint8_t* xy_le, uint8_t
 int mgb_msm(mgb_ctx* ctx, const uint8_t* scalars_le32, size_t n, const mgb_opts* opts,
             uint8_t* out_xy_le, int* out_is_zero, mgb_timing* timing);
 
-/* Same with scalars already in device memory (device pointer), for kernel-only timing. */
+/* Same with scalars already in device memory (device pointer), for kernel-only timing.
+ * Contract for caller-owned device scalars (here and in mgb_msm_partial / mgb_msm_sharded with
+ * scalars_on_device): the pointer must be 16-byte aligned (128-bit loads) and the data must be
+ * complete before the call -- the engine reads it on its own non-blocking stream, which is not
+ * ordered after the stream that produced it, so synchronise the producer first. */
 int mgb_msm_device(mgb_ctx* ctx, const void* d_scalars_le32, size_t n, const mgb_opts* opts,
                    uint8_t* out_xy_le, int* out_is_zero, mgb_timing* timing);
 
-/* Multi-GPU path (replaces the SPMD thread split of src/threads/threads.ts:354-359): each rank
- * runs the MSM on its shard and leaves the partial sum, un-normalised, in a caller-provided DEVICE
- * buffer of mgb_partial_bytes() bytes (to be all-gathered over NCCL by the host layer);
- * mgb_combine_partials adds `count` gathered partials (device buffer) and normalises. */
+/* Multi-GPU building blocks for a host layer that runs the collective itself: each rank runs the
+ * MSM on its shard and leaves the partial sum, un-normalised, in a caller-provided DEVICE buffer of
+ * mgb_partial_bytes() bytes; mgb_combine_partials adds `count` gathered partials (device buffer)
+ * and normalises.  n = 0 writes the neutral element.  (mgb_msm_sharded below does all of it inside
+ * the library and is what the bench uses.) */
 size_t mgb_partial_bytes(const mgb_ctx* ctx);
 int mgb_msm_partial(mgb_ctx* ctx, const void* scalars, int scalars_on_device, size_t n,
                     const mgb_opts* opts, void* d_partial_out, mgb_timing* timing);
 int mgb_combine_partials(mgb_ctx* ctx, const void* d_partials, int count,
                          uint8_t* out_xy_le, int* out_is_zero);
+
+/* Sharded MSM with the collective inside the library ("ctx owns ... the NCCL
+ * communicator").  Replaces the SPMD split of src/threads/threads.ts:354-359 plus the sum of the
+ * per-thread partial results on the main thread (src/msm-batched-affine.ts:311-320).
+ *
+ * One process per GPU: rank 0 calls mgb_comm_unique_id and hands the MGB_COMM_ID_BYTES bytes to the other
+ * ranks by any host channel (MPI, a TCP store, torch.distributed's broadcast, a worker message);
+ * every rank then calls mgb_comm_init(ctx, id, rank, world) on its own context (collective: returns
+ * when all ranks have joined).  mgb_msm_sharded runs the MSM of the rank's shard (n_local pairs:
+ * the rank's scalars against the first n_local points of ITS context; 0 is allowed and contributes
+ * the neutral element), then -- on the engine's stream, with no host round trip in between -- ONE
+ * ncclAllGather of the un-normalised partial accumulators and one kernel that adds them and
+ * normalises.  Every rank receives the same canonical result.  NCCL is bound at run time
+ * (dlopen of libnccl.so.2, or the path in MGB_NCCL_LIB): single-GPU hosts do not need it.
+ * A context with no communicator (world 1) computes the plain MSM. */
+#define MGB_COMM_ID_BYTES 128
+int mgb_comm_unique_id(uint8_t* id_out /* MGB_COMM_ID_BYTES */);
+int mgb_comm_init(mgb_ctx* ctx, const uint8_t* id /* MGB_COMM_ID_BYTES */, int rank, int world);
+int mgb_comm_info(const mgb_ctx* ctx, int* rank, int* world, int* nccl_version);   /* any out pointer may be NULL */
+int mgb_msm_sharded(mgb_ctx* ctx, const void* scalars, int scalars_on_device, size_t n_local,
+                    const mgb_opts* opts, uint8_t* out_xy_le, int* out_is_zero, mgb_timing* timing);
+
+/* One host process driving several GPUs (the shape a Node / TypeScript host needs: it cannot reach
+ * an MPI-style launcher).  mgb_multi_create builds one context per listed device and the
+ * communicators (ncclCommInitAll); the point set is split contiguously over the devices by the
+ * reference's `range()` rule (src/threads/threads.ts:354-359); mgb_multi_msm pairs the first n
+ * scalars with the first n points, each device working on the part of its shard below n (one
+ * host thread per device), and returns the canonical sum.  mgb_multi_random_points gives shard g
+ * the known-dlog points of seed + g. */
+typedef struct mgb_multi mgb_multi;
+int mgb_multi_create(mgb_multi** out, int curve, const int* device_ids, int n_devices, size_t max_points_per_device);
+int mgb_multi_set_points(mgb_multi* m, const uint8_t* xy_le, const uint8_t* is_zero, size_t n);
+int mgb_multi_random_points(mgb_multi* m, uint64_t seed, size_t n);
+int mgb_multi_get_points(mgb_multi* m, size_t first, size_t n, uint8_t* xy_le, uint8_t* is_zero);
+int mgb_multi_msm(mgb_multi* m, const uint8_t* scalars_le32, size_t n, const mgb_opts* opts,
+                  uint8_t* out_xy_le, int* out_is_zero, mgb_timing* timing /* device 0's phases */);
+const char* mgb_multi_last_error(const mgb_multi* m);
+void mgb_multi_destroy(mgb_multi* m);
 
 /* Test hooks for the field layer (the analogue of the Wasm exports checked by src/field.test.ts):
  * applies op elementwise on the device to n elements given as canonical LE bytes in/out.
@@ -133,7 +179,8 @@ int mgb_field_op(int device, int field, int op, const uint8_t* a, const uint8_t*
  * of Fp377 division-step inversions on all lanes / on lane 0 of each warp (threads <= 128), 10/11 = a
  * dependent chain of Fp377 products on a warp running alone: lane 0 with the per-thread routine / all
  * lanes with the warp-cooperative one (ms / (2 iters) = latency of one product), 12 = like 9 with the
- * lane-parallel inverse (one inversion per warp, all lanes working).  All
+ * lane-parallel inverse (one inversion per warp, all lanes working), 13 = Fp377 products two per call, their
+ * instruction streams free to interleave (instruction-level parallelism for a warp that runs alone).  All
  * multiplicands change every iteration (a loop-invariant product would be hoisted by ptxas).
  * Returns operations per second (lane operations for modes 0-3, field multiplications for 4-7) in
  * *ops_per_s and the kernel time in *ms. */

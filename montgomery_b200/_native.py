@@ -33,7 +33,12 @@ EXPORTS = [
     "mgb_create", "mgb_set_points", "mgb_random_points", "mgb_get_points", "mgb_msm", "mgb_msm_device",
     "mgb_partial_bytes", "mgb_msm_partial", "mgb_combine_partials", "mgb_field_op", "mgb_microbench",
     "mgb_last_error", "mgb_destroy",
+    "mgb_comm_unique_id", "mgb_comm_init", "mgb_comm_info", "mgb_msm_sharded",
+    "mgb_multi_create", "mgb_multi_set_points", "mgb_multi_random_points", "mgb_multi_get_points", "mgb_multi_msm",
+    "mgb_multi_last_error", "mgb_multi_destroy",
 ]
+COMM_ID_BYTES = 128
+E_INVALID, E_CUDA, E_NOMEM, E_STATE, E_COMM = -1, -2, -3, -4, -5
 
 
 def load():
@@ -59,8 +64,22 @@ def load():
     lib.mgb_last_error.restype = ctypes.c_char_p
     lib.mgb_destroy.argtypes = [vp]
     lib.mgb_destroy.restype = None
+    pi = ctypes.POINTER(ci)
+    lib.mgb_comm_unique_id.argtypes = [vp]
+    lib.mgb_comm_init.argtypes = [vp, vp, ci, ci]
+    lib.mgb_comm_info.argtypes = [vp, pi, pi, pi]
+    lib.mgb_msm_sharded.argtypes = [vp, vp, ci, sz, ctypes.POINTER(MgbOpts), vp, pi, ctypes.POINTER(MgbTiming)]
+    lib.mgb_multi_create.argtypes = [ctypes.POINTER(vp), ci, pi, ci, sz]
+    lib.mgb_multi_set_points.argtypes = [vp, vp, vp, sz]
+    lib.mgb_multi_random_points.argtypes = [vp, ctypes.c_uint64, sz]
+    lib.mgb_multi_get_points.argtypes = [vp, sz, sz, vp, vp]
+    lib.mgb_multi_msm.argtypes = [vp, vp, sz, ctypes.POINTER(MgbOpts), vp, pi, ctypes.POINTER(MgbTiming)]
+    lib.mgb_multi_last_error.argtypes = [vp]
+    lib.mgb_multi_last_error.restype = ctypes.c_char_p
+    lib.mgb_multi_destroy.argtypes = [vp]
+    lib.mgb_multi_destroy.restype = None
     for name in EXPORTS:
-        if name not in ("mgb_partial_bytes", "mgb_last_error", "mgb_destroy"):
+        if name not in ("mgb_partial_bytes", "mgb_last_error", "mgb_destroy", "mgb_multi_last_error", "mgb_multi_destroy"):
             getattr(lib, name).restype = ci
     return lib
 

@@ -28,6 +28,16 @@ def _ptr(a: np.ndarray):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
+def comm_unique_id() -> bytes:
+    """mgb_comm_unique_id: the 128-byte NCCL id rank 0 draws and hands to the other ranks (needs no GPU)."""
+    lib = _native.lib()
+    buf = (ctypes.c_uint8 * _native.COMM_ID_BYTES)()
+    rc = lib.mgb_comm_unique_id(buf)
+    if rc != 0:
+        raise MsmError(rc, lib.mgb_last_error(None).decode())
+    return bytes(buf)
+
+
 class MsmEngine:
     """One curve on one GPU: owns the device copy of the points and all scratch memory."""
 
@@ -137,6 +147,91 @@ class MsmEngine:
     def partial_bytes(self):
         return int(self.lib.mgb_partial_bytes(self._h))
 
+    # ---- sharded msm: the context owns the NCCL communicator (mgb_comm_init) and runs the collective itself
+    def comm_unique_id(self) -> bytes:
+        return comm_unique_id()
+
+    def comm_init(self, comm_id: bytes, rank: int, world: int):
+        assert len(comm_id) == _native.COMM_ID_BYTES
+        buf = (ctypes.c_uint8 * _native.COMM_ID_BYTES).from_buffer_copy(comm_id)
+        self._check(self.lib.mgb_comm_init(self._h, buf, rank, world))
+
+    def comm_info(self):
+        r, w, v = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        self._check(self.lib.mgb_comm_info(self._h, ctypes.byref(r), ctypes.byref(w), ctypes.byref(v)))
+        return {"rank": r.value, "world": w.value, "nccl_version": v.value}
+
+    def msm_sharded(self, scalars_ptr, on_device, n_local, c=None):
+        """This rank's shard of a sharded MSM; every rank gets the full result (mgb_msm_sharded)."""
+        out = np.zeros(self.curve.point_bytes, dtype=np.uint8)
+        is_zero = ctypes.c_int(0)
+        tm = _native.MgbTiming()
+        opts = self._opts(c, False)
+        self._check(self.lib.mgb_msm_sharded(self._h, ctypes.c_void_p(scalars_ptr), int(on_device), n_local, ctypes.byref(opts),
+                                             _ptr(out), ctypes.byref(is_zero), ctypes.byref(tm)))
+        cb = self.curve.coord_bytes
+        return {"x": int.from_bytes(out[:cb].tobytes(), "little"), "y": int.from_bytes(out[cb:].tobytes(), "little"),
+                "isZero": bool(is_zero.value)}, tm.as_dict()
+
+
+class MultiGpuMsm:
+    """One host process driving several GPUs (mgb_multi_*): the shape a Node host uses (bindings/node)."""
+
+    def __init__(self, curve: curves.CurveInfo, device_ids, max_points_per_device: int):
+        self.curve = curve
+        self.lib = _native.lib()
+        self._h = ctypes.c_void_p()
+        ids = (ctypes.c_int * len(device_ids))(*device_ids)
+        rc = self.lib.mgb_multi_create(ctypes.byref(self._h), curve.curve_id, ids, len(device_ids), max_points_per_device)
+        if rc != 0:
+            raise MsmError(rc, self.lib.mgb_multi_last_error(None).decode())
+
+    def _check(self, rc):
+        if rc != 0:
+            raise MsmError(rc, self.lib.mgb_multi_last_error(self._h).decode())
+
+    def set_points(self, xy_bytes, is_zero=None):
+        xy = np.ascontiguousarray(np.frombuffer(xy_bytes, dtype=np.uint8) if not isinstance(xy_bytes, np.ndarray) else xy_bytes.reshape(-1))
+        n = xy.size // self.curve.point_bytes
+        z = None if is_zero is None else np.ascontiguousarray(np.asarray(is_zero, dtype=np.uint8))
+        self._check(self.lib.mgb_multi_set_points(self._h, _ptr(xy), None if z is None else _ptr(z), n))
+        return n
+
+    def random_points(self, n, seed):
+        self._check(self.lib.mgb_multi_random_points(self._h, seed, n))
+
+    def get_points(self, first, n):
+        xy = np.empty(n * self.curve.point_bytes, dtype=np.uint8)
+        z = np.empty(n, dtype=np.uint8)
+        self._check(self.lib.mgb_multi_get_points(self._h, first, n, _ptr(xy), _ptr(z)))
+        return xy.reshape(n, self.curve.point_bytes), z
+
+    def msm(self, scalars, n=None, c=None):
+        sc = np.ascontiguousarray((scalars if isinstance(scalars, np.ndarray) else np.frombuffer(scalars, dtype=np.uint8)).reshape(-1))
+        if n is None:
+            n = sc.size // 32
+        if n * 32 > sc.size:
+            raise ValueError("msm: n = %d exceeds the %d scalars in the buffer" % (n, sc.size // 32))
+        out = np.zeros(self.curve.point_bytes, dtype=np.uint8)
+        is_zero = ctypes.c_int(0)
+        tm = _native.MgbTiming()
+        opts = _native.MgbOpts(int(c or 0), 0, 0, 0)
+        self._check(self.lib.mgb_multi_msm(self._h, _ptr(sc), n, ctypes.byref(opts), _ptr(out), ctypes.byref(is_zero), ctypes.byref(tm)))
+        cb = self.curve.coord_bytes
+        return {"x": int.from_bytes(out[:cb].tobytes(), "little"), "y": int.from_bytes(out[cb:].tobytes(), "little"),
+                "isZero": bool(is_zero.value)}, tm.as_dict()
+
+    def close(self):
+        if self._h:
+            self.lib.mgb_multi_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
 
 def _log_from_timing(tm):
     """Same shape as the reference's `log` (list of printable rows, src/msm-common.ts:176-213)."""
@@ -183,6 +278,7 @@ class _Parallel:
 
     def msm(self, scalars, points, N, verboseTiming=False, options=None):
         options = options or {}
+        points.engine.curve          # raises MsmError(MGB_E_STATE) on a closed handle
         if N > points.n:
             raise ValueError("msm: N = %d exceeds the %d points of the set" % (N, points.n))
         res, tm = points.engine.msm(scalars[:N] if isinstance(scalars, np.ndarray) else scalars, n=N, c=options.get("c"),
@@ -197,6 +293,7 @@ class _Parallel:
         """msm-basic over projective coordinates, no GLV (src/parallel.ts:69-87); Weierstrass curves only."""
         assert self._m.curve.kind == "weierstrass"
         options = options or {}
+        points.engine.curve          # raises MsmError(MGB_E_STATE) on a closed handle
         if N > points.n:
             raise ValueError("msmProjective: N = %d exceeds the %d points of the set" % (N, points.n))
         res, tm = points.engine.msm(scalars[:N] if isinstance(scalars, np.ndarray) else scalars, n=N, c=options.get("c"), projective=True)
@@ -220,7 +317,6 @@ class PointSet:
 
     def close(self):
         """Release the points: the module may give this set's engine (and its table) to the next set."""
-        self.n = 0
         self.engine = _ReleasedEngine()
 
     def toBigints(self, first=0, n=None):

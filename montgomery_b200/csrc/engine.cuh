@@ -605,11 +605,15 @@ __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ 
   typedef Fe<FP> fe;
   constexpr int N = CV::N;
   constexpr int CW = N / 4;             // 16-byte chunks per coordinate
-  // staging slots, in chunks: A.x | B.x (pairs of even e; the forward pass uses these too) | A.y | B.y | prefix
-  // product | 3 pair entries | A.x | B.x (pairs of odd e in the backward pass)
+  // staging slots, in chunks: A.x | B.x | A.y | B.y | prefix product | 3 pair entries: 18 chunks = 36 KB per block for a
+  // 12-limb field, so that FIVE blocks are resident per SM (20 warps; registers capped at 96).  The multiplier pipe is
+  // at 63 / 90 / 97 % of its rate with 1 / 2 / 3 warps of a scheduler inside a product at the same time (measured,
+  // profiles/r02_microbench_mul_vs_warps.jsonl) and a warp spends two thirds of its time there, so a fifth warp per
+  // scheduler is worth more than the second x buffer the round-1 kernel kept (48 KB, 4 blocks).
   constexpr int ST_A = 0, ST_PRE = 4 * CW, ST_ENT = 5 * CW;
-  constexpr int ST_X1 = ST_ENT + 3, ST_TOTAL = ST_X1 + 2 * CW;
+  constexpr int ST_TOTAL = ST_ENT + 3;
   __shared__ uint4 stage[ST_TOTAL][128];   // [chunk][thread]: conflict-free 16-byte accesses
+  static_assert(sizeof(uint4) * ST_TOTAL * 128 <= 48 * 1024, "static shared memory limit");
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const uint32_t q0 = FIRST ? offs[b_begin] >> 1 : 0u;
@@ -756,19 +760,19 @@ __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ 
     }
     fe inv = shfl_fe<FP>(pfx, 31);                  // -> 1 / (this warp's total)
     // Backward pass that keeps its operands in SHARED MEMORY instead of registers.  Field::mul is an out-of-line
-    // call that needs ~70 registers of its own; with 128 per thread the caller can keep ~55 values across a call,
-    // and the one-piece version below holds both points, the running inverse and the inverted denominator (72) --
-    // it spills, and every iteration waits for the reloads (ncu: 5 % of the samples of round 0).  Here only the
-    // running inverse and one intermediate live across a call; coordinates are re-read from the staging slots
-    // when a formula needs them:
-    //   * x halves of pair e sit in one of TWO slot pairs (parity of e), so the prefetch of pair e - 1, issued at
-    //     the top of iteration e (group X, with the prefix product and entry e - 2), does not overwrite them;
-    //   * y halves are needed only after two products: they are prefetched at the END of the previous iteration
-    //     (group Y) into a single slot pair.
-    // An iteration waits for "all but the most recent group" twice: X_e at the top (Y_e may still be in flight),
-    // Y_e before the slope (X_(e-1) may still be in flight).
+    // call that needs ~70 registers of its own; the caller can keep few values across a call, and a version that
+    // holds both points, the running inverse and the inverted denominator (72) spills, with every iteration waiting
+    // for the reloads (ncu, round 1: 5 % of the samples of round 0).  Here only the running inverse and one
+    // intermediate live across a call; coordinates are re-read from the staging slots when a formula needs them.
+    // Prefetch of pair e - 1 (issued during iteration e, two groups):
+    //   * X: x halves, prefix product (and, riding in the same group, entry e - 2): issued right after the last read
+    //     of pair e's x halves -- just before the final product m (x1 - x3) -- so one product (~2.4 K issue cycles,
+    //     several times that under contention) covers the trip to L2 / HBM;
+    //   * Y: y halves, issued after the last read of pair e's y halves at the end of the iteration.
+    // Iteration e waits for "all but the most recent group" at the top (X_e; Y_e may still be in flight) and for all
+    // groups before the slope.
     constexpr int ST_AY = ST_A + 2 * CW, ST_BY = ST_A + 3 * CW;
-    auto xslot = [&](int e) -> int { return (e & 1) ? ST_X1 : ST_A; };      // A.x at xslot, B.x at xslot + CW
+    auto xslot = [&](int) -> int { return ST_A; };                           // A.x at xslot, B.x at xslot + CW
     auto issue_xpart = [&](int e) {   // x of both operands and the prefix product of pair e
       const uint4 en = *ent_slot(e);
       if (en.x == REF_EMPTY) return;
@@ -816,9 +820,7 @@ __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ 
       const bool add = is_add(cur);
       const int xs = xslot(e);
       const fe pre = stage_fe(ST_PRE);
-      if (e > 0) issue_xpart(e - 1);
-      fetch_ent(e - 2);
-      cp_async_commit();                         // group X_(e-1)
+      fetch_ent(e - 2);                          // rides in group X_(e-1), committed below
       const fe inv_den = F::mul(u, pre);
       PairEnt out = {0u, 0u};
       if (valid) {
@@ -836,7 +838,7 @@ __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ 
         if (!G::prepare_x(stage_fe(xs), stage_fe(xs + CW), d)) {
           const typename CV::vpoint A = full_a(cur), B = full_b(cur);
           kind = G::add_prepare(A, B, d);
-          cp_async_wait_but_one();               // Y_e has landed: the slots can be overwritten
+          cp_async_wait_all();                   // Y_e has landed: the slots can be overwritten
           _Pragma("unroll") for (int c = 0; c < CW; c++) {
             stage[xs + c][tid] = make_uint4(A.x.v[4 * c], A.x.v[4 * c + 1], A.x.v[4 * c + 2], A.x.v[4 * c + 3]);
             stage[xs + CW + c][tid] = make_uint4(B.x.v[4 * c], B.x.v[4 * c + 1], B.x.v[4 * c + 2], B.x.v[4 * c + 3]);
@@ -847,10 +849,15 @@ __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ 
         }
         u = F::mul(u, d);
       }
-      cp_async_wait_but_one();                   // Y_e
+      cp_async_wait_all();                       // Y_e (and entry e - 2)
       auto stage_y = [&](int c0, uint32_t ref) -> fe {
         const fe y = stage_fe(c0);
         return (FIRST && !y_ready && (ref & REF_NEG)) ? F::neg(y) : y;
+      };
+      // the x halves of pair e are read for the last time just before the final product: their slots then take pair e - 1
+      auto prefetch_x = [&]() {
+        if (e > 0) issue_xpart(e - 1);
+        cp_async_commit();                       // group X_(e-1)
       };
       if (valid) {
         typename CV::vpoint R;
@@ -862,15 +869,21 @@ __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ 
           R.x = F::sqr(m);
           const fe ax = stage_fe(xs);
           R.x = F::sub(F::sub(R.x, ax), stage_fe(xs + CW));      // doubling: B = A, so this is m^2 - 2x
-          R.y = F::mul(m, F::sub(ax, R.x));
+          const fe t = F::sub(ax, R.x);
+          prefetch_x();
+          R.y = F::mul(m, t);
           R.y = F::sub(R.y, stage_y(ST_AY, cur.x));
         } else if (kind == 4) {
           R = G::affine_inf();
+          prefetch_x();
         } else {                                 // no partner (round 0) or B infinite: A; A infinite: B
           R.x = stage_fe(kind == 3 ? xs + CW : xs);
           R.y = stage_y(kind == 3 ? ST_BY : ST_AY, kind == 3 ? cur.y : cur.x);
+          prefetch_x();
         }
         CV::store_v(V, out.slot, R);
+      } else {
+        prefetch_x();
       }
       if (e > 0) issue_ypart(e - 1);
       cp_async_commit();                         // group Y_(e-1)

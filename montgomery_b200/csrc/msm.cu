@@ -5,6 +5,10 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <mutex>
+#include <thread>
+#include <dlfcn.h>
+#include <nccl.h>      // types only: the library is bound at run time (dlopen), see NcclApi
 #include "engine.cuh"
 #include "../../include/montgomery_b200.h"
 
@@ -42,6 +46,18 @@ struct mgb_ctx {
   uint32_t* h_pinned = nullptr;  // [0..31] out xy limbs + flag, [64..] misc readback
   int sm_count = 148;
   std::string err;
+  // multi-GPU: the context owns its NCCL communicator (mgb_comm_init / mgb_multi_create)
+  ncclComm_t comm = nullptr;
+  int comm_rank = 0, comm_world = 1;
+  DevBuf gathered;               // comm_world partial accumulators, rank order
+};
+
+// one host process, several GPUs (mgb_multi_*): one context per device, communicators from ncclCommInitAll
+struct mgb_multi {
+  std::vector<mgb_ctx*> ctxs;
+  std::vector<size_t> lo, hi;     // shard g holds the pairs [lo, hi) of the point set
+  size_t npoints = 0;
+  std::string err;
 };
 
 namespace {
@@ -51,6 +67,55 @@ int fail(mgb_ctx* ctx, int code, const std::string& msg) {
   if (ctx) ctx->err = msg;
   return code;
 }
+
+// NCCL is bound at run time: a single-GPU host never needs it, and a host that already carries an NCCL (PyTorch ships
+// its own libnccl.so.2) must share that copy rather than load a second one -- dlopen by SONAME returns the loaded one.
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetVersion)(int*) = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommGetAsyncError)(ncclComm_t, ncclResult_t*) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  std::string err;
+};
+
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* names[] = {getenv("MGB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+      if (!nm || !*nm) continue;
+      api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (api.handle) break;
+      api.err = dlerror();
+    }
+    if (!api.handle) return;
+    bool ok = true;
+    auto sym = [&](const char* nm) -> void* { void* f = dlsym(api.handle, nm); if (!f) { ok = false; api.err = std::string("missing symbol ") + nm; } return f; };
+    api.GetVersion = (decltype(api.GetVersion))sym("ncclGetVersion");
+    api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+    api.CommInitAll = (decltype(api.CommInitAll))sym("ncclCommInitAll");
+    api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+    api.CommGetAsyncError = (decltype(api.CommGetAsyncError))sym("ncclCommGetAsyncError");
+    api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+    api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+    if (!ok) { dlclose(api.handle); api.handle = nullptr; }
+  });
+  return api.handle ? &api : nullptr;
+}
+
+#define NC(ctx, api, call)                                                                    \
+  do {                                                                                        \
+    ncclResult_t r_ = (call);                                                                 \
+    if (r_ != ncclSuccess)                                                                    \
+      return fail(ctx, MGB_E_COMM, std::string(#call) + ": " + (api)->GetErrorString(r_));    \
+  } while (0)
 
 #define CU(ctx, call)                                                                         \
   do {                                                                                        \
@@ -302,19 +367,22 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
       PairEnt* pout = pl[(r & 1) ^ 1];
       if constexpr (CV::BATCH_AFFINE) {
         constexpr int EMAX = MGB_EMAX, MINB = MGB_MINB;
-        // additions of this round (exact over all windows, from the scan)
-        const uint64_t est = (r < SCAN_ROUNDS ? (uint64_t)round_pairs[r] : 0) * Kg / pr.K;
+        // pairs this launch walks (exact over all windows, from the scan): round 0 walks every aligned slot pair, the
+        // partner-less last elements of odd buckets included (they are copied); later rounds walk their pair list
+        const uint64_t est = (r == 0 ? (uint64_t)(ctx->h_pinned[64] / 2) : (r < SCAN_ROUNDS ? (uint64_t)round_pairs[r] : 0)) * Kg / pr.K;
         const uint64_t warps = (uint64_t)ctx->sm_count * MINB * 4;
         // Tile shape: every tile holds E pairs per lane, with E chosen so that the round is an (almost) whole number
         // k of tiles per resident warp:  per lane p = est / (32 * warps) additions, k = ceil(p / EMAX) tiles,
         // E = ceil(p / k).  A batch (warp products + inversion) costs the same however small, so few, large tiles
         // win -- but a power-of-two E leaves up to a quarter of the warps without a second tile (or without any
         // tile) while the others finish.  Measured at 2^20 (profiles/r02_tile_sweep.txt): E = 64/64/32/16/8 ->
-        // 56/28/28/14/7 takes the accumulation from 4.78 to 4.37 ms.  Late rounds (p < 32) get two tiles per warp:
-        // the dynamic hand-out of the second tile evens out the warps that drew an expensive first one.
+        // 56/28/28/14/7 takes the accumulation from 4.78 to 4.37 ms, and round 0 alone is 2.07 ms at E = 56 against
+        // 2.13 - 2.27 ms at 48, 52, 54, 58 or 60.  Rounds with more than 32 pairs per lane get two tiles per warp (the
+        // dynamic hand-out of the second one takes the warps out of lockstep: one tile of 111 pairs per lane with
+        // EMAX = 128 was slower, 2.54 ms), smaller rounds one.
         const uint64_t per_lane = std::max<uint64_t>(1, (est + 32 * warps - 1) / (32 * warps));
         uint64_t ktiles = (per_lane + EMAX - 1) / EMAX;
-        if (per_lane > 16 && per_lane <= (uint64_t)EMAX && r > 0) ktiles = 2;
+        if (per_lane > 32 && ktiles < 2) ktiles = 2;
         if (const char* ev = getenv("MGB_DEBUG_KTILES")) ktiles = std::max(1, atoi(ev));
         int emin = 4;
         if (const char* ev = getenv("MGB_DEBUG_EMIN")) emin = std::max(1, atoi(ev));
@@ -456,15 +524,63 @@ int msm_impl(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
 }
 
 template <class CV>
+__global__ void k_acc_neutral(uint32_t* out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) CV::st_acc(out, CV::acc_zero());
+}
+
+template <class CV>
 int msm_partial_impl(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const mgb_opts* opts, void* d_out, mgb_timing* tm) {
   if (tm) memset(tm, 0, sizeof(*tm));
-  if (n == 0) return fail(ctx, MGB_E_INVALID, "mgb_msm_partial: n must be > 0 on every rank");
+  if (n == 0) {   // an empty shard (fewer pairs than ranks) contributes the neutral element
+    ENS(ctx, ctx->acc_out, CV::ACC_LIMBS * 4);
+    k_acc_neutral<CV><<<1, 32, 0, ctx->stream>>>((uint32_t*)d_out);
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+  }
   int r = msm_core<CV>(ctx, scalars, on_device, n, opts, tm);
   if (r) return r;
   CU(ctx, cudaMemcpyAsync(d_out, ctx->acc_out.p, CV::ACC_LIMBS * 4, cudaMemcpyDeviceToDevice, ctx->stream));
   CU(ctx, cudaEventRecord(ctx->ev[EV_FINAL], ctx->stream));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
   return finish_timing(ctx, tm);
+}
+
+
+// One rank of the sharded MSM: partial sum of the local shard, ONE ncclAllGather of the un-normalised
+// partial accumulators on the engine's own stream straight behind k_final, sum + normalisation of the comm_world
+// partials in one kernel, one device->host copy, one synchronisation.  An empty shard contributes the neutral element.
+template <class CV>
+int msm_sharded_impl(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const mgb_opts* opts, uint8_t* out_xy, int* out_is_zero, mgb_timing* tm) {
+  if (tm) memset(tm, 0, sizeof(*tm));
+  const size_t acc_bytes = CV::ACC_LIMBS * 4;
+  ENS(ctx, ctx->acc_out, acc_bytes);
+  if (n == 0) {
+    k_acc_neutral<CV><<<1, 32, 0, ctx->stream>>>((uint32_t*)ctx->acc_out.p);
+    CU(ctx, cudaGetLastError());
+  } else {
+    int r = msm_core<CV>(ctx, scalars, on_device, n, opts, tm);
+    if (r) return r;
+  }
+  const void* partials = ctx->acc_out.p;
+  if (ctx->comm_world > 1) {
+    NcclApi* api = nccl_api();
+    if (!api || !ctx->comm) return fail(ctx, MGB_E_STATE, "sharded msm: the context has no communicator (mgb_comm_init)");
+    ENS(ctx, ctx->gathered, acc_bytes * ctx->comm_world);
+    NC(ctx, api, api->AllGather(ctx->acc_out.p, ctx->gathered.p, acc_bytes, ncclUint8, ctx->comm, ctx->stream));
+    partials = ctx->gathered.p;
+    if (tm) tm->n_launches += 1;
+  }
+  int r = normalize_out<CV>(ctx, partials, ctx->comm_world, out_xy, out_is_zero);
+  if (r) return r;
+  if (tm) tm->n_launches += 1;
+  if (ctx->comm) {     // asynchronous NCCL failures (a peer died, a transport error) surface here, not as a hang later
+    NcclApi* api = nccl_api();
+    ncclResult_t async = ncclSuccess;
+    NC(ctx, api, api->CommGetAsyncError(ctx->comm, &async));
+    if (async != ncclSuccess) return fail(ctx, MGB_E_COMM, std::string("NCCL asynchronous error: ") + api->GetErrorString(async));
+  }
+  return n ? finish_timing(ctx, tm) : 0;
 }
 
 #define DISPATCH(ctx, fn, ...)                                              \
@@ -495,6 +611,33 @@ int msm_common(mgb_ctx* ctx, const void* scalars, bool dev, size_t n, const mgb_
     if (ctx->curve == MGB_BLS12_381_G1) return msm_impl<CurveBls381Basic>(ctx, scalars, dev, n, opts, out_xy, out_is_zero, tm);
   }
   DISPATCH(ctx, msm_impl, ctx, scalars, dev, n, opts, out_xy, out_is_zero, tm);
+}
+
+int multi_fail(mgb_multi* m, int code, const std::string& msg) {
+  if (m) m->err = msg;
+  g_last_error = msg;
+  return code;
+}
+
+// contiguous split, the rule of the reference's range() (src/threads/threads.ts:354-359)
+void multi_shards(mgb_multi* m, size_t n) {
+  const size_t G = m->ctxs.size(), per = (n + G - 1) / G;
+  for (size_t g = 0; g < G; g++) { m->lo[g] = std::min(n, per * g); m->hi[g] = std::min(n, m->lo[g] + per); }
+  m->npoints = n;
+}
+
+// run fn(g) for every device on its own host thread; first non-zero code wins
+template <class Fn>
+int multi_each(mgb_multi* m, Fn fn) {
+  const size_t G = m->ctxs.size();
+  std::vector<int> rc(G, 0);
+  std::vector<std::thread> th;
+  for (size_t g = 1; g < G; g++) th.emplace_back([&, g] { rc[g] = fn(g); });
+  rc[0] = fn(0);
+  for (auto& t : th) t.join();
+  for (size_t g = 0; g < G; g++)
+    if (rc[g]) return multi_fail(m, rc[g], "device " + std::to_string(m->ctxs[g]->device) + ": " + m->ctxs[g]->err);
+  return 0;
 }
 
 }  // namespace
@@ -573,7 +716,7 @@ size_t mgb_partial_bytes(const mgb_ctx* ctx) {
 }
 
 int mgb_msm_partial(mgb_ctx* ctx, const void* scalars, int scalars_on_device, size_t n, const mgb_opts* opts, void* d_partial_out, mgb_timing* timing) {
-  if (!ctx || !d_partial_out || !scalars) return fail(ctx, MGB_E_INVALID, "mgb_msm_partial: NULL argument");
+  if (!ctx || !d_partial_out || (!scalars && n)) return fail(ctx, MGB_E_INVALID, "mgb_msm_partial: NULL argument");
   if (n > ctx->npoints) return fail(ctx, ctx->npoints ? MGB_E_INVALID : MGB_E_STATE, "mgb_msm_partial: n exceeds the number of points set");
   CU(ctx, cudaSetDevice(ctx->device));
   DISPATCH(ctx, msm_partial_impl, ctx, scalars, scalars_on_device != 0, n, opts, d_partial_out, timing);
@@ -585,11 +728,134 @@ int mgb_combine_partials(mgb_ctx* ctx, const void* d_partials, int count, uint8_
   DISPATCH(ctx, normalize_out, ctx, d_partials, count, out_xy_le, out_is_zero);
 }
 
+int mgb_comm_unique_id(uint8_t* id_out) {
+  if (!id_out) return fail(nullptr, MGB_E_INVALID, "mgb_comm_unique_id: NULL argument");
+  NcclApi* api = nccl_api();
+  if (!api) return fail(nullptr, MGB_E_COMM, "NCCL library not found (libnccl.so.2; set MGB_NCCL_LIB)");
+  static_assert(sizeof(ncclUniqueId) == MGB_COMM_ID_BYTES, "ncclUniqueId size");
+  ncclUniqueId id;
+  NC(nullptr, api, api->GetUniqueId(&id));
+  memcpy(id_out, &id, sizeof(id));
+  return 0;
+}
+
+int mgb_comm_init(mgb_ctx* ctx, const uint8_t* id, int rank, int world) {
+  if (!ctx || !id) return fail(ctx, MGB_E_INVALID, "mgb_comm_init: NULL argument");
+  if (world < 1 || rank < 0 || rank >= world) return fail(ctx, MGB_E_INVALID, "mgb_comm_init: need 0 <= rank < world");
+  if (ctx->comm) return fail(ctx, MGB_E_STATE, "mgb_comm_init: the context already has a communicator");
+  NcclApi* api = nccl_api();
+  if (!api) return fail(ctx, MGB_E_COMM, "NCCL library not found (libnccl.so.2; set MGB_NCCL_LIB)");
+  CU(ctx, cudaSetDevice(ctx->device));
+  ncclUniqueId uid;
+  memcpy(&uid, id, sizeof(uid));
+  NC(ctx, api, api->CommInitRank(&ctx->comm, world, uid, rank));
+  ctx->comm_rank = rank;
+  ctx->comm_world = world;
+  return 0;
+}
+
+int mgb_comm_info(const mgb_ctx* ctx, int* rank, int* world, int* nccl_version) {
+  if (!ctx) return fail(nullptr, MGB_E_INVALID, "mgb_comm_info: NULL ctx");
+  if (rank) *rank = ctx->comm_rank;
+  if (world) *world = ctx->comm_world;
+  if (nccl_version) {
+    *nccl_version = 0;
+    NcclApi* api = nccl_api();
+    if (api) api->GetVersion(nccl_version);
+  }
+  return 0;
+}
+
+int mgb_msm_sharded(mgb_ctx* ctx, const void* scalars, int scalars_on_device, size_t n_local, const mgb_opts* opts,
+                    uint8_t* out_xy_le, int* out_is_zero, mgb_timing* timing) {
+  if (!ctx || !out_xy_le || (!scalars && n_local)) return fail(ctx, MGB_E_INVALID, "mgb_msm_sharded: NULL argument");
+  if (n_local > ctx->npoints) return fail(ctx, ctx->npoints ? MGB_E_INVALID : MGB_E_STATE, "mgb_msm_sharded: n_local exceeds the number of points set");
+  if (opts && opts->projective) return fail(ctx, MGB_E_INVALID, "mgb_msm_sharded: the projective cross-check path is single-GPU only");
+  CU(ctx, cudaSetDevice(ctx->device));
+  DISPATCH(ctx, msm_sharded_impl, ctx, scalars, scalars_on_device != 0, n_local, opts, out_xy_le, out_is_zero, timing);
+}
+
+/* ---- one host process driving several GPUs (`device_ids, n_devices`) ---- */
+int mgb_multi_create(mgb_multi** out, int curve, const int* device_ids, int n_devices, size_t max_points_per_device) {
+  if (!out || !device_ids || n_devices < 1) return multi_fail(nullptr, MGB_E_INVALID, "mgb_multi_create: bad argument");
+  mgb_multi* m = new mgb_multi();
+  m->lo.assign(n_devices, 0);
+  m->hi.assign(n_devices, 0);
+  for (int g = 0; g < n_devices; g++) {
+    mgb_ctx* c = nullptr;
+    int rc = mgb_create(&c, curve, device_ids[g], max_points_per_device);
+    if (rc) { std::string e = g_last_error; mgb_multi_destroy(m); return multi_fail(nullptr, rc, e); }
+    m->ctxs.push_back(c);
+  }
+  if (n_devices > 1) {
+    NcclApi* api = nccl_api();
+    if (!api) { mgb_multi_destroy(m); return multi_fail(nullptr, MGB_E_COMM, "NCCL library not found (libnccl.so.2; set MGB_NCCL_LIB)"); }
+    std::vector<ncclComm_t> comms(n_devices);
+    ncclResult_t r = api->CommInitAll(comms.data(), n_devices, device_ids);
+    if (r != ncclSuccess) { std::string e = api->GetErrorString(r); mgb_multi_destroy(m); return multi_fail(nullptr, MGB_E_COMM, "ncclCommInitAll: " + e); }
+    for (int g = 0; g < n_devices; g++) { m->ctxs[g]->comm = comms[g]; m->ctxs[g]->comm_rank = g; m->ctxs[g]->comm_world = n_devices; }
+  }
+  *out = m;
+  return 0;
+}
+
+int mgb_multi_set_points(mgb_multi* m, const uint8_t* xy_le, const uint8_t* is_zero, size_t n) {
+  if (!m || (!xy_le && n)) return multi_fail(m, MGB_E_INVALID, "mgb_multi_set_points: NULL argument");
+  multi_shards(m, n);
+  const size_t pb = entry_bytes(m->ctxs[0]->curve) / 3 * 2;      // x||y bytes of one point
+  return multi_each(m, [&](size_t g) {
+    return mgb_set_points(m->ctxs[g], xy_le + m->lo[g] * pb, is_zero ? is_zero + m->lo[g] : nullptr, m->hi[g] - m->lo[g]);
+  });
+}
+
+int mgb_multi_random_points(mgb_multi* m, uint64_t seed, size_t n) {
+  if (!m) return multi_fail(m, MGB_E_INVALID, "mgb_multi_random_points: NULL argument");
+  multi_shards(m, n);
+  // shard g is the point set of seed + g (as the one-process-per-GPU host layer does): the union is the global set
+  return multi_each(m, [&](size_t g) { return mgb_random_points(m->ctxs[g], seed + g, m->hi[g] - m->lo[g]); });
+}
+
+int mgb_multi_get_points(mgb_multi* m, size_t first, size_t n, uint8_t* xy_le, uint8_t* is_zero) {
+  if (!m || (!xy_le && n)) return multi_fail(m, MGB_E_INVALID, "mgb_multi_get_points: NULL argument");
+  if (first + n > m->npoints) return multi_fail(m, MGB_E_INVALID, "mgb_multi_get_points: range exceeds stored points");
+  const size_t pb = entry_bytes(m->ctxs[0]->curve) / 3 * 2;
+  for (size_t g = 0; g < m->ctxs.size(); g++) {
+    const size_t a = std::max(first, m->lo[g]), b = std::min(first + n, m->hi[g]);
+    if (a >= b) continue;
+    int rc = mgb_get_points(m->ctxs[g], a - m->lo[g], b - a, xy_le + (a - first) * pb, is_zero ? is_zero + (a - first) : nullptr);
+    if (rc) return multi_fail(m, rc, m->ctxs[g]->err);
+  }
+  return 0;
+}
+
+int mgb_multi_msm(mgb_multi* m, const uint8_t* scalars_le32, size_t n, const mgb_opts* opts, uint8_t* out_xy_le, int* out_is_zero, mgb_timing* timing) {
+  if (!m || !out_xy_le || (!scalars_le32 && n)) return multi_fail(m, MGB_E_INVALID, "mgb_multi_msm: NULL argument");
+  if (n > m->npoints) return multi_fail(m, m->npoints ? MGB_E_INVALID : MGB_E_STATE, "mgb_multi_msm: n exceeds the number of points set");
+  // every device takes the pairs of ITS point shard that lie below n; every rank ends with the full sum, device 0 reports it
+  std::vector<std::vector<uint8_t>> scratch(m->ctxs.size(), std::vector<uint8_t>(256));
+  std::vector<int> zero(m->ctxs.size(), 0);
+  return multi_each(m, [&](size_t g) {
+    const size_t lo = std::min(n, m->lo[g]), hi = std::min(n, m->hi[g]);
+    return mgb_msm_sharded(m->ctxs[g], scalars_le32 + lo * 32, 0, hi - lo, opts, g == 0 ? out_xy_le : scratch[g].data(),
+                           g == 0 ? out_is_zero : &zero[g], g == 0 ? timing : nullptr);
+  });
+}
+
+const char* mgb_multi_last_error(const mgb_multi* m) { return m ? m->err.c_str() : g_last_error.c_str(); }
+
+void mgb_multi_destroy(mgb_multi* m) {
+  if (!m) return;
+  for (mgb_ctx* c : m->ctxs) mgb_destroy(c);
+  delete m;
+}
+
 const char* mgb_last_error(const mgb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
 
 void mgb_destroy(mgb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  if (ctx->comm) { if (NcclApi* api = nccl_api()) api->CommDestroy(ctx->comm); ctx->comm = nullptr; }
+  if (ctx->gathered.p) cudaFree(ctx->gathered.p);
   DevBuf* bufs[] = {&ctx->table, &ctx->scalars, &ctx->ent_bucket, &ctx->ent_rank, &ctx->counts, &ctx->offs, &ctx->tile_sums, &ctx->pairs, &ctx->pairs2, &ctx->V, &ctx->recs, &ctx->lifes, &ctx->prebuf, &ctx->bsum, &ctx->redU[0], &ctx->redU[1], &ctx->redW[0], &ctx->redW[1], &ctx->misc,
                     &ctx->acc_out, &ctx->out_xy, &ctx->stage};
   for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);

@@ -164,6 +164,38 @@ __global__ void __launch_bounds__(1024) k_mulbench(uint32_t* out, uint32_t seed,
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// two independent products per call, instruction streams free to interleave (one basic block): does a warp that runs
+// alone on its scheduler keep the multiplier pipe busier with two carry-chain sets in flight than with one?
+template <class P>
+struct Fe2 { Fe<P> a, b; };
+template <class P>
+MGB_NOINLINE_DEV Fe2<P> mul2_call(Fe<P> a, Fe<P> b, Fe<P> c, Fe<P> d) {
+  Fe2<P> r;
+  r.a = Field<P>::mul_inl(a, b);
+  r.b = Field<P>::mul_inl(c, d);
+  return r;
+}
+template <class P>
+__global__ void __launch_bounds__(256) k_mul2bench(uint32_t* out, uint32_t seed, int iters) {
+  typedef Field<P> F;
+  Fe<P> a = F::one(), b = F::one(), c = F::one(), d = F::one();
+  a.v[0] ^= (seed ^ threadIdx.x) & 0xffff;
+  b.v[1] ^= blockIdx.x & 0xffff;
+  c.v[2] ^= (seed ^ threadIdx.x) & 0xfff;
+  d.v[3] ^= blockIdx.x & 0xfff;
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+    Fe2<P> r = mul2_call<P>(a, b, c, d);
+    a = r.a; c = r.b;
+    r = mul2_call<P>(b, a, d, c);
+    b = r.a; d = r.b;
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < P::N; k++) s ^= a.v[k] ^ b.v[k] ^ c.v[k] ^ d.v[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // inversion latency: dependent chain of division-step inverses, all lanes or lane 0 only
 template <class P, bool LANE0, bool COOP = false>
 __global__ void __launch_bounds__(128) k_invbench(uint32_t* out, uint32_t seed, int iters) {
@@ -249,11 +281,12 @@ int mgb_microbench(int device, int mode, int blocks_per_sm, int threads, int ite
       case 10: k_mullat<Fp377, false><<<grid, 32>>>(d, 12345u, it); break;
       case 11: k_mullat<Fp377, true><<<grid, 32>>>(d, 12345u, it); break;
       case 12: k_invbench<Fp377, true, true><<<grid, threads>>>(d, 12345u, it); break;
+      case 13: k_mul2bench<Fp377><<<grid, threads>>>(d, 12345u, it); break;
       default: break;
     }
   };
-  if (mode < 0 || mode > 12) return MGB_E_INVALID;
-  if (mode >= 8 && threads > 128) return MGB_E_INVALID;
+  if (mode < 0 || mode > 13) return MGB_E_INVALID;
+  if (mode >= 8 && mode <= 12 && threads > 128) return MGB_E_INVALID;
   if (mode == 10 || mode == 11) threads = 32;                         // one warp per block: the chain runs alone on its scheduler
   launch(iters / 8 + 1);  // warm-up
   CUT(cudaDeviceSynchronize());
@@ -267,6 +300,7 @@ int mgb_microbench(int device, int mode, int blocks_per_sm, int threads, int ite
   double per_thread;
   if (mode <= 2) per_thread = 16.0 * 8 * iters;        // instructions per thread
   else if (mode == 3) per_thread = 16.0 * 8 * iters;   // wide MADs per thread
+  else if (mode == 13) per_thread = 4.0 * iters;        // field multiplications per thread (two per call)
   else if (mode == 12) per_thread = 1.0 / 32 * iters;   // inversions per WARP
   else if (mode >= 10) per_thread = 2.0 * iters / 32;   // products per WARP (one chain per warp)
   else if (mode >= 8) per_thread = (mode == 9 ? 1.0 / 32 : 1.0) * iters;   // inversions per thread

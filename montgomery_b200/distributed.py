@@ -6,6 +6,9 @@ main thread adds the per-thread partial sums (msm-batched-affine.ts:311-320).  H
 pairs [lo, hi) of `shard_range`, computes the partial sum of its shard on its own B200, and the G
 un-normalised partial accumulators (192 bytes each for BLS12-377) are exchanged with ONE all-gather
 over NCCL / NVLink; every rank then adds them and normalises.  MSM has no other exchange step.
+The collective lives in the C library (`mgb_comm_init`, `mgb_msm_sharded`, include/montgomery_b200.h):
+ncclAllGather on the engine's stream straight after the Horner kernel, one combine + normalise
+kernel, one device-to-host copy, one synchronisation.
 """
 import torch
 import torch.distributed as dist
@@ -28,15 +31,33 @@ def all_gather_partials(partial: torch.Tensor) -> torch.Tensor:
     return out.view(world, partial.numel())
 
 
+def exchange_comm_id(rank: int, device=None) -> bytes:
+    """Rank 0 draws the NCCL unique id (mgb_comm_unique_id) and broadcasts its 128 bytes over the already
+    initialised torch.distributed group -- the host-side channel of this Python host; any other (MPI, a TCP
+    store, a worker message) does as well.  Works on the nccl backend (device = this rank's GPU) and on gloo."""
+    from . import _native
+    from .api import comm_unique_id
+    dev = torch.device("cuda", device) if dist.get_backend() == "nccl" else torch.device("cpu")
+    if rank == 0:
+        t = torch.tensor(list(comm_unique_id()), dtype=torch.uint8, device=dev)
+    else:
+        t = torch.zeros(_native.COMM_ID_BYTES, dtype=torch.uint8, device=dev)
+    dist.broadcast(t, src=0)
+    return bytes(t.cpu().tolist())
+
+
 class ShardedMsm:
-    """The sharded engine.  Every rank calls the same methods with its own shard."""
+    """The sharded engine.  Every rank calls the same methods with its own shard.  The data path is entirely
+    inside the C library: the context owns its NCCL communicator, and `mgb_msm_sharded` runs the partial MSM,
+    the all-gather of the partial sums and the combine on the engine's stream with one synchronisation.
+    torch.distributed is used once, to hand the communicator id to the other ranks."""
 
     def __init__(self, curve, local_device: int, max_points_per_rank: int):
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.engine = MsmEngine(curve, local_device, max_points_per_rank)
-        nwords = self.engine.partial_bytes // 4
-        self._partial = torch.zeros(nwords, dtype=torch.int32, device=torch.device("cuda", local_device))
+        if self.world > 1:
+            self.engine.comm_init(exchange_comm_id(self.rank, local_device), self.rank, self.world)
 
     def set_points(self, xy_bytes_shard, is_zero=None):
         return self.engine.set_points(xy_bytes_shard, is_zero)
@@ -46,19 +67,15 @@ class ShardedMsm:
         self.engine.random_points(n_local, seed + self.rank)
 
     def msm(self, scalars, n_local: int, on_device: bool = False, c=None):
-        """scalars: pinned/any host tensor or numpy array (on_device=False) or a CUDA uint8 tensor."""
-        if self.world == 1:
-            if on_device:
-                return self.engine.msm(None, n=n_local, c=c, device_ptr=scalars.data_ptr())
-            arr = scalars.numpy() if isinstance(scalars, torch.Tensor) else scalars
-            return self.engine.msm(arr, n=n_local, c=c)
+        """scalars: pinned/any host tensor or numpy array (on_device=False) or a CUDA uint8 tensor (complete
+        before the call: the engine reads it on its own stream).  Every rank returns the full result."""
+        if n_local == 0:
+            return self.engine.msm_sharded(0, on_device, 0, c=c)
         ptr = scalars.data_ptr() if isinstance(scalars, torch.Tensor) else scalars.ctypes.data
-        tm = self.engine.msm_partial(ptr, on_device, n_local, self._partial.data_ptr(), c=c)
-        gathered = all_gather_partials(self._partial)
-        torch.cuda.current_stream().synchronize()
-        res = self.engine.combine_partials(gathered.data_ptr(), self.world)
-        tm["n_launches"] += 2          # the all-gather and the combine/normalise kernel
-        return res, tm
+        nbytes = scalars.numel() * scalars.element_size() if isinstance(scalars, torch.Tensor) else scalars.nbytes
+        if n_local * 32 > nbytes:
+            raise ValueError("msm: n_local = %d exceeds the %d scalars in the buffer" % (n_local, nbytes // 32))
+        return self.engine.msm_sharded(ptr, on_device, n_local, c=c)
 
     def close(self):
         self.engine.close()

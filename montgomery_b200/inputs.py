@@ -61,3 +61,24 @@ def scalars_to_ints(sc: np.ndarray):
 def ints_to_le_bytes(vals, nbytes: int) -> np.ndarray:
     buf = b"".join(int(v).to_bytes(nbytes, "little") for v in vals)
     return np.frombuffer(buf, dtype=np.uint8).reshape(len(vals), nbytes).copy()
+
+
+def dot_known_dlogs(sc: np.ndarray, a: np.ndarray) -> int:
+    """sum_i s_i * a_i as an exact Python int, for (n, 32) uint8 little-endian scalars and uint64 multipliers --
+    the scalar of the closed form  msm(s, a_i G) = [(sum s_i a_i) mod q] G  used by the parity checks at sizes where
+    a per-element Python loop would take minutes.  Vectorised: every 32x32-bit partial product is exact in uint64,
+    and its two 32-bit halves are summed separately (n < 2^31 keeps those sums below 2^63)."""
+    n = sc.shape[0]
+    assert sc.shape == (n, 32) and a.shape == (n,) and n < (1 << 31)
+    w = np.ascontiguousarray(sc).view("<u4").reshape(n, 8).astype(np.uint64)      # 8 words of 32 bits per scalar
+    a = a.astype(np.uint64)
+    halves = (a & np.uint64(0xFFFFFFFF), a >> np.uint64(32))
+    total = 0
+    m32 = np.uint64(0xFFFFFFFF)
+    for k in range(8):
+        for h in (0, 1):
+            prod = w[:, k] * halves[h]                                            # < 2^64, exact
+            lo = int((prod & m32).sum(dtype=np.uint64))
+            hi = int((prod >> np.uint64(32)).sum(dtype=np.uint64))
+            total += (lo + (hi << 32)) << (32 * (k + h))
+    return total
