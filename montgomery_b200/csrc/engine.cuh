@@ -82,6 +82,7 @@ struct WeierstrassPolicy {
   typedef typename G::affine vpoint;   // materialised bucket element
   typedef GL Glv;
   typedef CoopWeierstrass<FP> Coop;
+  typedef OneWarpWeierstrass<FP> OneWarp;
   typedef QuadWeierstrass<FP> Quad;
   static constexpr int N = FP::N;
   static constexpr bool USE_GLV = true;
@@ -159,6 +160,7 @@ struct TwistedEdwardsPolicy {
   typedef typename G::acc acc;
   typedef typename G::acc vpoint;
   typedef CoopTwistedEdwards<FP, CC> Coop;
+  typedef OneWarpTwistedEdwards<FP, CC> OneWarp;
   static constexpr int N = FP::N;
   static constexpr bool USE_GLV = false;
   static constexpr bool BATCH_AFFINE = false;
@@ -488,36 +490,47 @@ MGB_DEV void emit_pair(bool active, PairEnt ent, PairEnt* __restrict__ pairs, ui
   }
 }
 
+// Grid: x covers the points in chunks of SCATTER_U * 256, y = (half, window of the group): no index division, and
+// every thread has SCATTER_U independent entries in flight (the chain entry -> bucket offset / count -> scattered
+// write is three dependent memory round trips; one entry per thread left the kernel latency-bound).
+static constexpr int SCATTER_U = 4;
 template <class CV>
 __global__ void __launch_bounds__(256) k_scatter(MsmParams pr, int w_begin, int Kg, const uint32_t* __restrict__ ent_bucket, const uint32_t* __restrict__ ent_rank,
                                                  const uint32_t* __restrict__ offs, const uint32_t* __restrict__ counts, const uint32_t* __restrict__ table,
                                                  uint32_t* __restrict__ V, uint32_t* __restrict__ recs /* 2 words per aligned slot pair */, uint8_t* __restrict__ lifes) {
-  // thread -> (half h, window w of the group [w_begin, w_begin + Kg), point i)
-  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (size_t)pr.n * CV::HALVES * Kg) return;
-  uint32_t el = (uint32_t)(t / pr.n), i = (uint32_t)(t - (size_t)el * pr.n);
-  uint32_t h = el / (uint32_t)Kg, w = (uint32_t)w_begin + el % (uint32_t)Kg;
-  size_t pos = (size_t)(h * pr.K + w) * pr.n + i;
-  uint32_t b = ent_bucket[pos];
-  if (b == NO_BUCKET) return;
-  uint32_t rk = ent_rank[pos];
+  const uint32_t el = blockIdx.y;
+  const uint32_t h = el / (uint32_t)Kg, w = (uint32_t)w_begin + el % (uint32_t)Kg;
+  const size_t row = (size_t)(h * pr.K + w) * pr.n;
   const bool endo = h != 0;
-  uint32_t n = counts[b], j = rk & ~REF_NEG;
-  uint32_t slot = offs[b] + j;
-  if (V) { CV::store_v(V, slot, CV::load_entry(table, i, endo, (rk & REF_NEG) != 0)); return; }
-  uint32_t* rec = recs + (size_t)(slot >> 1) * 2;
-  const uint32_t ref = i | (endo ? REF_ENDO : 0u) | (rk & REF_NEG);
-  if (j & 1) { rec[1] = ref; return; }
-  uint32_t rest = n - j - 1;                          // elements after this one
-  uint32_t life = 0;
-  if (rest) {
-    life = 32 - __clz(rest);                          // floor(log2(rest)) + 1
-    if (j) life = min(life, (uint32_t)(__ffs(j) - 1));
-  } else {
-    rec[1] = REF_EMPTY;                               // padding slot of an odd-sized bucket
+  uint32_t i[SCATTER_U], b[SCATTER_U], rk[SCATTER_U], n[SCATTER_U], o[SCATTER_U];
+  _Pragma("unroll") for (int u = 0; u < SCATTER_U; u++) {
+    i[u] = (blockIdx.x * SCATTER_U + u) * blockDim.x + threadIdx.x;
+    b[u] = NO_BUCKET; rk[u] = 0;
+    if (i[u] < pr.n) { b[u] = ent_bucket[row + i[u]]; rk[u] = ent_rank[row + i[u]]; }
   }
-  rec[0] = ref;
-  lifes[slot >> 1] = (uint8_t)life;
+  _Pragma("unroll") for (int u = 0; u < SCATTER_U; u++) {
+    n[u] = 0; o[u] = 0;
+    if (b[u] != NO_BUCKET) { n[u] = counts[b[u]]; o[u] = offs[b[u]]; }
+  }
+  _Pragma("unroll") for (int u = 0; u < SCATTER_U; u++) {
+    if (b[u] == NO_BUCKET) continue;
+    const uint32_t j = rk[u] & ~REF_NEG;
+    const uint32_t slot = o[u] + j;
+    if (V) { CV::store_v(V, slot, CV::load_entry(table, i[u], endo, (rk[u] & REF_NEG) != 0)); continue; }
+    uint32_t* rec = recs + (size_t)(slot >> 1) * 2;
+    const uint32_t ref = i[u] | (endo ? REF_ENDO : 0u) | (rk[u] & REF_NEG);
+    if (j & 1) { rec[1] = ref; continue; }
+    const uint32_t rest = n[u] - j - 1;                 // elements after this one
+    uint32_t life = 0;
+    if (rest) {
+      life = 32 - __clz(rest);                          // floor(log2(rest)) + 1
+      if (j) life = min(life, (uint32_t)(__ffs(j) - 1));
+    } else {
+      rec[1] = REF_EMPTY;                               // padding slot of an odd-sized bucket
+    }
+    rec[0] = ref;
+    lifes[slot >> 1] = (uint8_t)life;
+  }
 }
 
 // ---------------------------------------------------------------- k_batch_add (Weierstrass)
@@ -1202,9 +1215,9 @@ __global__ void __launch_bounds__(128) k_final(int K, int c, const uint32_t* __r
   __shared__ int flag;
   CoopMem<FP> m{sm};
 #if MGB_ONEWARP_HORNER
-  if constexpr (std::is_same<typename CV::Coop, CoopWeierstrass<FP>>::value) {
+  {
     if (threadIdx.x >= 32) return;
-    typedef OneWarpWeierstrass<FP> OW;
+    typedef typename CV::OneWarp OW;
     unsigned long long v = ow_load<FP>(Sw + (size_t)(K - 1) * CV::ACC_LIMBS);
     for (int w = K - 2; w >= 0; w--) {
       for (int d = 0; d < c; d++) v = OW::dbl(v);

@@ -40,7 +40,7 @@ struct mgb_ctx {
   size_t max_points = 0, npoints = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t aux[3] = {};          // extra streams: window groups are pipelined against each other
-  cudaEvent_t ev_fork = nullptr, ev_join[3] = {}, ev_chunk[4] = {};
+  cudaEvent_t ev_fork = nullptr, ev_plan = nullptr, ev_join[3] = {}, ev_chunk[4] = {};
   cudaEvent_t ev[EV_COUNT] = {};
   DevBuf table, scalars, ent_bucket, ent_rank, counts, offs, tile_sums, pairs, pairs2, V, recs, lifes, prebuf, bsum, redU[2], redW[2], misc, acc_out, out_xy, stage;
   uint32_t* h_pinned = nullptr;  // [0..31] out xy limbs + flag, [64..] misc readback
@@ -300,7 +300,26 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   CU(ctx, cudaMemcpyAsync(ctx->h_pinned + 64, misc, 8, cudaMemcpyDeviceToHost, st));
   CU(ctx, cudaMemcpyAsync(ctx->h_pinned + 66, (uint32_t*)ctx->counts.p + pr.nbuckets, 4, cudaMemcpyDeviceToHost, st));
   CU(ctx, cudaMemcpyAsync(ctx->h_pinned + 68, misc + 512, SCAN_ROUNDS * 4, cudaMemcpyDeviceToHost, st));
-  CU(ctx, cudaStreamSynchronize(st));
+  CU(ctx, cudaEventRecord(ctx->ev_plan, st));
+  // The host needs the counters above to size the tree rounds.  For inputs that certainly have a round 0 the scatter
+  // does not depend on them, so it is launched FIRST and the host waits for the counters (an event, not the stream)
+  // while it runs: the round trip no longer idles the GPU.  Should the plan come out without a round 0 after all
+  // (only possible for tiny buckets), the scatter is simply run again in its materialising form.
+  int G = 1;   // window groups pipelined on separate streams; measured on B200: 2 groups change the total by < 1 %; the mechanism stays for tuning
+  if (const char* ev = getenv("MGB_DEBUG_GROUPS")) G = std::max(1, std::min(4, atoi(ev)));
+  G = std::min(G, pr.K);
+  const bool early_scatter = G == 1 && pr.nent >= (1u << 19) && !getenv("MGB_DEBUG_NROUNDS");
+  if (early_scatter) {
+    ENS(ctx, ctx->recs, (max_slots / 2 + 1) * 8);
+    ENS(ctx, ctx->lifes, max_slots / 2 + 8);
+    k_scatter<CV><<<dim3(cdiv(n, 256 * SCATTER_U), (unsigned)(CV::HALVES * pr.K)), 256, 0, st>>>(
+        pr, 0, pr.K, (const uint32_t*)ctx->ent_bucket.p, (const uint32_t*)ctx->ent_rank.p, (const uint32_t*)ctx->offs.p, (const uint32_t*)ctx->counts.p,
+        (const uint32_t*)ctx->table.p, nullptr, (uint32_t*)ctx->recs.p, (uint8_t*)ctx->lifes.p);
+    launches++;
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaEventRecord(ctx->ev[EV_SORT], st));
+  }
+  CU(ctx, cudaEventSynchronize(ctx->ev_plan));
   const uint32_t maxcount = ctx->h_pinned[65];
   const uint32_t* round_pairs = ctx->h_pinned + 68;
   if (ctx->h_pinned[66] & 2u)
@@ -341,9 +360,6 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   // ---- window groups, pipelined on separate streams: every round ends with a tail in which few
   // tiles are left (and the late rounds and the reduction are latency-bound throughout); the
   // kernels of another, independent group of windows fill the SMs meanwhile.
-  int G = 1;   // measured on B200: 2 groups change the total by < 1 %; the mechanism stays for tuning / larger parts
-  if (const char* ev = getenv("MGB_DEBUG_GROUPS")) G = std::max(1, std::min(4, atoi(ev)));
-  G = std::min(G, pr.K);
   CU(ctx, cudaEventRecord(ctx->ev_fork, st));
   size_t pair_off = 0, pair2_off = 0;
   for (int g = 0; g < G; g++) {
@@ -358,10 +374,12 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
     const uint32_t b_begin = (uint32_t)w_begin * pr.L, b_end = (uint32_t)w_end * pr.L;
     uint32_t* cnt = misc + 8 + 64 * g;
     uint32_t* tcnt = misc + 264 + 64 * g;
-    k_scatter<CV><<<cdiv(nent_g, 256), 256, 0, sg>>>(pr, w_begin, Kg, (const uint32_t*)ctx->ent_bucket.p, (const uint32_t*)ctx->ent_rank.p,
-                                                    offs, counts, table, fuse ? nullptr : (uint32_t*)ctx->V.p, recs, lifes);
-    launches++;
-    if (g == 0) CU(ctx, cudaEventRecord(ctx->ev[EV_SORT], st));
+    if (!(early_scatter && fuse)) {
+      k_scatter<CV><<<dim3(cdiv(n, 256 * SCATTER_U), (unsigned)(CV::HALVES * Kg)), 256, 0, sg>>>(pr, w_begin, Kg, (const uint32_t*)ctx->ent_bucket.p, (const uint32_t*)ctx->ent_rank.p,
+                                                      offs, counts, table, fuse ? nullptr : (uint32_t*)ctx->V.p, recs, lifes);
+      launches++;
+      if (g == 0) CU(ctx, cudaEventRecord(ctx->ev[EV_SORT], st));
+    }
     for (int r = 0; r < rounds; r++) {
       PairEnt* pin = pl[r & 1];
       PairEnt* pout = pl[(r & 1) ^ 1];
@@ -664,6 +682,7 @@ int mgb_create(mgb_ctx** out, int curve, int device, size_t max_points) {
     CU(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 3; i++) { CU(ctx, cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking)); CU(ctx, cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming)); }
     CU(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CU(ctx, cudaEventCreateWithFlags(&ctx->ev_plan, cudaEventDisableTiming));
     for (int i = 0; i < 4; i++) CU(ctx, cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
     for (int i = 0; i < EV_COUNT; i++) CU(ctx, cudaEventCreate(&ctx->ev[i]));
     CU(ctx, cudaMallocHost((void**)&ctx->h_pinned, 256 * 4));
@@ -864,6 +883,7 @@ void mgb_destroy(mgb_ctx* ctx) {
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   for (int i = 0; i < 3; i++) { if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]); if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_plan) cudaEventDestroy(ctx->ev_plan);
   for (int i = 0; i < 4; i++) if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
   delete ctx;
 }

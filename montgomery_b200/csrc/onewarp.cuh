@@ -1,4 +1,4 @@
-// One-warp XYZZ point arithmetic (experiment for the next round; the Horner kernels use coop.cuh).
+// One-warp point arithmetic for the Horner kernels (XYZZ Weierstrass, extended twisted Edwards).
 //
 // coop.cuh runs a dependent chain of point operations on a 128-thread block: the four warps take
 // the (up to four) products of a formula level, each spread over 12 lanes of its warp, and meet at
@@ -100,6 +100,78 @@ struct OneWarpWeierstrass {
     if (infB) res = a;
     if (infA) res = b;
     return res;
+  }
+};
+
+// The same for extended twisted-Edwards points (a = -1): 8-lane group g holds coordinate g of (X, Y, Z, T).  A doubling
+// is dbl-2008-hwcd -- four squares, then four products: TWO product levels instead of the three of the unified
+// addition the block-cooperative CoopTwistedEdwards::dbl_n runs through shared memory (5.6 us per doubling there:
+// the 2^18-point ed-on-BLS12-377 MSM spent 1.33 of its 2.73 ms in the 238 doublings of its Horner chain).  The
+// addition is the strongly unified add-2008-hwcd-3 (complete: doubling, neutral element, inverses), three levels.
+template <class P, class C>
+struct OneWarpTwistedEdwards {
+  typedef WarpField2<P> WF;
+  typedef typename WF::u64 u64;
+  typedef Field<P> F;
+  typedef Fe<P> fe;
+  typedef TwistedEdwards<P, C> G;
+  static constexpr int N = P::N, D = WF::D, W = WF::W;
+
+  MGB_DEV static int group() { return warp::lane() >> 3; }
+  MGB_DEV static u64 from_group(u64 v, int sg) {
+    const int src = sg * W + (warp::lane() & (W - 1));
+    return ((u64)warp::shfl((uint32_t)(v >> 32), src, 32) << 32) | warp::shfl((uint32_t)v, src, 32);
+  }
+  MGB_DEV static u64 pick(int g, u64 a0, u64 a1, u64 a2, u64 a3) { return g == 0 ? a0 : (g == 1 ? a1 : (g == 2 ? a2 : a3)); }
+  MGB_DEV static u64 digit_of(const fe& a) {
+    const int l = warp::lane() & (W - 1);
+    u64 r = 0;
+    _Pragma("unroll") for (int k = 0; k < D; k++) r = (l == k) ? (((u64)a.v[2 * k + 1] << 32) | a.v[2 * k]) : r;
+    return r;
+  }
+  MGB_DEV static u64 spread(const typename G::acc& A) { return pick(group(), digit_of(A.X), digit_of(A.Y), digit_of(A.Z), digit_of(A.T)); }
+  MGB_DEV static typename G::acc gather(u64 v) {      // the whole point on every lane
+    typename G::acc A;
+    fe* c[4] = {&A.X, &A.Y, &A.Z, &A.T};
+    _Pragma("unroll") for (int g = 0; g < 4; g++) {
+      _Pragma("unroll") for (int k = 0; k < D; k++) {
+        const int src = g * W + k;
+        const uint32_t lo = warp::shfl((uint32_t)v, src, 32), hi = warp::shfl((uint32_t)(v >> 32), src, 32);
+        c[g]->v[2 * k] = lo; c[g]->v[2 * k + 1] = hi;
+      }
+    }
+    return A;
+  }
+
+  // [E F, G H, F G, E H] = (X3, Y3, Z3, T3) from E, F, G, H known on every group
+  MGB_DEV static u64 finish(u64 E, u64 Ff, u64 Gg, u64 H) {
+    const int g = group();
+    return WF::mul(pick(g, E, Gg, Ff, E), pick(g, Ff, H, Gg, H));
+  }
+  // 2P  (dbl-2008-hwcd with a = -1): A = X^2, B = Y^2, C = 2 Z^2, E = (X + Y)^2 - A - B, G = B - A, F = G - C, H = -A - B
+  MGB_DEV static u64 dbl(u64 v) {
+    const int g = group();
+    const u64 xb = from_group(v, 0), yb = from_group(v, 1);
+    const u64 xy = WF::add(xb, yb);                                  // (every lane runs the ballots inside)
+    const u64 a1 = g == 3 ? xy : v;                                  // [X, Y, Z, X + Y]
+    const u64 t1 = WF::mul(a1, a1);                                  // [A, B, ZZ, (X + Y)^2]
+    const u64 A = from_group(t1, 0), B = from_group(t1, 1), ZZ = from_group(t1, 2), S = from_group(t1, 3);
+    const u64 AB = WF::add(A, B);
+    const u64 E = WF::sub(S, AB), Gg = WF::sub(B, A);
+    const u64 Ff = WF::sub(Gg, WF::dbl(ZZ)), H = WF::sub(0ull, AB);
+    return finish(E, Ff, Gg, H);
+  }
+  // P + Q  (add-2008-hwcd-3): A = (Y1 - X1)(Y2 - X2), B = (Y1 + X1)(Y2 + X2), C = k T1 T2, D = 2 Z1 Z2
+  MGB_DEV static u64 add(u64 a, u64 b) {
+    const int g = group();
+    const u64 x1 = from_group(a, 0), y1 = from_group(a, 1), x2 = from_group(b, 0), y2 = from_group(b, 1);
+    const u64 l1 = pick(g, WF::sub(y1, x1), WF::add(y1, x1), a, a);  // [Y1 - X1, Y1 + X1, Z1, T1]
+    const u64 r1 = pick(g, WF::sub(y2, x2), WF::add(y2, x2), b, b);
+    const u64 t1 = WF::mul(l1, r1);                                  // [A, B, Z1 Z2, T1 T2]
+    const u64 t2 = WF::mul(t1, digit_of(G::k2d()));                  // group 3: C = k T1 T2
+    const u64 A = from_group(t1, 0), B = from_group(t1, 1), Cc = from_group(t2, 3);
+    const u64 Dd = WF::dbl(from_group(t1, 2));
+    return finish(WF::sub(B, A), WF::sub(Dd, Cc), WF::add(Dd, Cc), WF::add(B, A));
   }
 };
 

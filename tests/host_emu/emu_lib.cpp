@@ -177,6 +177,22 @@ template <class P> static void onewarp_op(int op, int count, uint32_t* out, cons
   });
 }
 
+// extended twisted-Edwards points in one warp (OneWarpTwistedEdwards): same three operations
+template <class P, class C> static void onewarp_te_op(int op, int count, uint32_t* out, const uint32_t* a, const uint32_t* b) {
+  typedef OneWarpTwistedEdwards<P, C> OW;
+  typedef TwistedEdwards<P, C> T;
+  constexpr int N = P::N;
+  auto ldx = [&](const uint32_t* p) { typename T::acc r; r.X = ld<P>(p); r.Y = ld<P>(p + N); r.Z = ld<P>(p + 2 * N); r.T = ld<P>(p + 3 * N); return r; };
+  simt::run_warp([&](int lane) {
+    auto v = OW::spread(ldx(a));
+    const auto q = OW::spread(ldx(b));
+    if (op == 0 || op == 2) for (int i = 0; i < count; i++) v = OW::dbl(v);
+    if (op == 1 || op == 2) v = OW::add(v, q);
+    const typename T::acc r = OW::gather(v);
+    if (lane == 13) { st<P>(out, r.X); st<P>(out + N, r.Y); st<P>(out + 2 * N, r.Z); st<P>(out + 3 * N, r.T); }
+  });
+}
+
 // quad-cooperative XYZZ addition: lane 4j + k holds coordinate k of the j-th of 8 independent additions
 template <class P> static void quad_add(uint32_t* out, const uint32_t* a, const uint32_t* b) {
   constexpr int N = P::N;
@@ -196,6 +212,9 @@ void emu_onewarp_w(int curve, int op, int count, uint32_t* out, const uint32_t* 
   if (curve == 0) onewarp_op<Fp377>(op, count, out, a, b);
   else if (curve == 1) onewarp_op<FpPallas>(op, count, out, a, b);
   else onewarp_op<Fp381>(op, count, out, a, b);
+}
+void emu_onewarp_te(int op, int count, uint32_t* out, const uint32_t* a, const uint32_t* b) {
+  onewarp_te_op<Fr377, Ed377Consts>(op, count, out, a, b);
 }
 void emu_coop_te(int op, int count, uint32_t* out, const uint32_t* a, const uint32_t* b) {
   coop_op<CoopTwistedEdwards<Fr377, Ed377Consts>, Fr377>(op, count, out, a, b);

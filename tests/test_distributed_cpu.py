@@ -1,7 +1,7 @@
 """World-size-2 gloo test (CPU) of the host-side sharding logic: contiguous shard ranges, the
-all-gather of partial sums in rank order, and that combining per-shard partial MSMs gives the full
-MSM.  The per-shard partials are computed by the oracle here (there is no GPU in this test); the GPU
-version of the same flow is scripts/check_multi_gpu.py (run under torchrun on >= 2 GPUs)."""
+all-gather of partial sums in rank order, that combining per-shard partial MSMs gives the full
+MSM, and the hand-over of the NCCL communicator id (mgb_comm_unique_id) to the other ranks.  The per-shard partials are computed by the oracle here (there is no GPU in this test); the GPU
+version of the same flow is scripts/check_multi_gpu.py, launched under torchrun by tests/test_gpu_round2.py on >= 2 GPUs."""
 import os
 import sys
 
@@ -41,6 +41,13 @@ def _worker(rank, world, port, n, out_q):
         total = O.P.add(total, pt)
     full = sum(s * int(ai) for s, ai in zip(sc, a)) % O.q
     ok = O.P.to_affine(total) == O.P.to_affine(O.P.scale(full, O.P.one))
+    # the communicator id of the in-library collective travels over the same group (mgb_comm_unique_id needs no GPU):
+    # every rank must end up with rank 0's 128 bytes
+    from montgomery_b200.distributed import exchange_comm_id
+    cid = exchange_comm_id(rank)
+    ids = [None] * world
+    dist.all_gather_object(ids, cid)
+    ok = ok and len(cid) == 128 and any(cid) and all(i == ids[0] for i in ids)
     out_q.put((rank, lo, hi, ok))
     dist.destroy_process_group()
 

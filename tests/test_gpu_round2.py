@@ -194,7 +194,7 @@ def test_one_process_multi_device_api(label):
     for devs in ([0], list(range(ndev))) if ndev > 1 else ([0],):
         G = len(devs)
         n = 5000 + 3                                                             # not a multiple of the device count
-        mg = m.MultiGpuMsm(cv, devs, 4096)
+        mg = m.MultiGpuMsm(cv, devs, 8192)
         try:
             mg.random_points(n, seed=40)
             per = -(-n // G)

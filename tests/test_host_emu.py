@@ -296,7 +296,11 @@ def test_coop_weierstrass_horner_steps(emu, cid, prm, n, impl):
     assert dec_x(I(out, n, 4)) == Q
 
 
-def test_coop_twisted_edwards_horner_steps(emu):
+@pytest.mark.parametrize("impl", ["block", "onewarp"])
+def test_coop_twisted_edwards_horner_steps(emu, impl):
+    """impl = block: CoopTwistedEdwards on a 128-thread block (round 1); onewarp: OneWarpTwistedEdwards, the whole extended
+    point in one warp, dedicated doubling (what k_final runs since round 2)."""
+    run_te = emu.emu_coop_te if impl == "block" else emu.emu_onewarp_te
     prm, n = ED_ON_BLS12_377, 8
     p = prm.p
     R = 1 << (32 * n)
@@ -321,13 +325,23 @@ def test_coop_twisted_edwards_horner_steps(emu):
     D = P
     for _ in range(3):
         D = T.double(D)
-    emu.emu_coop_te(0, 3, out, L(enc_e(P), n), L(enc_e(Q), n))
+    run_te(0, 3, out, L(enc_e(P), n), L(enc_e(Q), n))
     assert dec_e(I(out, n, 4)) == T.to_affine(D)
     for X, Y in [(P, Q), (P, P), (P, T.negate(P)), (T.zero, Q), (P, T.zero)]:
-        emu.emu_coop_te(1, 0, out, L(enc_e(X), n), L(enc_e(Y), n))
+        run_te(1, 0, out, L(enc_e(X), n), L(enc_e(Y), n))
         assert dec_e(I(out, n, 4)) == T.to_affine(T.add(X, Y))
-    emu.emu_coop_te(2, 3, out, L(enc_e(P), n), L(enc_e(Q), n))
+    run_te(2, 3, out, L(enc_e(P), n), L(enc_e(Q), n))
     assert dec_e(I(out, n, 4)) == T.to_affine(T.add(D, Q))
+    for count in (0, 1, 2, 7):
+        E2 = P
+        for _ in range(count):
+            E2 = T.double(E2)
+        run_te(0, count, out, L(enc_e(P), n), L(enc_e(Q), n))
+        assert dec_e(I(out, n, 4)) == T.to_affine(E2), count
+    run_te(0, 4, out, L(enc_e(T.zero), n), L(enc_e(Q), n))      # doubling the neutral element
+    assert dec_e(I(out, n, 4)) == (0, 1)
+    run_te(2, 5, out, L(enc_e(T.zero), n), L(enc_e(Q), n))      # empty top window
+    assert dec_e(I(out, n, 4)) == T.to_affine(Q)
 
 
 @pytest.mark.parametrize("cid,prm,n", [(0, BLS12_377, 12), (1, PALLAS, 8)])
