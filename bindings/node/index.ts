@@ -43,6 +43,27 @@ export function create(curve: Curve, { device = 0, maxPoints = 1 << 20 } = {}) {
   return { Parallel };
 }
 
+// Several GPUs behind the same `Parallel` shape.  The reference scales by `startThreads(n)` and a per-thread split of the
+// inputs (src/threads/threads.ts:354-359, msm-batched-affine.ts:311-320); here `devices` plays the role of the thread count:
+// the library splits the point set contiguously over the GPUs, each computes a partial sum, one NCCL all-gather and a
+// point addition combine them (mgb_multi_*: contexts and communicators live inside the library, one Node process).
+export function createSharded(curve: Curve, { devices = [0], maxPointsPerDevice = 1 << 21 } = {}) {
+  const mctx = addon.createMulti(curve, Int32Array.from(devices), maxPointsPerDevice);
+  const cb = coordBytes[curve];
+  async function run(scalars: Uint8Array, points: Points, N: number, c = 0): Promise<MsmResult> {
+    if (N > points.n) throw Error(`msm: N = ${N} exceeds the ${points.n} points held`);
+    const { xy, isZero, log } = await addon.msmSharded(mctx, scalars, N, c);
+    return { result: { x: fromLE(xy.subarray(0, cb)), y: fromLE(xy.subarray(cb, 2 * cb)), isZero }, log };
+  }
+  const Parallel = {
+    pointsFromBytes(bytes: Uint8Array): Points { const n = bytes.length / (2 * cb); addon.setPointsMulti(mctx, bytes, n); return { n }; },
+    randomPointsFast(n: number, seed = 0x6d6f6e74): Points { addon.randomPointsMulti(mctx, seed, n); return { n }; },
+    msm: (scalars: Uint8Array, points: Points, N: number, _verbose = false, { c = 0 } = {}) => run(scalars, points, N, c),
+    msmUnsafe: (scalars: Uint8Array, points: Points, N: number, _verbose = false, { c = 0 } = {}) => run(scalars, points, N, c),
+  };
+  return { Parallel };
+}
+
 // scripts/zprize23/submission-bls377.ts: byte inputs, points converted once and kept on the GPU
 const BLS12_377 = create(Curve.BLS12_377_G1);
 let cachedBytes: Uint8Array | undefined, cachedPoints: Points | undefined;

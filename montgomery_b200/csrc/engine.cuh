@@ -150,6 +150,15 @@ struct WeierstrassPolicy {
     if (inf) { x = F::zero(); y = F::zero(); return; }
     x = F::from_mont(p.x); y = F::from_mont(p.y);
   }
+  // the same called by ALL 32 lanes of a warp with the same accumulator: the one inversion runs on the lane-parallel
+  // division-step routine (warp.cuh, 20.6 us instead of 35.3 us on one lane); every lane returns the result
+  MGB_DEV static void acc_to_plain_warp(const acc& a, Fe<FP>& x, Fe<FP>& y, bool& inf) {
+    inf = G::acc_is_zero(a);                                  // warp-uniform
+    if (inf) { x = F::zero(); y = F::zero(); return; }
+    const Fe<FP> t = WarpField<FP>::inv_call(a.ZZZ);          // x = X / ZZ, y = Y / ZZZ: 1 / ZZ = t^2 ZZ^2 (ZZ^3 = ZZZ^2)
+    const Fe<FP> izz = F::mul(F::sqr(t), F::sqr(a.ZZ));
+    x = F::from_mont(F::mul(a.X, izz)); y = F::from_mont(F::mul(a.Y, t));
+  }
 };
 
 template <class FP, class CC>
@@ -208,6 +217,13 @@ struct TwistedEdwardsPolicy {
   MGB_DEV static void acc_to_plain(const acc& a, Fe<FP>& x, Fe<FP>& y, bool& inf) {
     Fe<FP> xm, ym; G::to_affine(a, xm, ym);
     x = F::from_mont(xm); y = F::from_mont(ym);
+    Fe<FP> o = F::zero(); o.v[0] = 1;
+    inf = F::is_zero(x) && F::eq(y, o);
+  }
+  // called by all 32 lanes of a warp with the same accumulator (lane-parallel inversion, see WeierstrassPolicy)
+  MGB_DEV static void acc_to_plain_warp(const acc& a, Fe<FP>& x, Fe<FP>& y, bool& inf) {
+    const Fe<FP> zi = WarpField<FP>::inv_call(a.Z);
+    x = F::from_mont(F::mul(a.X, zi)); y = F::from_mont(F::mul(a.Y, zi));
     Fe<FP> o = F::zero(); o.v[0] = 1;
     inf = F::is_zero(x) && F::eq(y, o);
   }
@@ -353,29 +369,52 @@ __global__ void __launch_bounds__(256) k_digits(MsmParams pr, uint32_t i_begin, 
   }
   const int c = pr.c;
   const uint32_t L = pr.L, cmask = (1u << c) - 1;
+  // digit w of half h -> bucket (NO_BUCKET for a zero digit) and "the digit is negative"
+  auto digit = [&](int h, int w, uint32_t& carry, bool& dneg) -> uint32_t {
+    const int bit = w * c;
+    const int limb = bit >> 5, sh = bit & 31;
+    uint32_t lo = 0, hi = 0;
+    _Pragma("unroll") for (int k = 0; k <= ML; k++) { if (k == limb) lo = mag[h][k]; if (k == limb + 1) hi = mag[h][k]; }
+    const uint32_t slice = (uint32_t)((((uint64_t)hi << 32) | lo) >> sh) & cmask;
+    uint32_t l = slice + carry;
+    dneg = false;
+    if (l > L) { l = 2 * L - l; carry = 1; dneg = true; } else carry = 0;
+    if (l == 0) return NO_BUCKET;
+    uint32_t bucket = (uint32_t)w * L + (l - 1);
+    if (w == pr.K - 1 && pr.top_sub) {
+      // sparse top window: spread each digit over 2^top_sub buckets of equal weight
+      if (l > (L >> pr.top_sub)) { atomicOr(&counts[pr.nbuckets], 1u); l = L >> pr.top_sub; }  // cannot happen for |k| < 2^(MAG_BITS-1)
+      bucket = (uint32_t)w * L + (((l - 1) << pr.top_sub) | ((2 * i + h) & ((1u << pr.top_sub) - 1)));
+    }
+    return bucket;
+  };
+  constexpr int KU = 12;       // windows handled with all their histogram atomics in flight at once
   _Pragma("unroll") for (int h = 0; h < CV::HALVES; h++) {
     uint32_t carry = 0;
-    for (int w = 0; w < pr.K; w++) {
-      int bit = w * c;
-      int limb = bit >> 5, sh = bit & 31;
-      uint32_t lo = 0, hi = 0;
-      _Pragma("unroll") for (int k = 0; k <= ML; k++) { if (k == limb) lo = mag[h][k]; if (k == limb + 1) hi = mag[h][k]; }
-      uint32_t slice = (uint32_t)((((uint64_t)hi << 32) | lo) >> sh) & cmask;
-      uint32_t l = slice + carry;
-      bool dneg = false;
-      if (l > L) { l = 2 * L - l; carry = 1; dneg = true; } else carry = 0;
-      uint32_t e = (uint32_t)(h * pr.K + w);
-      size_t pos = (size_t)e * pr.n + i;
-      if (l == 0) { ent_bucket[pos] = NO_BUCKET; continue; }
-      uint32_t bucket = (uint32_t)w * L + (l - 1);
-      if (w == pr.K - 1 && pr.top_sub) {
-        // sparse top window: spread each digit over 2^top_sub buckets of equal weight
-        if (l > (L >> pr.top_sub)) { atomicOr(&counts[pr.nbuckets], 1u); l = L >> pr.top_sub; }  // cannot happen for |k| < 2^(MAG_BITS-1)
-        bucket = (uint32_t)w * L + (((l - 1) << pr.top_sub) | ((2 * i + h) & ((1u << pr.top_sub) - 1)));
+    if (pr.K <= KU) {
+      // The rank of an entry is the value its histogram atomicAdd returns; issued one window at a time, a thread
+      // waits for ~K dependent round trips to L2.  Here the digits of a half are formed first, then all atomics are
+      // issued back to back, then the results are stored.
+      uint32_t bk[KU], rk[KU];
+      bool dn[KU];
+      _Pragma("unroll") for (int w = 0; w < KU; w++) { bk[w] = NO_BUCKET; dn[w] = false; if (w < pr.K) bk[w] = digit(h, w, carry, dn[w]); }
+      _Pragma("unroll") for (int w = 0; w < KU; w++) { rk[w] = 0; if (bk[w] != NO_BUCKET) rk[w] = atomicAdd(&counts[bk[w]], 1u); }
+      _Pragma("unroll") for (int w = 0; w < KU; w++) {
+        if (w >= pr.K) break;
+        const size_t pos = (size_t)(h * pr.K + w) * pr.n + i;
+        ent_bucket[pos] = bk[w];
+        if (bk[w] != NO_BUCKET) ent_rank[pos] = rk[w] | ((dn[w] != neg[h]) ? REF_NEG : 0u);  // rank < 2^31
       }
-      uint32_t rank = atomicAdd(&counts[bucket], 1u);
-      ent_bucket[pos] = bucket;
-      ent_rank[pos] = rank | ((dneg != neg[h]) ? REF_NEG : 0u);  // rank < 2^31
+    } else {
+      for (int w = 0; w < pr.K; w++) {
+        bool dneg;
+        const uint32_t bucket = digit(h, w, carry, dneg);
+        const size_t pos = (size_t)(h * pr.K + w) * pr.n + i;
+        ent_bucket[pos] = bucket;
+        if (bucket == NO_BUCKET) continue;
+        const uint32_t rank = atomicAdd(&counts[bucket], 1u);
+        ent_rank[pos] = rank | ((dneg != neg[h]) ? REF_NEG : 0u);  // rank < 2^31
+      }
     }
   }
 }
@@ -447,11 +486,17 @@ static __global__ void __launch_bounds__(SCAN_T) k_scan_sums(uint32_t* __restric
   }
   if (threadIdx.x == 0) *grand = carry;
 }
+// also writes (offset, count) of every bucket side by side: the scatter fetches both with ONE 8-byte gather per entry
 static __global__ void __launch_bounds__(SCAN_T) k_scan_add(uint32_t* __restrict__ offs, const uint32_t* __restrict__ tile_sums,
-                                                     uint32_t n, const uint32_t* __restrict__ grand) {
+                                                     uint32_t n, const uint32_t* __restrict__ grand,
+                                                     const uint32_t* __restrict__ counts, uint2* __restrict__ offcnt) {
   uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
   uint32_t add = tile_sums[blockIdx.x];
-  _Pragma("unroll") for (int k = 0; k < SCAN_ITEMS; k++) if (base + k < n) offs[base + k] += add;
+  _Pragma("unroll") for (int k = 0; k < SCAN_ITEMS; k++) if (base + k < n) {
+    const uint32_t o = offs[base + k] + add;
+    offs[base + k] = o;
+    offcnt[base + k] = make_uint2(o, counts[base + k]);
+  }
   if (blockIdx.x == 0 && threadIdx.x == 0) offs[n] = *grand;
 }
 
@@ -496,7 +541,7 @@ MGB_DEV void emit_pair(bool active, PairEnt ent, PairEnt* __restrict__ pairs, ui
 static constexpr int SCATTER_U = 4;
 template <class CV>
 __global__ void __launch_bounds__(256) k_scatter(MsmParams pr, int w_begin, int Kg, const uint32_t* __restrict__ ent_bucket, const uint32_t* __restrict__ ent_rank,
-                                                 const uint32_t* __restrict__ offs, const uint32_t* __restrict__ counts, const uint32_t* __restrict__ table,
+                                                 const uint2* __restrict__ offcnt /* (offset, count) per bucket */, const uint32_t* __restrict__ table,
                                                  uint32_t* __restrict__ V, uint32_t* __restrict__ recs /* 2 words per aligned slot pair */, uint8_t* __restrict__ lifes) {
   const uint32_t el = blockIdx.y;
   const uint32_t h = el / (uint32_t)Kg, w = (uint32_t)w_begin + el % (uint32_t)Kg;
@@ -510,7 +555,7 @@ __global__ void __launch_bounds__(256) k_scatter(MsmParams pr, int w_begin, int 
   }
   _Pragma("unroll") for (int u = 0; u < SCATTER_U; u++) {
     n[u] = 0; o[u] = 0;
-    if (b[u] != NO_BUCKET) { n[u] = counts[b[u]]; o[u] = offs[b[u]]; }
+    if (b[u] != NO_BUCKET) { const uint2 oc = offcnt[b[u]]; o[u] = oc.x; n[u] = oc.y; }
   }
   _Pragma("unroll") for (int u = 0; u < SCATTER_U; u++) {
     if (b[u] == NO_BUCKET) continue;
@@ -1207,8 +1252,11 @@ __global__ void __launch_bounds__(128) k_window_assemble(MsmParams pr, ReduceGeo
 
 // result = sum_w 2^(c*w) S_w by Horner (msm-batched-affine.ts:322-334): (K-1)*c dependent doublings.
 // One 128-thread block; the four warps share the multiplications of each formula level (coop.cuh).
+// out_xy != nullptr (single-GPU msm): the same warp also normalises -- canonical x || y and the is-zero flag, as
+// k_normalize would -- so the result needs no further launch.
 template <class CV>
-__global__ void __launch_bounds__(128) k_final(int K, int c, const uint32_t* __restrict__ Sw, uint32_t* __restrict__ out_acc) {
+__global__ void __launch_bounds__(128) k_final(int K, int c, const uint32_t* __restrict__ Sw, uint32_t* __restrict__ out_acc,
+                                               uint32_t* __restrict__ out_xy, uint32_t* __restrict__ out_flag) {
   typedef typename CV::P FP;
   constexpr int N = CV::N;
   __shared__ uint32_t sm[COOP_SLOTS * N];
@@ -1224,6 +1272,15 @@ __global__ void __launch_bounds__(128) k_final(int K, int c, const uint32_t* __r
       v = OW::add(v, ow_load<FP>(Sw + (size_t)w * CV::ACC_LIMBS));
     }
     ow_store<FP>(out_acc, v);
+    if (out_xy) {
+      Fe<FP> x, y;
+      bool inf;
+      CV::acc_to_plain_warp(OW::gather(v), x, y, inf);
+      if (threadIdx.x == 0) {
+        _Pragma("unroll") for (int i = 0; i < N; i++) { out_xy[i] = x.v[i]; out_xy[N + i] = y.v[i]; }
+        *out_flag = inf ? 1u : 0u;
+      }
+    }
     return;
   }
 #endif
@@ -1240,19 +1297,31 @@ __global__ void __launch_bounds__(128) k_final(int K, int c, const uint32_t* __r
     CV::Coop::add(m, &flag);
   }
   if (threadIdx.x < 4 * N) out_acc[threadIdx.x] = sm[threadIdx.x];
+  if (out_xy && threadIdx.x < 32) {
+    Fe<FP> x, y;
+    bool inf;
+    CV::acc_to_plain_warp(CV::ld_acc(sm), x, y, inf);
+    if (threadIdx.x == 0) {
+      _Pragma("unroll") for (int i = 0; i < N; i++) { out_xy[i] = x.v[i]; out_xy[N + i] = y.v[i]; }
+      *out_flag = inf ? 1u : 0u;
+    }
+  }
 }
 
-// sum `count` partial accumulators (multi-GPU combine) and/or normalise: out = canonical x||y + flag
+// sum `count` partial accumulators (multi-GPU combine) and/or normalise: out = canonical x||y + flag.  One warp: every
+// lane forms the same sum, the inversion of the normalisation is lane-parallel.
 template <class CV>
-__global__ void k_normalize(const uint32_t* __restrict__ accs, int count, uint32_t* __restrict__ out_xy, uint32_t* __restrict__ out_flag) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void __launch_bounds__(32) k_normalize(const uint32_t* __restrict__ accs, int count, uint32_t* __restrict__ out_xy, uint32_t* __restrict__ out_flag) {
+  if (blockIdx.x != 0) return;
   typename CV::acc res = CV::ld_acc(accs);
   for (int i = 1; i < count; i++) res = CV::add(res, CV::ld_acc(accs + (size_t)i * CV::ACC_LIMBS));
   Fe<typename CV::P> x, y;
   bool inf;
-  CV::acc_to_plain(res, x, y, inf);
-  _Pragma("unroll") for (int i = 0; i < CV::N; i++) { out_xy[i] = x.v[i]; out_xy[CV::N + i] = y.v[i]; }
-  *out_flag = inf ? 1u : 0u;
+  CV::acc_to_plain_warp(res, x, y, inf);
+  if (threadIdx.x == 0) {
+    _Pragma("unroll") for (int i = 0; i < CV::N; i++) { out_xy[i] = x.v[i]; out_xy[CV::N + i] = y.v[i]; }
+    *out_flag = inf ? 1u : 0u;
+  }
 }
 
 // ---------------------------------------------------------------- point ingestion / generation

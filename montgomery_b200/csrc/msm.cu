@@ -42,7 +42,7 @@ struct mgb_ctx {
   cudaStream_t aux[3] = {};          // extra streams: window groups are pipelined against each other
   cudaEvent_t ev_fork = nullptr, ev_plan = nullptr, ev_join[3] = {}, ev_chunk[4] = {};
   cudaEvent_t ev[EV_COUNT] = {};
-  DevBuf table, scalars, ent_bucket, ent_rank, counts, offs, tile_sums, pairs, pairs2, V, recs, lifes, prebuf, bsum, redU[2], redW[2], misc, acc_out, out_xy, stage;
+  DevBuf table, scalars, ent_bucket, ent_rank, counts, offs, offcnt, tile_sums, pairs, pairs2, V, recs, lifes, prebuf, bsum, redU[2], redW[2], misc, acc_out, out_xy, stage;
   uint32_t* h_pinned = nullptr;  // [0..31] out xy limbs + flag, [64..] misc readback
   int sm_count = 148;
   std::string err;
@@ -196,7 +196,7 @@ int get_points_impl(mgb_ctx* ctx, size_t first, size_t n, uint8_t* xy, uint8_t* 
 
 // Runs the pipeline; leaves the un-normalised result accumulator in ctx->acc_out.
 template <class CV>
-int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const mgb_opts* opts, mgb_timing* tm) {
+int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const mgb_opts* opts, mgb_timing* tm, bool normalize = false) {
   cudaStream_t st = ctx->stream;
   uint32_t launches = 0;
   int c = (opts && opts->c > 0) ? opts->c : default_window(CV::MAG_BITS, n);
@@ -264,6 +264,7 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   ENS(ctx, ctx->ent_rank, (size_t)pr.nent * 4);
   ENS(ctx, ctx->counts, ((size_t)pr.nbuckets + 1) * 4);
   ENS(ctx, ctx->offs, ((size_t)pr.nbuckets + 1) * 4);
+  ENS(ctx, ctx->offcnt, ((size_t)pr.nbuckets + 1) * 8);
   const uint32_t ntiles = cdiv(pr.nbuckets, SCAN_TILE);
   ENS(ctx, ctx->tile_sums, (size_t)ntiles * 4);
   // every non-empty bucket occupies an even number of slots (k_scan_tiles)
@@ -294,7 +295,7 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   // ---- bucket offsets; the totals come back to the host to size the rounds
   k_scan_tiles<<<ntiles, SCAN_T, 0, st>>>((const uint32_t*)ctx->counts.p, (uint32_t*)ctx->offs.p, (uint32_t*)ctx->tile_sums.p, pr.nbuckets, misc + 1, misc + 512);
   k_scan_sums<<<1, SCAN_T, 0, st>>>((uint32_t*)ctx->tile_sums.p, ntiles, misc);
-  k_scan_add<<<ntiles, SCAN_T, 0, st>>>((uint32_t*)ctx->offs.p, (const uint32_t*)ctx->tile_sums.p, pr.nbuckets, misc);
+  k_scan_add<<<ntiles, SCAN_T, 0, st>>>((uint32_t*)ctx->offs.p, (const uint32_t*)ctx->tile_sums.p, pr.nbuckets, misc, (const uint32_t*)ctx->counts.p, (uint2*)ctx->offcnt.p);
   launches += 3;
   CU(ctx, cudaGetLastError());
   CU(ctx, cudaMemcpyAsync(ctx->h_pinned + 64, misc, 8, cudaMemcpyDeviceToHost, st));
@@ -313,7 +314,7 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
     ENS(ctx, ctx->recs, (max_slots / 2 + 1) * 8);
     ENS(ctx, ctx->lifes, max_slots / 2 + 8);
     k_scatter<CV><<<dim3(cdiv(n, 256 * SCATTER_U), (unsigned)(CV::HALVES * pr.K)), 256, 0, st>>>(
-        pr, 0, pr.K, (const uint32_t*)ctx->ent_bucket.p, (const uint32_t*)ctx->ent_rank.p, (const uint32_t*)ctx->offs.p, (const uint32_t*)ctx->counts.p,
+        pr, 0, pr.K, (const uint32_t*)ctx->ent_bucket.p, (const uint32_t*)ctx->ent_rank.p, (const uint2*)ctx->offcnt.p,
         (const uint32_t*)ctx->table.p, nullptr, (uint32_t*)ctx->recs.p, (uint8_t*)ctx->lifes.p);
     launches++;
     CU(ctx, cudaGetLastError());
@@ -376,7 +377,7 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
     uint32_t* tcnt = misc + 264 + 64 * g;
     if (!(early_scatter && fuse)) {
       k_scatter<CV><<<dim3(cdiv(n, 256 * SCATTER_U), (unsigned)(CV::HALVES * Kg)), 256, 0, sg>>>(pr, w_begin, Kg, (const uint32_t*)ctx->ent_bucket.p, (const uint32_t*)ctx->ent_rank.p,
-                                                      offs, counts, table, fuse ? nullptr : (uint32_t*)ctx->V.p, recs, lifes);
+                                                      (const uint2*)ctx->offcnt.p, table, fuse ? nullptr : (uint32_t*)ctx->V.p, recs, lifes);
       launches++;
       if (g == 0) CU(ctx, cudaEventRecord(ctx->ev[EV_SORT], st));
     }
@@ -478,7 +479,9 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   for (int g = 1; g < G; g++) CU(ctx, cudaStreamWaitEvent(st, ctx->ev_join[g - 1], 0));
   CU(ctx, cudaGetLastError());
   CU(ctx, cudaEventRecord(ctx->ev[EV_REDUCE], st));
-  k_final<CV><<<1, 128, 0, st>>>(pr.K, pr.c, (const uint32_t*)ctx->redW[0].p, (uint32_t*)ctx->acc_out.p);
+  uint32_t* d_xy = nullptr;
+  if (normalize) { ENS(ctx, ctx->out_xy, 64 * 4); d_xy = (uint32_t*)ctx->out_xy.p; }
+  k_final<CV><<<1, 128, 0, st>>>(pr.K, pr.c, (const uint32_t*)ctx->redW[0].p, (uint32_t*)ctx->acc_out.p, d_xy, d_xy ? d_xy + 2 * CV::N : nullptr);
   launches++;
   CU(ctx, cudaGetLastError());
   if (tm) {
@@ -510,12 +513,15 @@ int finish_timing(mgb_ctx* ctx, mgb_timing* tm) {
   return 0;
 }
 
+// d_accs == nullptr: k_final has normalised already (msm_core with normalize = true), only the read-back is left
 template <class CV>
 int normalize_out(mgb_ctx* ctx, const void* d_accs, int count, uint8_t* out_xy, int* out_is_zero) {
   ENS(ctx, ctx->out_xy, 64 * 4);
   uint32_t* d = (uint32_t*)ctx->out_xy.p;
-  k_normalize<CV><<<1, 32, 0, ctx->stream>>>((const uint32_t*)d_accs, count, d, d + 2 * CV::N);
-  CU(ctx, cudaGetLastError());
+  if (d_accs) {
+    k_normalize<CV><<<1, 32, 0, ctx->stream>>>((const uint32_t*)d_accs, count, d, d + 2 * CV::N);
+    CU(ctx, cudaGetLastError());
+  }
   CU(ctx, cudaMemcpyAsync(ctx->h_pinned, d, (2 * CV::N + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CU(ctx, cudaEventRecord(ctx->ev[EV_FINAL], ctx->stream));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -533,11 +539,10 @@ int msm_impl(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
     if (out_is_zero) *out_is_zero = 1;
     return 0;
   }
-  int r = msm_core<CV>(ctx, scalars, on_device, n, opts, tm);
+  int r = msm_core<CV>(ctx, scalars, on_device, n, opts, tm, true);     // k_final normalises as well
   if (r) return r;
-  r = normalize_out<CV>(ctx, ctx->acc_out.p, 1, out_xy, out_is_zero);
+  r = normalize_out<CV>(ctx, nullptr, 1, out_xy, out_is_zero);
   if (r) return r;
-  if (tm) tm->n_launches += 1;
   return finish_timing(ctx, tm);
 }
 
@@ -577,10 +582,10 @@ int msm_sharded_impl(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n
     k_acc_neutral<CV><<<1, 32, 0, ctx->stream>>>((uint32_t*)ctx->acc_out.p);
     CU(ctx, cudaGetLastError());
   } else {
-    int r = msm_core<CV>(ctx, scalars, on_device, n, opts, tm);
+    int r = msm_core<CV>(ctx, scalars, on_device, n, opts, tm, ctx->comm_world == 1);
     if (r) return r;
   }
-  const void* partials = ctx->acc_out.p;
+  const void* partials = (ctx->comm_world == 1 && n) ? nullptr : ctx->acc_out.p;
   if (ctx->comm_world > 1) {
     NcclApi* api = nccl_api();
     if (!api || !ctx->comm) return fail(ctx, MGB_E_STATE, "sharded msm: the context has no communicator (mgb_comm_init)");
@@ -591,7 +596,7 @@ int msm_sharded_impl(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n
   }
   int r = normalize_out<CV>(ctx, partials, ctx->comm_world, out_xy, out_is_zero);
   if (r) return r;
-  if (tm) tm->n_launches += 1;
+  if (tm && partials) tm->n_launches += 1;
   if (ctx->comm) {     // asynchronous NCCL failures (a peer died, a transport error) surface here, not as a hang later
     NcclApi* api = nccl_api();
     ncclResult_t async = ncclSuccess;
@@ -875,7 +880,7 @@ void mgb_destroy(mgb_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->comm) { if (NcclApi* api = nccl_api()) api->CommDestroy(ctx->comm); ctx->comm = nullptr; }
   if (ctx->gathered.p) cudaFree(ctx->gathered.p);
-  DevBuf* bufs[] = {&ctx->table, &ctx->scalars, &ctx->ent_bucket, &ctx->ent_rank, &ctx->counts, &ctx->offs, &ctx->tile_sums, &ctx->pairs, &ctx->pairs2, &ctx->V, &ctx->recs, &ctx->lifes, &ctx->prebuf, &ctx->bsum, &ctx->redU[0], &ctx->redU[1], &ctx->redW[0], &ctx->redW[1], &ctx->misc,
+  DevBuf* bufs[] = {&ctx->table, &ctx->scalars, &ctx->ent_bucket, &ctx->ent_rank, &ctx->counts, &ctx->offs, &ctx->offcnt, &ctx->tile_sums, &ctx->pairs, &ctx->pairs2, &ctx->V, &ctx->recs, &ctx->lifes, &ctx->prebuf, &ctx->bsum, &ctx->redU[0], &ctx->redU[1], &ctx->redW[0], &ctx->redW[1], &ctx->misc,
                     &ctx->acc_out, &ctx->out_xy, &ctx->stage};
   for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);

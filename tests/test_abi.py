@@ -91,3 +91,16 @@ def test_c99_host_builds_and_links(tmp_path):
     if shutil.which("nvidia-smi") is None:
         res = subprocess.run([exe, "8"], capture_output=True, text=True)
         assert res.returncode == 3 and "mgb_create: -2" in res.stderr
+
+
+def test_node_addon_type_checks():
+    """bindings/node/addon.c (the N-API face a TypeScript host loads) against the C header: there is no Node.js in this image,
+    so the addon is type-checked with gcc against a stand-in for <node_api.h> that declares the N-API calls it uses
+    (tests/host_emu/node_api_stub/) -- every mgb_* call in it must match include/montgomery_b200.h."""
+    import subprocess
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "tests", "host_emu", "node_api_stub"),
+                           "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "bindings", "node", "addon.c")])
+    src = open(os.path.join(ROOT, "bindings", "node", "addon.c")).read()
+    for sym in ("mgb_create", "mgb_set_points", "mgb_random_points", "mgb_msm", "mgb_multi_create", "mgb_multi_set_points",
+                "mgb_multi_random_points", "mgb_multi_msm", "mgb_multi_destroy", "mgb_destroy"):
+        assert sym + "(" in src, sym

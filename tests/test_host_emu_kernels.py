@@ -165,7 +165,8 @@ def test_final_horner_kernel(emu_k, cid, prm, n):
         for v in coords:
             words += limbs(v)
     out = (U32 * (4 * n))()
-    emu_k.emu_final(cid, K, c, (U32 * len(words))(*words), out)
+    xy, flag = (U32 * (2 * n))(), (U32 * 1)(7)
+    emu_k.emu_final(cid, K, c, (U32 * len(words))(*words), out, xy, flag)
     X, Y, ZZ, ZZZ = [sum(int(out[k * n + i]) << (32 * i) for i in range(n)) * Ri % p for k in range(4)]
     got = None if ZZ == 0 else (X * pow(ZZ, -1, p) % p, Y * pow(ZZZ, -1, p) % p)
     exp = None
@@ -174,6 +175,18 @@ def test_final_horner_kernel(emu_k, cid, prm, n):
             exp = A.double(exp)
         exp = A.add(exp, S[w])
     assert got == exp
+    # the fused normalisation (single-GPU path): canonical plain coordinates + flag from the same launch
+    assert flag[0] == 0 and tuple(sum(int(xy[k * n + i]) << (32 * i) for i in range(n)) for k in range(2)) == exp
+    none = (U32 * (4 * n))()
+    emu_k.emu_final(cid, K, c, (U32 * len(words))(*words), none, None, None)       # multi-GPU path: accumulator only
+    assert list(none) == list(out)
+    # a sum that is the neutral element: flag 1, zero coordinates
+    zwords = []
+    for _ in range(2):
+        for v in (0, M(1), 0, 0):
+            zwords += limbs(v)
+    emu_k.emu_final(cid, 2, c, (U32 * len(zwords))(*zwords), out, xy, flag)
+    assert flag[0] == 1 and not any(xy)
 
 
 def test_final_horner_kernel_twisted_edwards(emu_k):
@@ -196,7 +209,8 @@ def test_final_horner_kernel_twisted_edwards(emu_k):
         for v in (M(x * z % p), M(y * z % p), M(z), M(x * y * z % p)):
             words += limbs(v)
     out = (U32 * (4 * n))()
-    emu_k.emu_final(3, K, c, (U32 * len(words))(*words), out)
+    xy, flag = (U32 * (2 * n))(), (U32 * 1)(7)
+    emu_k.emu_final(3, K, c, (U32 * len(words))(*words), out, xy, flag)
     X, Y, Z, Tt = [sum(int(out[k * n + i]) << (32 * i) for i in range(n)) * Ri % p for k in range(4)]
     zi = pow(Z, -1, p)
     exp = T.zero
@@ -205,6 +219,7 @@ def test_final_horner_kernel_twisted_edwards(emu_k):
             exp = T.double(exp)
         exp = T.add(exp, S[w])
     assert (X * zi % p, Y * zi % p) == T.to_affine(exp) and (X * Y - Tt * Z) % p == 0
+    assert flag[0] == 0 and tuple(sum(int(xy[k * n + i]) << (32 * i) for i in range(n)) for k in range(2)) == T.to_affine(exp)
 
 
 def test_pair_add_two_rounds_twisted_edwards(emu_k):
