@@ -154,6 +154,26 @@ def dist_setup(args):
     return rank, world, local
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this rank's host threads to the CPUs NVML reports as local to its GPU BEFORE any pinned host buffer is
+    allocated, so that the scalar buffers of the end-to-end path are first-touched on the GPU's own NUMA node (with
+    several ranks on one host the uploads otherwise cross the socket interconnect and contend with each other:
+    round 1 lost 12 % end to end at 8 GPUs).  Best effort: returns a short description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = (cpus & allowed) or allowed
+        os.sched_setaffinity(0, cpus)
+        return {"bound": True, "cpus": len(cpus), "of": ncpu}
+    except Exception as e:      # no NVML, container without the capability, ...
+        return {"bound": False, "why": str(e)[:80]}
+
+
 def cpu_reference_msm(label, points_bytes, scalars, n, threads):
     from oracle import cpu_ref
     res, ms = cpu_ref.msm(label, scalars, points_bytes, n, threads=threads)
@@ -205,6 +225,7 @@ def run_b200(args):
 
     rank, world, local = dist_setup(args)
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node = --gpus"
+    numa = bind_to_gpu_numa_node(local) if world > 1 else {"bound": False, "why": "single rank"}
     torch.cuda.set_device(local)
     dist = None
     # stdout carries exactly one JSON line: NCCL prints its version banner with a plain printf when a communicator
@@ -398,6 +419,7 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": "points/s", "ms_per_step": head["el_e2e"] / args.steps * 1e3,
                 "h2d_bytes_per_step": n * 32 * world, "d2h_bytes_per_step": (2 * curve.coord_bytes + 4) * world, "phases_ms": head["phases_e2e"]},
         "gpu_launches": head["launches"], "clocks": head["clocks"], "roofline": roofline, "hbm_phases": hbm,
+        "host_affinity": numa,
     }
     if configs:
         line["configs"] = configs

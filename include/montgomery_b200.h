@@ -58,6 +58,9 @@ typedef struct mgb_opts {
   int unsafe;
   int verbose;
   int projective;
+  int affine_reduction;   /* 1: bucket reduction by batched-affine additions (the reference's `reduceBucketsAffine`
+                             experiment, src/msm-batched-affine-single-thread.ts:522-700); batched-affine curves only,
+                             same result, slower on a B200 than the default (kept as a measured alternative) */
 } mgb_opts;
 
 /* Per-phase device times in milliseconds (CUDA events on the context's stream); the analogue of

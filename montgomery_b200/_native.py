@@ -14,7 +14,8 @@ BLS12_377_G1, PALLAS, ED_ON_BLS12_377, BLS12_381_G1 = 0, 1, 2, 3
 
 
 class MgbOpts(ctypes.Structure):
-    _fields_ = [("c", ctypes.c_int), ("unsafe", ctypes.c_int), ("verbose", ctypes.c_int), ("projective", ctypes.c_int)]
+    _fields_ = [("c", ctypes.c_int), ("unsafe", ctypes.c_int), ("verbose", ctypes.c_int), ("projective", ctypes.c_int),
+                ("affine_reduction", ctypes.c_int)]
 
 
 class MgbTiming(ctypes.Structure):

@@ -94,15 +94,15 @@ class MsmEngine:
         return xy.reshape(n, self.curve.point_bytes), z
 
     # ---- msm
-    def _opts(self, c, unsafe, projective=False):
-        return _native.MgbOpts(int(c or 0), int(bool(unsafe)), 0, int(bool(projective)))
+    def _opts(self, c, unsafe, projective=False, affine_reduction=False):
+        return _native.MgbOpts(int(c or 0), int(bool(unsafe)), 0, int(bool(projective)), int(bool(affine_reduction)))
 
-    def msm(self, scalars, n=None, c=None, unsafe=False, device_ptr=None, projective=False):
+    def msm(self, scalars, n=None, c=None, unsafe=False, device_ptr=None, projective=False, affine_reduction=False):
         """scalars: (n, 32) uint8 host array (or bytes); or device_ptr = raw device pointer."""
         out = np.zeros(self.curve.point_bytes, dtype=np.uint8)
         is_zero = ctypes.c_int(0)
         tm = _native.MgbTiming()
-        opts = self._opts(c, unsafe, projective)
+        opts = self._opts(c, unsafe, projective, affine_reduction)
         if device_ptr is not None:
             if n is None:
                 raise ValueError("msm(device_ptr=...): n is required (the length of a raw device buffer is unknown)")
@@ -215,7 +215,7 @@ class MultiGpuMsm:
         out = np.zeros(self.curve.point_bytes, dtype=np.uint8)
         is_zero = ctypes.c_int(0)
         tm = _native.MgbTiming()
-        opts = _native.MgbOpts(int(c or 0), 0, 0, 0)
+        opts = _native.MgbOpts(int(c or 0), 0, 0, 0, 0)
         self._check(self.lib.mgb_multi_msm(self._h, _ptr(sc), n, ctypes.byref(opts), _ptr(out), ctypes.byref(is_zero), ctypes.byref(tm)))
         cb = self.curve.coord_bytes
         return {"x": int.from_bytes(out[:cb].tobytes(), "little"), "y": int.from_bytes(out[cb:].tobytes(), "little"),
@@ -282,7 +282,7 @@ class _Parallel:
         if N > points.n:
             raise ValueError("msm: N = %d exceeds the %d points of the set" % (N, points.n))
         res, tm = points.engine.msm(scalars[:N] if isinstance(scalars, np.ndarray) else scalars, n=N, c=options.get("c"),
-                                    unsafe=not options.get("useSafeAdditions", True))
+                                    unsafe=not options.get("useSafeAdditions", True), affine_reduction=bool(options.get("affineReduction")))
         log = _log_from_timing(tm)
         if verboseTiming:
             for row in log:

@@ -1063,6 +1063,68 @@ __global__ void __launch_bounds__(128) k_group_partial(MsmParams pr, ReduceGeom 
   CV::st_acc(P + (size_t)t * CV::ACC_LIMBS, acc);
 }
 
+// ---- affine bucket reduction (reference: reduceBucketsAffine, src/msm-batched-affine-single-thread.ts:522-700,
+// doc/zprize22.md:317-358: "reducing buckets into one sum per partition, using only batch-affine additions").
+// The reference splits every window into independent sub-sums so that the reduction, too, amortises one inversion over
+// many additions.  The GPU form of the idea, on top of the digit decomposition above: the members of a group
+// (window w, digit d, value v) are gathered side by side into a scratch array W, GS slots per group (bucket sums are
+// single affine points once the bucket trees have run to completion; empty buckets and padding are the point at
+// infinity), and every group is summed by the SAME in-place log-depth tree of batched-affine additions that sums the
+// buckets (k_batch_add over pair lists: slot j of a group absorbs j + 2^r in round r).  All D K L additions that touch a
+// bucket cost 6 multiplications instead of the 10 - 14 of the XYZZ formulas; what is left for XYZZ are the few hundred
+// group sums themselves.  Opt-in (mgb_opts.affine_reduction): log2(GS) extra launches, each a round of at most
+// 0.4 M additions, cost more latency than the multiplications they save (measured, profiles/r02_ab_affine_reduction.txt).
+// Slots per group: GS0 for the windows below the top one, GS1 for the top window (its digits are clipped when the top
+// window is sparse and spread over sub-buckets, MsmParams::top_sub, so its groups can be larger).  Groups lie back to back.
+struct AffineRedGeom {
+  int GS0, GS1;
+  uint32_t g_top;        // first group of the top window = (K - 1) * D * 32
+  uint32_t n0;           // slots of the groups below it = g_top * GS0
+  uint32_t total;        // all slots
+};
+MGB_DEV uint32_t affine_group_base(const AffineRedGeom& ag, uint32_t g) {
+  return g < ag.g_top ? g * (uint32_t)ag.GS0 : ag.n0 + (g - ag.g_top) * (uint32_t)ag.GS1;
+}
+template <class CV>
+__global__ void __launch_bounds__(256) k_affine_gather(MsmParams pr, ReduceGeom gm, AffineRedGeom ag, const uint32_t* __restrict__ V,
+                                                       const uint32_t* __restrict__ offs, const uint32_t* __restrict__ counts,
+                                                       uint32_t* __restrict__ W, PairEnt* __restrict__ pairs, uint32_t* __restrict__ npairs) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ag.total) return;
+  const bool top = t >= ag.n0;
+  const int GS = top ? ag.GS1 : ag.GS0;
+  const uint32_t tt = top ? t - ag.n0 : t;
+  const uint32_t m = tt & (uint32_t)(GS - 1), g = (top ? ag.g_top : 0u) + tt / (uint32_t)GS;
+  const uint32_t v = g & 31, wd = g >> 5;
+  const uint32_t d = wd % gm.D, w = wd / gm.D;
+  const int sub = (w == (uint32_t)pr.K - 1) ? pr.top_sub : 0;
+  const int nb = pr.c - 1;
+  const int sh = min(gm.shift[d] + sub, nb);
+  const int wdt = min(gm.width[d], nb - sh);
+  const uint32_t gsize = pr.L >> wdt;
+  typename CV::vpoint pt = CV::G::affine_inf();
+  if (v < (1u << wdt) && !(wdt == 0 && d > 0) && m < gsize) {
+    const uint32_t low = m & ((1u << sh) - 1), high = m >> sh;
+    const uint32_t b = w * pr.L + ((high << (sh + wdt)) | (v << sh) | low);
+    if (counts[b]) pt = CV::load_v(V, offs[b]);        // the bucket's sum sits in its first slot after the last tree round
+  }
+  CV::store_v(W, t, pt);
+  if ((m & 1) == 0) {                                   // round 0 of the group trees: every even slot is a left operand
+    int lg = 0;
+    while ((1 << lg) < GS) lg++;
+    const uint32_t life = m ? (uint32_t)(__ffs(m) - 1) : (uint32_t)lg;
+    pairs[t >> 1] = PairEnt{t, life};
+  }
+  if (t == 0) *npairs = ag.total >> 1;
+}
+// group sums (first slot of every group in W) -> XYZZ partial sums P[g] (NP = 1) for k_digit_sums
+template <class CV>
+__global__ void __launch_bounds__(128) k_affine_group_sums(uint32_t ngroups, AffineRedGeom ag, const uint32_t* __restrict__ W, uint32_t* __restrict__ P) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ngroups) return;
+  CV::st_acc(P + (size_t)g * CV::ACC_LIMBS, CV::G::from_affine(CV::load_v(W, affine_group_base(ag, g))));
+}
+
 // one tree level: P[g][i] += P[g][i + half] for i < half
 template <class CV>
 __global__ void __launch_bounds__(128) k_tree_round(uint32_t ngroups, int NP, int half, uint32_t* __restrict__ P) {

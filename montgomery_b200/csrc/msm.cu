@@ -42,7 +42,7 @@ struct mgb_ctx {
   cudaStream_t aux[3] = {};          // extra streams: window groups are pipelined against each other
   cudaEvent_t ev_fork = nullptr, ev_plan = nullptr, ev_join[3] = {}, ev_chunk[4] = {};
   cudaEvent_t ev[EV_COUNT] = {};
-  DevBuf table, scalars, ent_bucket, ent_rank, counts, offs, offcnt, tile_sums, pairs, pairs2, V, recs, lifes, prebuf, bsum, redU[2], redW[2], misc, acc_out, out_xy, stage;
+  DevBuf table, scalars, ent_bucket, ent_rank, counts, offs, offcnt, tile_sums, pairs, pairs2, V, W, recs, lifes, prebuf, bsum, redU[2], redW[2], misc, acc_out, out_xy, stage;
   uint32_t* h_pinned = nullptr;  // [0..31] out xy limbs + flag, [64..] misc readback
   int sm_count = 148;
   std::string err;
@@ -139,17 +139,24 @@ int ensure(mgb_ctx* ctx, DevBuf& b, size_t bytes) {
 }
 #define ENS(ctx, buf, bytes) do { int r_ = ensure(ctx, buf, bytes); if (r_) return r_; } while (0)
 
-// Window size.  Large inputs: log2(n) - 4, i.e. an average bucket of ~64 half-scalars (GLV) -- enough
-// for the batched additions to amortise their inversions, few enough buckets for the reduction
-// (measured at 2^20: c = 15 / 16 / 17 -> 10.8 / 9.1 / 9.9 ms).  Small inputs are bound by the latency
-// of a round, not by throughput, so they take log2(n) - 2: smaller buckets, two rounds fewer
-// (measured at 2^16: c = 12 / 14 -> 2.65 / 2.41 ms).  A sparse top window is balanced by sub-bucket
-// spreading (MsmParams::top_sub), not avoided.  The reference's own table (msm-common.ts:25-41) is
-// tuned for 16 CPU threads and is not used here.
-int default_window(int /*mag_bits*/, size_t n) {
+// Window size, from sweeps on a B200 (profiles/r02_window_sweeps_*.txt).  Two things decide it: the accumulation cost
+// falls with c (fewer windows, 2 n K entries), the reduction cost is a function of the bucket count K 2^(c-1) alone and
+// does not shrink with n (0.36 / 0.48 / 0.78 / 0.89 / 1.6 / 2.4 / 4.0 / 7.8 ms for c = 12 .. 20, whatever n is).  For the
+// GLV curves c = 16 is special: K = 8 windows cover the 127/128-bit half-scalars exactly, so it wins from 2^18 to
+// 2^21 points (2^21: 10.4 ms against 11.9 ms at c = 17); below, the latency-bound reduction asks for few buckets, above,
+// c = 18 (K = 8 again, sparse top window).  Curves without the decomposition (twisted Edwards, msmProjective: ~252-bit
+// scalars) keep log2(n) - 4 from 2^18 on and log2(n) - 2 below (2^16 / 2^18 / 2^20: c = 14 / 14 / 16 measured best).
+// A sparse top window is balanced by sub-bucket spreading (MsmParams::top_sub), not avoided.  The reference's own table
+// (msm-common.ts:25-41) is tuned for 16 CPU threads and is not used here; opts.c overrides everything.
+int default_window(bool glv, size_t n) {
   int lg = 0;
   while (((size_t)1 << lg) < n) lg++;
-  const int c = lg >= 18 ? lg - 4 : lg - 2;
+  int c;
+  if (!glv || lg < 14) c = lg >= 18 ? lg - 4 : lg - 2;
+  else if (lg <= 15) c = 12;
+  else if (lg <= 17) c = 13;
+  else if (lg <= 21) c = 16;
+  else c = 18;
   return std::max(5, std::min(c, 22));
 }
 
@@ -199,7 +206,7 @@ template <class CV>
 int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const mgb_opts* opts, mgb_timing* tm, bool normalize = false) {
   cudaStream_t st = ctx->stream;
   uint32_t launches = 0;
-  int c = (opts && opts->c > 0) ? opts->c : default_window(CV::MAG_BITS, n);
+  int c = (opts && opts->c > 0) ? opts->c : default_window(CV::USE_GLV, n);
   if (c < 2 || c > 24) return fail(ctx, MGB_E_INVALID, "window size c must be in [2, 24]");
   MsmParams pr;
   pr.n = (uint32_t)n;
@@ -229,7 +236,8 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
     const uint32_t gmax = pr.L >> minw;        // largest group
     // buckets per partial sum: more of the (throughput-bound) first tree level folded into k_group_partial
     // when there are buckets enough to keep every SM busy anyway (measured at 2^18 / 2^20 / 2^22 points: 2 / 4 / 4 best)
-    gm.CH = pr.nbuckets >= (1u << 18) ? 4 : 2;
+    // (profiles/r02_ab_reduction_chunk.txt: CH = 1 / 2 / 4 at 2^16, c = 13: reduce 0.46 / 0.48 / 0.55 ms; 2^18, c = 16: 1.08 / 1.01 / 0.96 ms)
+    gm.CH = pr.nbuckets >= (1u << 18) ? 4 : (pr.nbuckets >= (1u << 15) ? 1 : 2);
     if (const char* ev = getenv("MGB_DEBUG_CH")) gm.CH = std::max(1, atoi(ev));
     gm.NP = 1;
     while ((uint32_t)gm.NP * gm.CH < gmax) gm.NP <<= 1;
@@ -341,6 +349,9 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   while (rounds < r_full && rounds < SCAN_ROUNDS && round_pairs[rounds] >= min_pairs) rounds++;
   rounds = std::max(rounds, r_full - 4);
   if (opts && opts->verbose > 1) rounds = r_full;
+  // affine bucket reduction (opt-in): the bucket trees run to completion, every bucket sum is one affine point
+  const bool affine_red = CV::BATCH_AFFINE && opts && opts->affine_reduction && G == 1;
+  if (affine_red) rounds = r_full;
   if (const char* ev = getenv("MGB_DEBUG_NROUNDS")) rounds = std::max(0, std::min(r_full, atoi(ev)));   // tuning aid
   // Elements a bucket has left after the last round are summed once by k_bucket_finish when there are many of them
   // (otherwise k_group_partial adds the single leftover directly as a mixed addition, which is cheaper).
@@ -446,6 +457,57 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
     const uint32_t ngroups_g = (uint32_t)Kg * gm.D * 32;
     uint32_t* Pg = (uint32_t*)ctx->redU[0].p + (size_t)w_begin * gm.D * 32 * gm.NP * CV::ACC_LIMBS;
     const uint32_t* bsum = nullptr;
+    bool reduced_affine = false;
+    if constexpr (CV::BATCH_AFFINE) {
+      if (affine_red) {
+        constexpr int EMAX = MGB_EMAX, MINB = MGB_MINB;
+        int minw = 32, minw_top = 32;
+        for (int d = 0; d < gm.D; d++) {
+          minw = std::min(minw, gm.width[d]);
+          const int nbits = c - 1, shd = std::min(gm.shift[d] + pr.top_sub, nbits), wdt = std::min(gm.width[d], nbits - shd);
+          if (!(wdt == 0 && d > 0)) minw_top = std::min(minw_top, wdt);
+        }
+        AffineRedGeom ag;
+        ag.GS0 = 2;                                                          // at least two slots: every even slot is a pair-list entry
+        while ((uint32_t)ag.GS0 < (pr.L >> minw)) ag.GS0 <<= 1;               // slots per group (largest group, power of two)
+        ag.GS1 = 2;
+        while ((uint32_t)ag.GS1 < (pr.L >> minw_top)) ag.GS1 <<= 1;           // the same for the (possibly clipped) top window
+        ag.g_top = (uint32_t)(pr.K - 1) * gm.D * 32;
+        ag.n0 = ag.g_top * (uint32_t)ag.GS0;
+        const size_t nslots = (size_t)ag.n0 + (size_t)gm.D * 32 * ag.GS1;
+        if (nslots >= (1ull << 31)) return fail(ctx, MGB_E_INVALID, "affine_reduction: too many group slots for this window size");
+        ag.total = (uint32_t)nslots;
+        const int GSmax = std::max(ag.GS0, ag.GS1);
+        ENS(ctx, ctx->W, nslots * CV::V_LIMBS * 4);
+        ENS(ctx, ctx->pairs, (nslots / 2 + 8) * sizeof(PairEnt));
+        ENS(ctx, ctx->pairs2, (nslots / 4 + 8) * sizeof(PairEnt));
+        PairEnt* apl[2] = {(PairEnt*)ctx->pairs.p, (PairEnt*)ctx->pairs2.p};   // round r reads apl[r & 1], writes apl[(r & 1) ^ 1]
+        uint32_t* acnt = misc + 700;                                           // pair counts of the group-tree rounds
+        uint32_t* atcnt = misc + 800;                                          // their tile counters
+        k_affine_gather<CV><<<cdiv(nslots, 256), 256, 0, sg>>>(pr, gm, ag, (const uint32_t*)ctx->V.p, offs, counts, (uint32_t*)ctx->W.p, apl[0], acnt);
+        launches++;
+        const uint64_t warps = (uint64_t)ctx->sm_count * MINB * 4;
+        const size_t pre_bytes = (size_t)ctx->sm_count * MINB * 4 * EMAX * (CV::N / 4) * 32 * 16;
+        ENS(ctx, ctx->prebuf, pre_bytes * 4);
+        int r = 0;
+        for (size_t np = nslots / 2; np >= 1 && (1 << r) < GSmax; np >>= 1, r++) {
+          const uint64_t per_lane = std::max<uint64_t>(1, (np + 32 * warps - 1) / (32 * warps));
+          const uint64_t kt = std::max<uint64_t>((per_lane + EMAX - 1) / EMAX, per_lane > 32 ? 2 : 1);
+          const int E = (int)std::min<uint64_t>(EMAX, std::max<uint64_t>(4, (per_lane + kt - 1) / kt));
+          auto kern = k_batch_add<CV, EMAX, MINB, false>;
+          cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, MINB > 4 ? 90 : 75);
+          kern<<<ctx->sm_count * MINB, 128, 0, sg>>>((uint32_t*)ctx->W.p, apl[r & 1], acnt + r, r, E, 0xffffffffu, apl[(r & 1) ^ 1], acnt + r + 1, atcnt + r,
+                                                    nullptr, nullptr, nullptr, nullptr, 0, 0, (uint4*)ctx->prebuf.p);
+          launches++;
+        }
+        k_affine_group_sums<CV><<<cdiv(ngroups_g, 128), 128, 0, sg>>>(ngroups_g, ag, (const uint32_t*)ctx->W.p, (uint32_t*)ctx->redU[0].p);
+        launches++;
+        reduced_affine = true;
+      }
+    }
+    ReduceGeom gmr = gm;                       // geometry seen by the digit sums: one partial sum per group after the affine trees
+    if (reduced_affine) gmr.NP = 1;
+    if (!reduced_affine) {
     if (use_finish) {
       ENS(ctx, ctx->bsum, (size_t)pr.nbuckets * CV::ACC_LIMBS * 4);
       k_bucket_finish<CV><<<cdiv(b_end - b_begin, 128), 128, 0, sg>>>(b_begin, b_end, rounds, (const uint32_t*)ctx->V.p, offs, counts, (uint32_t*)ctx->bsum.p);
@@ -455,7 +517,8 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
     k_group_partial<CV><<<cdiv(ngroups_g * gm.NP, 128), 128, 0, sg>>>(pr, gm, w_begin, Kg, rounds, (const uint32_t*)ctx->V.p, offs, counts, bsum,
                                                                      (uint32_t*)ctx->redU[0].p);
     launches++;
-    int remaining = gm.NP;
+    }
+    int remaining = gmr.NP;
     for (; remaining > 32; remaining >>= 1) {
       k_tree_round<CV><<<cdiv((size_t)ngroups_g * (remaining / 2), 128), 128, 0, sg>>>(ngroups_g, gm.NP, remaining / 2, Pg);
       launches++;
@@ -463,7 +526,7 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
     if constexpr (CV::BATCH_AFFINE) {
       // latency-bound stages, four lanes per point addition (coop.cuh): last tree levels, digit sums, per-window assembly
       if (remaining > 1) { k_tree_tail_quad<CV><<<ngroups_g, 64, 0, sg>>>(gm.NP, remaining, Pg); launches++; }
-      k_digit_sums<CV><<<Kg * gm.D, 128, 0, sg>>>(pr, gm, w_begin, (const uint32_t*)ctx->redU[0].p, (uint32_t*)ctx->redW[1].p);
+      k_digit_sums<CV><<<Kg * gm.D, 128, 0, sg>>>(pr, gmr, w_begin, (const uint32_t*)ctx->redU[0].p, (uint32_t*)ctx->redW[1].p);
       k_window_assemble<CV><<<Kg, 128, 0, sg>>>(pr, gm, w_begin, (const uint32_t*)ctx->redW[1].p, (uint32_t*)ctx->redW[0].p);
       launches += 2;
     } else {
@@ -503,12 +566,15 @@ int finish_timing(mgb_ctx* ctx, mgb_timing* tm) {
   tm->total = el(EV_START, EV_FINAL);
   // additions done by the tree rounds: exact per-round counts from the scan (rounds beyond SCAN_ROUNDS -- heavily
   // skewed inputs only -- from the pair-list counters)
-  uint32_t h[1024];
-  CU(ctx, cudaMemcpy(h, (uint32_t*)ctx->misc.p, sizeof(h), cudaMemcpyDeviceToHost));
   uint64_t s = 0;
-  for (int r = 0; r < tm->rounds && r < SCAN_ROUNDS; r++) s += h[512 + r];
-  for (int g = 0; g < 4; g++)
-    for (int r = SCAN_ROUNDS; r < tm->rounds && r < 63; r++) s += h[8 + 64 * g + r];
+  const uint32_t* round_pairs = ctx->h_pinned + 68;      // read back by msm_core before the rounds were sized
+  for (int r = 0; r < tm->rounds && r < SCAN_ROUNDS; r++) s += round_pairs[r];
+  if (tm->rounds > SCAN_ROUNDS) {                        // heavily skewed inputs only: a blocking copy of the counters
+    uint32_t h[1024];
+    CU(ctx, cudaMemcpy(h, (uint32_t*)ctx->misc.p, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int g = 0; g < 4; g++)
+      for (int r = SCAN_ROUNDS; r < tm->rounds && r < 63; r++) s += h[8 + 64 * g + r];
+  }
   tm->n_pairs = s;
   return 0;
 }
@@ -880,7 +946,7 @@ void mgb_destroy(mgb_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->comm) { if (NcclApi* api = nccl_api()) api->CommDestroy(ctx->comm); ctx->comm = nullptr; }
   if (ctx->gathered.p) cudaFree(ctx->gathered.p);
-  DevBuf* bufs[] = {&ctx->table, &ctx->scalars, &ctx->ent_bucket, &ctx->ent_rank, &ctx->counts, &ctx->offs, &ctx->offcnt, &ctx->tile_sums, &ctx->pairs, &ctx->pairs2, &ctx->V, &ctx->recs, &ctx->lifes, &ctx->prebuf, &ctx->bsum, &ctx->redU[0], &ctx->redU[1], &ctx->redW[0], &ctx->redW[1], &ctx->misc,
+  DevBuf* bufs[] = {&ctx->table, &ctx->scalars, &ctx->ent_bucket, &ctx->ent_rank, &ctx->counts, &ctx->offs, &ctx->offcnt, &ctx->tile_sums, &ctx->pairs, &ctx->pairs2, &ctx->V, &ctx->W, &ctx->recs, &ctx->lifes, &ctx->prebuf, &ctx->bsum, &ctx->redU[0], &ctx->redU[1], &ctx->redW[0], &ctx->redW[1], &ctx->misc,
                     &ctx->acc_out, &ctx->out_xy, &ctx->stage};
   for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);

@@ -248,3 +248,41 @@ def test_closed_form_beyond_the_reference_limit(logn):
         assert tm["n_pairs"] > 10 * n
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("label", ["bls12-377", "pallas", "bls12-381"])
+def test_affine_bucket_reduction_equals_default(label):
+    """mgb_opts.affine_reduction (the reference's reduceBucketsAffine idea): group sums by batched-affine
+    trees instead of XYZZ additions -- same canonical point as the default reduction and as the oracle, for several
+    sizes, window sizes (incl. a sparse, sub-bucket-spread top window) and degenerate inputs."""
+    cv = CURVES[label]
+    O = OracleCurve(label)
+    n = 1 << 13
+    eng = m.MsmEngine(cv, 0, n)
+    try:
+        eng.random_points(n, seed=60)
+        sc = inputs.random_scalars(cv.q, n, 61)
+        for k, c in [(n, None), (n, 7), (n, 11), (n, 14), (3000, 9), (257, 5), (64, None), (1, None)]:
+            ref, _ = eng.msm(sc[:k], n=k, c=c)
+            got, tm = eng.msm(sc[:k], n=k, c=c, affine_reduction=True)
+            assert got == ref, (label, k, c)
+        assert got == O.result_of(O.scale(int.from_bytes(sc[0].tobytes(), "little") * int(inputs.known_dlogs(60, 1)[0]), O.G))
+        assert closed_form(label, [(60, sc)]) == eng.msm(sc, n=n, affine_reduction=True)[0]
+        # all scalars equal (one huge bucket per window, everything else empty), zeros, and P + (-P) inside a group
+        same = np.repeat(sc[:1], n, axis=0)
+        assert eng.msm(same, n=n, affine_reduction=True)[0] == eng.msm(same, n=n)[0]
+        zeros = np.zeros((n, 32), dtype=np.uint8)
+        assert eng.msm(zeros, n=n, affine_reduction=True)[0]["isZero"]
+        q1 = scalars_to_bytes([1, cv.q - 1] * (n // 2))       # pairs s, -s over different points: no cancellation expected, just signs
+        assert eng.msm(q1, n=n, affine_reduction=True)[0] == eng.msm(q1, n=n)[0]
+    finally:
+        eng.close()
+    # the twisted-Edwards engine has no batched-affine path: the flag is accepted and ignored
+    cv = CURVES["ed-on-bls12-377"]
+    eng = m.MsmEngine(cv, 0, 512)
+    try:
+        eng.random_points(512, seed=62)
+        sc = inputs.random_scalars(cv.q, 512, 63)
+        assert eng.msm(sc, affine_reduction=True)[0] == eng.msm(sc)[0]
+    finally:
+        eng.close()
