@@ -22,10 +22,15 @@ namespace mgb {
 // negation it folds the sign into the modulus immediates and splits every modulus product into
 // IMAD.X + IMAD.HI.U32.X (6 issue cycles on the multiplier pipe) instead of one IMAD.WIDE.U32.X
 // (4 cycles) -- measured +24% on the whole multiplication.
+// c_mgb_zero: a zero in constant memory, i.e. one the compiler must treat as unknown.  "x + 0 + carry" with a literal
+// zero becomes IMAD.X (multiplier pipe), with this zero as the addend IADD3.X (ALU pipe); the multiplier pipe is what
+// bounds the accumulation kernel (ncu: 88 % busy), the ALU pipe is a quarter busy.  See mul_impl.
 #ifdef MGB_HOST_EMU
 static const uint32_t c_mgb_minv[4] = MGB_MINV_TABLE;
+static const uint32_t c_mgb_zero = 0;
 #else
 static __device__ __constant__ uint32_t c_mgb_minv[4] = MGB_MINV_TABLE;
+static __device__ __constant__ uint32_t c_mgb_zero = 0;
 #endif
 
 template <class P>
@@ -121,6 +126,10 @@ struct Field {
       a2[0] = a[0] << 1;
       _Pragma("unroll") for (int j = 1; j < N; j++) a2[j] = (a[j] << 1) | (a[j - 1] >> 31);
     }
+    // A zero the compiler cannot see through (c_mgb_zero).  The two carry absorbers of every row
+    // are "x + 0 + carry": with a literal 0 ptxas emits IMAD.X (multiplier pipe, the bottleneck), with an opaque
+    // register addend it emits IADD3.X (ALU pipe) -- 22 multiplier-pipe instructions fewer per product.
+    const uint32_t zr = c_mgb_zero;
     uint32_t X[N], Y[N];
     _Pragma("unroll") for (int i = 0; i < N; i++) {
       uint32_t* E = (i & 1) ? Y : X;
@@ -156,9 +165,14 @@ struct Field {
           first = false;
         }
         if (first) O[N - 1] = ptx::add_cc(O[N - 1], 0);   // (cannot happen: row N-1 still has a product with j >= i)
-        O[N - 1] = ptx::addc(O[N - 1], 0);
+        O[N - 1] = ptx::addc(O[N - 1], zr);
       }
-      const uint32_t m = E[0] * c_mgb_minv[P::ID];
+      // Quotient digit m = -t0 / p mod 2^32.  For the moduli with p = 1 mod 2^32 that is a negation: formed as
+      // zr - t0 with the opaque zero (ptxas must not learn that m = -t0: see the note at c_mgb_minv), it is one IADD3 on the
+      // ALU pipe instead of an IMAD on the multiplier pipe (12 of a product's 320 multiplier-pipe instructions).
+      uint32_t m;
+      if constexpr (P::mod(0) == 1u) m = zr - E[0];
+      else m = E[0] * c_mgb_minv[P::ID];
       // Modulus limbs that are zero or a power of two (Pallas: p_4..p_6 = 0, p_7 = 1 << 30) do not go through the
       // multiplier: the 64-bit product m * p_j is two shifts on the ALU pipe and enters the carry chain as a plain addend.
       uint32_t clo[N], chi[N];
@@ -204,7 +218,7 @@ struct Field {
           E[j + 1] = ptx::madc_hi_cc(P::mod(j), m, E[j + 1]);
         }
       });
-      O[N - 1] = ptx::addc(O[N - 1], 0);
+      O[N - 1] = ptx::addc(O[N - 1], zr);
     }
     uint32_t* E = ((N - 1) & 1) ? Y : X;
     uint32_t* O = ((N - 1) & 1) ? X : Y;
