@@ -693,6 +693,7 @@ size_t entry_bytes(int curve) {
 int msm_common(mgb_ctx* ctx, const void* scalars, bool dev, size_t n, const mgb_opts* opts, uint8_t* out_xy, int* out_is_zero, mgb_timing* tm) {
   if (!ctx || !out_xy || (!scalars && n)) return fail(ctx, MGB_E_INVALID, "mgb_msm: NULL argument");
   if (n > ctx->npoints) return fail(ctx, ctx->npoints ? MGB_E_INVALID : MGB_E_STATE, "mgb_msm: n exceeds the number of points set");
+  if (dev && ((uintptr_t)scalars & 15)) return fail(ctx, MGB_E_INVALID, "mgb_msm_device: the device scalar buffer must be 16-byte aligned");
   CU(ctx, cudaSetDevice(ctx->device));
   if (opts && opts->projective) {
     if (ctx->curve == MGB_BLS12_377_G1) return msm_impl<CurveBls377Basic>(ctx, scalars, dev, n, opts, out_xy, out_is_zero, tm);
@@ -808,6 +809,7 @@ size_t mgb_partial_bytes(const mgb_ctx* ctx) {
 int mgb_msm_partial(mgb_ctx* ctx, const void* scalars, int scalars_on_device, size_t n, const mgb_opts* opts, void* d_partial_out, mgb_timing* timing) {
   if (!ctx || !d_partial_out || (!scalars && n)) return fail(ctx, MGB_E_INVALID, "mgb_msm_partial: NULL argument");
   if (n > ctx->npoints) return fail(ctx, ctx->npoints ? MGB_E_INVALID : MGB_E_STATE, "mgb_msm_partial: n exceeds the number of points set");
+  if (scalars_on_device && ((uintptr_t)scalars & 15)) return fail(ctx, MGB_E_INVALID, "mgb_msm_partial: the device scalar buffer must be 16-byte aligned");
   CU(ctx, cudaSetDevice(ctx->device));
   DISPATCH(ctx, msm_partial_impl, ctx, scalars, scalars_on_device != 0, n, opts, d_partial_out, timing);
 }
@@ -861,6 +863,7 @@ int mgb_msm_sharded(mgb_ctx* ctx, const void* scalars, int scalars_on_device, si
   if (!ctx || !out_xy_le || (!scalars && n_local)) return fail(ctx, MGB_E_INVALID, "mgb_msm_sharded: NULL argument");
   if (n_local > ctx->npoints) return fail(ctx, ctx->npoints ? MGB_E_INVALID : MGB_E_STATE, "mgb_msm_sharded: n_local exceeds the number of points set");
   if (opts && opts->projective) return fail(ctx, MGB_E_INVALID, "mgb_msm_sharded: the projective cross-check path is single-GPU only");
+  if (scalars_on_device && ((uintptr_t)scalars & 15)) return fail(ctx, MGB_E_INVALID, "mgb_msm_sharded: the device scalar buffer must be 16-byte aligned");
   CU(ctx, cudaSetDevice(ctx->device));
   DISPATCH(ctx, msm_sharded_impl, ctx, scalars, scalars_on_device != 0, n_local, opts, out_xy_le, out_is_zero, timing);
 }

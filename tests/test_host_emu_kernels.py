@@ -336,3 +336,20 @@ def test_set_get_points_and_combine_weierstrass(emu_k, cid, prm, n):
     words2[4 * n:] = sum((limbs(v) for v in (neg[0] * R % p, neg[1] * R % p, R % p, R % p)), [])
     emu_k.emu_normalize(cid, (U32 * len(words2))(*words2), 2, out, ctypes.byref(flag))         # P + (-P): the neutral element
     assert flag.value == 1 and val(out[:]) == 0
+    # the eight-GPU shape and beyond: 8, 11 and 17 partials (quad q sums q, q + 8, ..., then a tree over the eight quads),
+    # with a duplicate (doubling inside the tree) and neutral elements among them
+    for count in (8, 11, 17):
+        sel = [pts[i % len(pts)] for i in range(count)]
+        sel[3] = None
+        sel[5] = sel[4]
+        words3 = []
+        for P in sel:
+            z = rnd.randrange(1, p)
+            coords = [0, R % p, 0, 0] if P is None else [P[0] * z * z * R % p, P[1] * z * z * z * R % p, z * z * R % p, z * z * z * R % p]
+            for v in coords:
+                words3 += limbs(v)
+        exp = None
+        for P in sel:
+            exp = A.add(exp, P)
+        emu_k.emu_normalize(cid, (U32 * len(words3))(*words3), count, out, ctypes.byref(flag))
+        assert (val(out[:n]), val(out[n:]), flag.value) == ((*exp, 0) if exp is not None else (0, 0, 1)), count
