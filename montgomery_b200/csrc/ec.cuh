@@ -111,6 +111,27 @@ struct Weierstrass {
     return r;
   }
 
+  // mmadd-2008-s: both operands affine (ZZ = ZZZ = 1), result XYZZ; 4M + 2S instead of the 8M + 2S of madd.  Complete.
+  MGB_DEV static acc mmadd(const affine& p, const affine& q) {
+    if (is_inf(q)) return from_affine(p);
+    if (is_inf(p)) return from_affine(q);
+    fe Pd = F::sub(q.x, p.x);
+    fe R = F::sub(q.y, p.y);
+    if (F::is_zero(Pd)) {
+      if (F::is_zero(R)) return dbl(from_affine(p));
+      return acc_zero();
+    }
+    fe PP = F::sqr(Pd);
+    fe PPP = F::mul(Pd, PP);
+    fe Q = F::mul(p.x, PP);
+    acc r;
+    r.X = F::sub(F::sub(F::sqr(R), PPP), F::dbl(Q));
+    r.Y = F::sub(F::mul(R, F::sub(Q, r.X)), F::mul(p.y, PPP));
+    r.ZZ = PP;
+    r.ZZZ = PPP;
+    return r;
+  }
+
   // x = X/ZZ, y = Y/ZZZ with one inversion: t = 1/ZZZ, 1/ZZ = t^2 * ZZ^2
   MGB_DEV static affine to_affine(const acc& p) {
     if (acc_is_zero(p)) return affine_inf();

@@ -118,6 +118,7 @@ struct WeierstrassPolicy {
   MGB_DEV static acc add(const acc& a, const acc& b) { return G::add(a, b); }
   MGB_DEV static acc dbl(const acc& a) { return G::dbl(a); }
   MGB_DEV static acc add_v(const acc& a, const vpoint& p) { return G::madd(a, p); }
+  MGB_DEV static acc add_vv(const vpoint& p, const vpoint& q) { return G::mmadd(p, q); }   // two stored (affine) elements: 6 products, not 10
   MGB_DEV static acc ld_acc(const uint32_t* p) { acc r; r.X = ld_fe<FP>(p); r.Y = ld_fe<FP>(p + N); r.ZZ = ld_fe<FP>(p + 2 * N); r.ZZZ = ld_fe<FP>(p + 3 * N); return r; }
   MGB_DEV static void st_acc(uint32_t* p, const acc& a) { st_fe<FP>(p, a.X); st_fe<FP>(p + N, a.Y); st_fe<FP>(p + 2 * N, a.ZZ); st_fe<FP>(p + 3 * N, a.ZZZ); }
   MGB_DEV static acc generator() {
@@ -213,6 +214,7 @@ struct TwistedEdwardsPolicy {
   MGB_DEV static acc add(const acc& a, const acc& b) { return G::add(a, b); }
   MGB_DEV static acc dbl(const acc& a) { return G::dbl(a); }
   MGB_DEV static acc add_v(const acc& a, const vpoint& p) { return G::add(a, p); }
+  MGB_DEV static acc add_vv(const vpoint& p, const vpoint& q) { return G::add(p, q); }
   MGB_DEV static acc ld_acc(const uint32_t* p) { acc r; r.X = ld_fe<FP>(p); r.Y = ld_fe<FP>(p + N); r.Z = ld_fe<FP>(p + 2 * N); r.T = ld_fe<FP>(p + 3 * N); return r; }
   MGB_DEV static void st_acc(uint32_t* p, const acc& a) { st_fe<FP>(p, a.X); st_fe<FP>(p + N, a.Y); st_fe<FP>(p + 2 * N, a.Z); st_fe<FP>(p + 3 * N, a.T); }
   MGB_DEV static acc generator() {
@@ -278,6 +280,7 @@ struct WeierstrassBasicPolicy : MAIN {
   MGB_DEV static vpoint load_v(const uint32_t* V, uint32_t slot) { return MAIN::ld_acc(V + (size_t)slot * V_LIMBS); }
   MGB_DEV static void store_v(uint32_t* V, uint32_t slot, const vpoint& p) { MAIN::st_acc(V + (size_t)slot * V_LIMBS, p); }
   MGB_DEV static acc add_v(const acc& a, const vpoint& p) { return G::add(a, p); }
+  MGB_DEV static acc add_vv(const vpoint& p, const vpoint& q) { return G::add(p, q); }
 };
 
 typedef WeierstrassPolicy<Fp377, Bls12377Consts, Glv377, 127> CurveBls377;     // |k| < 2^126 (gen_constants.py self-check; reference maxBits = 126)
@@ -1042,8 +1045,11 @@ __global__ void __launch_bounds__(128) k_bucket_finish(uint32_t b_begin, uint32_
   if (b >= b_end) return;
   const uint32_t o = offs[b], n = counts[b], stride = 1u << rounds;
   if (n == 0) return;                                   // k_group_partial skips empty buckets by their count
-  typename CV::acc acc = CV::acc_zero();
-  for (uint32_t q = 0; q < n; q += stride) acc = CV::add_v(acc, CV::load_v(V, o + q));
+  // the first two leftovers are both stored elements (affine on the batched-affine curves: 6 products instead of 10)
+  typename CV::acc acc;
+  if (n > stride) acc = CV::add_vv(CV::load_v(V, o), CV::load_v(V, o + stride));
+  else acc = CV::add_v(CV::acc_zero(), CV::load_v(V, o));
+  for (uint32_t q = 2 * stride; q < n; q += stride) acc = CV::add_v(acc, CV::load_v(V, o + q));
   CV::st_acc(Bsum + (size_t)b * CV::ACC_LIMBS, acc);
 }
 
@@ -1188,6 +1194,18 @@ MGB_DEV typename CV::acc shfl_acc(const typename CV::acc& a, int src) {
   return r;
 }
 
+// one-warp Horner (MGB_ONEWARP_HORNER): lane 8g + l holds 64-bit digit l of coordinate g of an XYZZ accumulator
+template <class FP>
+MGB_DEV unsigned long long ow_load(const uint32_t* src) {
+  const int g = (threadIdx.x & 31) >> 3, l = threadIdx.x & 7;
+  return l < FP::N / 2 ? (((unsigned long long)src[g * FP::N + 2 * l + 1] << 32) | src[g * FP::N + 2 * l]) : 0ull;
+}
+template <class FP>
+MGB_DEV void ow_store(uint32_t* dst, unsigned long long v) {
+  const int g = (threadIdx.x & 31) >> 3, l = threadIdx.x & 7;
+  if (l < FP::N / 2) { dst[g * FP::N + 2 * l] = (uint32_t)v; dst[g * FP::N + 2 * l + 1] = (uint32_t)(v >> 32); }
+}
+
 // block = one window, warp d = one digit: X_d = sum_v v * G_v by an inclusive suffix scan over the
 // lanes (S_v = sum_{v' >= v} G_v', X = sum_{v >= 1} S_v), then thread 0 assembles
 // S_w = sum_d 2^(sh_d) X_d + sum_l B_l.
@@ -1215,6 +1233,19 @@ __global__ void __launch_bounds__(192) k_window_sums(MsmParams pr, ReduceGeom gm
     }
   }
   __syncthreads();
+#if MGB_ONEWARP_HORNER
+  if (threadIdx.x < 32) {       // Horner over the digits with the point spread over the lanes of warp 0 (onewarp.cuh), as k_final does
+    typedef typename CV::OneWarp OW;
+    typedef typename CV::P FP;
+    unsigned long long v = ow_load<FP>(sm + (gm.D - 1) * CV::ACC_LIMBS);
+    for (int dd = gm.D - 2; dd >= 0; dd--) {
+      for (int k = 0; k < gm.width[dd]; k++) v = OW::dbl(v);
+      v = OW::add(v, ow_load<FP>(sm + dd * CV::ACC_LIMBS));
+    }
+    v = OW::add(v, ow_load<FP>(sm + 6 * CV::ACC_LIMBS));
+    ow_store<FP>(Sw + (size_t)w * CV::ACC_LIMBS, v);
+  }
+#else
   if (threadIdx.x == 0) {
     typename CV::acc acc = CV::ld_acc(sm + (gm.D - 1) * CV::ACC_LIMBS);
     for (int dd = gm.D - 2; dd >= 0; dd--) {
@@ -1224,6 +1255,7 @@ __global__ void __launch_bounds__(192) k_window_sums(MsmParams pr, ReduceGeom gm
     acc = CV::add(acc, CV::ld_acc(sm + 6 * CV::ACC_LIMBS));
     CV::st_acc(Sw + (size_t)w * CV::ACC_LIMBS, acc);
   }
+#endif
 }
 
 // ---- quad-cooperative variants of the latency-bound reduction stages (Weierstrass, see coop.cuh) ----
@@ -1282,18 +1314,6 @@ __global__ void __launch_bounds__(128) k_digit_sums(MsmParams pr, ReduceGeom gm,
     X = Q::add(X, o);
   }
   if (v == 0) st_fe<FP>(out + ((size_t)w * gm.D + d) * CV::ACC_LIMBS + k * N, X);
-}
-
-// one-warp Horner (MGB_ONEWARP_HORNER): lane 8g + l holds 64-bit digit l of coordinate g of an XYZZ accumulator
-template <class FP>
-MGB_DEV unsigned long long ow_load(const uint32_t* src) {
-  const int g = (threadIdx.x & 31) >> 3, l = threadIdx.x & 7;
-  return l < FP::N / 2 ? (((unsigned long long)src[g * FP::N + 2 * l + 1] << 32) | src[g * FP::N + 2 * l]) : 0ull;
-}
-template <class FP>
-MGB_DEV void ow_store(uint32_t* dst, unsigned long long v) {
-  const int g = (threadIdx.x & 31) >> 3, l = threadIdx.x & 7;
-  if (l < FP::N / 2) { dst[g * FP::N + 2 * l] = (uint32_t)v; dst[g * FP::N + 2 * l + 1] = (uint32_t)(v >> 32); }
 }
 
 // block = one window: S_w = sum_d 2^(sh_d) X_d + sum_l B_l by Horner over the digits; the four warps
