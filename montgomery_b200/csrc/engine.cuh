@@ -23,20 +23,6 @@
 #include "coop.cuh"
 #include "onewarp.cuh"
 
-// Build-time switches, both ON since round 2 (A/B on a B200, profiles/r02_ab_winv_onewarp.json; =0 rebuilds the
-// round-1 paths for comparison):
-//   MGB_ONEWARP_HORNER  the Horner kernels of the Weierstrass curves run in one warp (onewarp.cuh): final sum
-//                       0.370 -> 0.335 ms at 2^20, 0.414 -> 0.373 ms at 2^16
-//   MGB_WARP_INV        k_batch_add inverts a tile's total with the lane-parallel inverse of warp.cuh (20.6 us
-//                       instead of 35.3 us alone, and all lanes use the issue slots): accumulate 5.01 -> 4.78 ms,
-//                       and 4.39 ms with tile sizes balanced over the resident warps (see msm_core)
-#ifndef MGB_ONEWARP_HORNER
-#define MGB_ONEWARP_HORNER 1
-#endif
-#ifndef MGB_WARP_INV
-#define MGB_WARP_INV 1
-#endif
-
 namespace mgb {
 
 // ---------------------------------------------------------------- vector loads / stores
@@ -81,7 +67,6 @@ struct WeierstrassPolicy {
   typedef typename G::acc acc;
   typedef typename G::affine vpoint;   // materialised bucket element
   typedef GL Glv;
-  typedef CoopWeierstrass<FP> Coop;
   typedef OneWarpWeierstrass<FP> OneWarp;
   typedef QuadWeierstrass<FP> Quad;
   static constexpr int N = FP::N;
@@ -188,7 +173,6 @@ struct TwistedEdwardsPolicy {
   typedef TwistedEdwards<FP, CC> G;
   typedef typename G::acc acc;
   typedef typename G::acc vpoint;
-  typedef CoopTwistedEdwards<FP, CC> Coop;
   typedef OneWarpTwistedEdwards<FP, CC> OneWarp;
   static constexpr int N = FP::N;
   static constexpr bool USE_GLV = false;
@@ -886,12 +870,9 @@ __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ 
     cp_async_commit();
     issue_ypart(E - 1);
     cp_async_commit();
-#if MGB_WARP_INV
-    inv = WarpField<FP>::inv_call(inv);           // experiment: all lanes share the inversion (warp.cuh)
-#else
-    if (lane == 0) inv = F::inv_divsteps(inv);
-    inv = shfl_fe<FP>(inv, 0);
-#endif
+    // all lanes share the inversion (lane-parallel division steps, warp.cuh): 20.6 us instead of 35.3 us on lane 0 alone,
+    // and 32 instead of 1 active lanes in what was a tenth of the kernel's issue slots (A/B: profiles/r02_ab_winv_onewarp.jsonl)
+    inv = WarpField<FP>::inv_call(inv);
     fe u = inv;                                   // -> 1 / (this lane's total)
     {
       const fe left = shfl_fe<FP>(pfx, lane == 0 ? 0 : lane - 1);
@@ -1194,7 +1175,7 @@ MGB_DEV typename CV::acc shfl_acc(const typename CV::acc& a, int src) {
   return r;
 }
 
-// one-warp Horner (MGB_ONEWARP_HORNER): lane 8g + l holds 64-bit digit l of coordinate g of an XYZZ accumulator
+// one-warp Horner: lane 8g + l holds 64-bit digit l of coordinate g of an accumulator (onewarp.cuh)
 template <class FP>
 MGB_DEV unsigned long long ow_load(const uint32_t* src) {
   const int g = (threadIdx.x & 31) >> 3, l = threadIdx.x & 7;
@@ -1233,7 +1214,6 @@ __global__ void __launch_bounds__(192) k_window_sums(MsmParams pr, ReduceGeom gm
     }
   }
   __syncthreads();
-#if MGB_ONEWARP_HORNER
   if (threadIdx.x < 32) {       // Horner over the digits with the point spread over the lanes of warp 0 (onewarp.cuh), as k_final does
     typedef typename CV::OneWarp OW;
     typedef typename CV::P FP;
@@ -1245,17 +1225,6 @@ __global__ void __launch_bounds__(192) k_window_sums(MsmParams pr, ReduceGeom gm
     v = OW::add(v, ow_load<FP>(sm + 6 * CV::ACC_LIMBS));
     ow_store<FP>(Sw + (size_t)w * CV::ACC_LIMBS, v);
   }
-#else
-  if (threadIdx.x == 0) {
-    typename CV::acc acc = CV::ld_acc(sm + (gm.D - 1) * CV::ACC_LIMBS);
-    for (int dd = gm.D - 2; dd >= 0; dd--) {
-      for (int k = 0; k < gm.width[dd]; k++) acc = CV::dbl(acc);
-      acc = CV::add(acc, CV::ld_acc(sm + dd * CV::ACC_LIMBS));
-    }
-    acc = CV::add(acc, CV::ld_acc(sm + 6 * CV::ACC_LIMBS));
-    CV::st_acc(Sw + (size_t)w * CV::ACC_LIMBS, acc);
-  }
-#endif
 }
 
 // ---- quad-cooperative variants of the latency-bound reduction stages (Weierstrass, see coop.cuh) ----
@@ -1316,98 +1285,46 @@ __global__ void __launch_bounds__(128) k_digit_sums(MsmParams pr, ReduceGeom gm,
   if (v == 0) st_fe<FP>(out + ((size_t)w * gm.D + d) * CV::ACC_LIMBS + k * N, X);
 }
 
-// block = one window: S_w = sum_d 2^(sh_d) X_d + sum_l B_l by Horner over the digits; the four warps
-// share the multiplications of each formula level (coop.cuh), as in k_final.
+// block = one window, ONE warp: S_w = sum_d 2^(sh_d) X_d + sum_l B_l by Horner over the digits, the point spread over the
+// lanes (onewarp.cuh), as in k_final.
 template <class CV>
-__global__ void __launch_bounds__(128) k_window_assemble(MsmParams pr, ReduceGeom gm, int w_begin, const uint32_t* __restrict__ in, uint32_t* __restrict__ Sw) {
+__global__ void __launch_bounds__(32) k_window_assemble(MsmParams pr, ReduceGeom gm, int w_begin, const uint32_t* __restrict__ in, uint32_t* __restrict__ Sw) {
   typedef typename CV::P FP;
-  constexpr int N = CV::N;
-  __shared__ uint32_t sm[COOP_SLOTS * N];
-  __shared__ int flag;
-  CoopMem<FP> m{sm};
+  typedef typename CV::OneWarp OW;
   const int w = w_begin + blockIdx.x;
-#if MGB_ONEWARP_HORNER
-  if constexpr (std::is_same<typename CV::Coop, CoopWeierstrass<FP>>::value) {
-    if (threadIdx.x >= 32) return;
-    typedef OneWarpWeierstrass<FP> OW;
-    unsigned long long v = ow_load<FP>(in + ((size_t)w * gm.D + gm.D - 1) * CV::ACC_LIMBS);
-    for (int dd = gm.D - 2; dd >= 0; dd--) {
-      for (int k = 0; k < gm.width[dd]; k++) v = OW::dbl(v);
-      v = OW::add(v, ow_load<FP>(in + ((size_t)w * gm.D + dd) * CV::ACC_LIMBS));
-    }
-    v = OW::add(v, ow_load<FP>(in + ((size_t)pr.K * gm.D + w) * CV::ACC_LIMBS));
-    ow_store<FP>(Sw + (size_t)w * CV::ACC_LIMBS, v);
-    return;
-  }
-#endif
-  auto load_point = [&](int slot0, const uint32_t* src) {
-    if (threadIdx.x < 4 * N) sm[slot0 * N + threadIdx.x] = src[threadIdx.x];
-  };
-  load_point(0, in + ((size_t)w * gm.D + gm.D - 1) * CV::ACC_LIMBS);
-  __syncthreads();
+  unsigned long long v = ow_load<FP>(in + ((size_t)w * gm.D + gm.D - 1) * CV::ACC_LIMBS);
   for (int dd = gm.D - 2; dd >= 0; dd--) {
-    CV::Coop::dbl_n(m, &flag, gm.width[dd]);
-    load_point(4, in + ((size_t)w * gm.D + dd) * CV::ACC_LIMBS);
-    __syncthreads();
-    CV::Coop::add(m, &flag);
+    for (int k = 0; k < gm.width[dd]; k++) v = OW::dbl(v);
+    v = OW::add(v, ow_load<FP>(in + ((size_t)w * gm.D + dd) * CV::ACC_LIMBS));
   }
-  load_point(4, in + ((size_t)pr.K * gm.D + w) * CV::ACC_LIMBS);
-  __syncthreads();
-  CV::Coop::add(m, &flag);
-  if (threadIdx.x < 4 * N) Sw[(size_t)w * CV::ACC_LIMBS + threadIdx.x] = sm[threadIdx.x];
+  v = OW::add(v, ow_load<FP>(in + ((size_t)pr.K * gm.D + w) * CV::ACC_LIMBS));
+  ow_store<FP>(Sw + (size_t)w * CV::ACC_LIMBS, v);
 }
 
 // result = sum_w 2^(c*w) S_w by Horner (msm-batched-affine.ts:322-334): (K-1)*c dependent doublings.
 // One 128-thread block; the four warps share the multiplications of each formula level (coop.cuh).
 // out_xy != nullptr (single-GPU msm): the same warp also normalises -- canonical x || y and the is-zero flag, as
 // k_normalize would -- so the result needs no further launch.
+// One warp: the point is spread over the lanes (onewarp.cuh: 8-lane group g = coordinate g, one 64-bit digit per lane, the
+// four products of a formula level are one WarpField2::mul; no shared memory, no barrier in the chain).  Round 1 ran the
+// chain on a 128-thread block with a barrier per formula level: 0.370 -> 0.335 ms at 2^20 (profiles/r02_ab_winv_onewarp.jsonl),
+// and 1.33 -> 0.31 ms for the 238 doublings of the twisted-Edwards curve at 2^18.
 template <class CV>
-__global__ void __launch_bounds__(128) k_final(int K, int c, const uint32_t* __restrict__ Sw, uint32_t* __restrict__ out_acc,
-                                               uint32_t* __restrict__ out_xy, uint32_t* __restrict__ out_flag) {
+__global__ void __launch_bounds__(32) k_final(int K, int c, const uint32_t* __restrict__ Sw, uint32_t* __restrict__ out_acc,
+                                              uint32_t* __restrict__ out_xy, uint32_t* __restrict__ out_flag) {
   typedef typename CV::P FP;
+  typedef typename CV::OneWarp OW;
   constexpr int N = CV::N;
-  __shared__ uint32_t sm[COOP_SLOTS * N];
-  __shared__ int flag;
-  CoopMem<FP> m{sm};
-#if MGB_ONEWARP_HORNER
-  {
-    if (threadIdx.x >= 32) return;
-    typedef typename CV::OneWarp OW;
-    unsigned long long v = ow_load<FP>(Sw + (size_t)(K - 1) * CV::ACC_LIMBS);
-    for (int w = K - 2; w >= 0; w--) {
-      for (int d = 0; d < c; d++) v = OW::dbl(v);
-      v = OW::add(v, ow_load<FP>(Sw + (size_t)w * CV::ACC_LIMBS));
-    }
-    ow_store<FP>(out_acc, v);
-    if (out_xy) {
-      Fe<FP> x, y;
-      bool inf;
-      CV::acc_to_plain_warp(OW::gather(v), x, y, inf);
-      if (threadIdx.x == 0) {
-        _Pragma("unroll") for (int i = 0; i < N; i++) { out_xy[i] = x.v[i]; out_xy[N + i] = y.v[i]; }
-        *out_flag = inf ? 1u : 0u;
-      }
-    }
-    return;
-  }
-#endif
-  // accumulator slots 0..3 and operand slots 4..7 hold the 4 coordinates of CV::acc in order
-  auto load_point = [&](int slot0, const uint32_t* src) {
-    if (threadIdx.x < 4 * N) sm[slot0 * N + threadIdx.x] = src[threadIdx.x];
-  };
-  load_point(0, Sw + (size_t)(K - 1) * CV::ACC_LIMBS);
-  __syncthreads();
+  unsigned long long v = ow_load<FP>(Sw + (size_t)(K - 1) * CV::ACC_LIMBS);
   for (int w = K - 2; w >= 0; w--) {
-    CV::Coop::dbl_n(m, &flag, c);
-    load_point(4, Sw + (size_t)w * CV::ACC_LIMBS);
-    __syncthreads();
-    CV::Coop::add(m, &flag);
+    for (int d = 0; d < c; d++) v = OW::dbl(v);
+    v = OW::add(v, ow_load<FP>(Sw + (size_t)w * CV::ACC_LIMBS));
   }
-  if (threadIdx.x < 4 * N) out_acc[threadIdx.x] = sm[threadIdx.x];
-  if (out_xy && threadIdx.x < 32) {
+  ow_store<FP>(out_acc, v);
+  if (out_xy) {
     Fe<FP> x, y;
     bool inf;
-    CV::acc_to_plain_warp(CV::ld_acc(sm), x, y, inf);
+    CV::acc_to_plain_warp(OW::gather(v), x, y, inf);
     if (threadIdx.x == 0) {
       _Pragma("unroll") for (int i = 0; i < N; i++) { out_xy[i] = x.v[i]; out_xy[N + i] = y.v[i]; }
       *out_flag = inf ? 1u : 0u;

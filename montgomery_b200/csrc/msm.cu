@@ -527,7 +527,7 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
       // latency-bound stages, four lanes per point addition (coop.cuh): last tree levels, digit sums, per-window assembly
       if (remaining > 1) { k_tree_tail_quad<CV><<<ngroups_g, 64, 0, sg>>>(gm.NP, remaining, Pg); launches++; }
       k_digit_sums<CV><<<Kg * gm.D, 128, 0, sg>>>(pr, gmr, w_begin, (const uint32_t*)ctx->redU[0].p, (uint32_t*)ctx->redW[1].p);
-      k_window_assemble<CV><<<Kg, 128, 0, sg>>>(pr, gm, w_begin, (const uint32_t*)ctx->redW[1].p, (uint32_t*)ctx->redW[0].p);
+      k_window_assemble<CV><<<Kg, 32, 0, sg>>>(pr, gm, w_begin, (const uint32_t*)ctx->redW[1].p, (uint32_t*)ctx->redW[0].p);
       launches += 2;
     } else {
       if (remaining > 1) {
@@ -544,7 +544,7 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   CU(ctx, cudaEventRecord(ctx->ev[EV_REDUCE], st));
   uint32_t* d_xy = nullptr;
   if (normalize) { ENS(ctx, ctx->out_xy, 64 * 4); d_xy = (uint32_t*)ctx->out_xy.p; }
-  k_final<CV><<<1, 128, 0, st>>>(pr.K, pr.c, (const uint32_t*)ctx->redW[0].p, (uint32_t*)ctx->acc_out.p, d_xy, d_xy ? d_xy + 2 * CV::N : nullptr);
+  k_final<CV><<<1, 32, 0, st>>>(pr.K, pr.c, (const uint32_t*)ctx->redW[0].p, (uint32_t*)ctx->acc_out.p, d_xy, d_xy ? d_xy + 2 * CV::N : nullptr);
   launches++;
   CU(ctx, cudaGetLastError());
   if (tm) {

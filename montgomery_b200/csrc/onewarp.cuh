@@ -1,8 +1,8 @@
 // One-warp point arithmetic for the Horner kernels (XYZZ Weierstrass, extended twisted Edwards).
 //
-// coop.cuh runs a dependent chain of point operations on a 128-thread block: the four warps take
-// the (up to four) products of a formula level, each spread over 12 lanes of its warp, and meet at
-// a block barrier after every level.  Here the whole point lives in ONE warp: 8-lane group g holds
+// A dependent chain of point operations (Horner over the windows, assembly of a window sum) has ONE point operation in
+// flight.  Round 1 ran it on a 128-thread block: the four warps took the (up to four) products of a formula level, each
+// spread over 12 lanes of its warp, and met at a block barrier after every level.  Here the whole point lives in ONE warp: 8-lane group g holds
 // coordinate g (X, Y, ZZ, ZZZ), one 64-bit digit per lane (WarpField2), the four products of a
 // level are one WarpField2::mul, the additions / subtractions between them run on the distributed
 // digits (carry lookahead over ballots), and operands move between groups by shuffles -- no
@@ -105,8 +105,8 @@ struct OneWarpWeierstrass {
 
 // The same for extended twisted-Edwards points (a = -1): 8-lane group g holds coordinate g of (X, Y, Z, T).  A doubling
 // is dbl-2008-hwcd -- four squares, then four products: TWO product levels instead of the three of the unified
-// addition the block-cooperative CoopTwistedEdwards::dbl_n runs through shared memory (5.6 us per doubling there:
-// the 2^18-point ed-on-BLS12-377 MSM spent 1.33 of its 2.73 ms in the 238 doublings of its Horner chain).  The
+// addition round 1's block-cooperative routine ran through shared memory (5.6 us per doubling there: the 2^18-point
+// ed-on-BLS12-377 MSM spent 1.33 of its 2.73 ms in the 238 doublings of its Horner chain; now 0.31 ms).  The
 // addition is the strongly unified add-2008-hwcd-3 (complete: doubling, neutral element, inverses), three levels.
 template <class P, class C>
 struct OneWarpTwistedEdwards {

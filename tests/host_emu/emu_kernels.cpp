@@ -32,10 +32,10 @@ extern "C" void emu_batch_add(int curve, int first, uint32_t* V, const uint32_t*
 #undef GO
 }
 
-// k_final: result = sum_w 2^(c w) S_w by Horner, one 128-thread block (one warp with -DMGB_ONEWARP_HORNER=1)
+// k_final: result = sum_w 2^(c w) S_w by Horner in one warp
 // out_xy / out_flag (2 N + 1 words, may be NULL): the fused normalisation of the single-GPU path
 extern "C" void emu_final(int curve, int K, int c, const uint32_t* Sw, uint32_t* out_acc, uint32_t* out_xy, uint32_t* out_flag) {
-  simt::run_grid(1, 128, [&] {
+  simt::run_grid(1, 32, [&] {
     if (curve == 0) k_final<CurveBls377>(K, c, Sw, out_acc, out_xy, out_flag);
     else if (curve == 1) k_final<CurvePallas>(K, c, Sw, out_acc, out_xy, out_flag);
     else if (curve == 2) k_final<CurveBls381>(K, c, Sw, out_acc, out_xy, out_flag);

@@ -145,22 +145,8 @@ template <class P> static void warp_inv(uint32_t* out, const uint32_t* a, int n)
   });
 }
 
-// ---- the block-cooperative point arithmetic of the Horner kernels (coop.cuh) on an emulated 128-thread block,
-// driven the way k_final drives it: operands in the shared slots 0..3 (accumulator) and 4..7, result in 0..3.
-// op 0: P <- 2^count P (dbl_n), op 1: P <- P + Q, op 2: P <- 2^count P + Q (what one Horner step does)
-template <class COOP, class P> static void coop_op(int op, int count, uint32_t* out, const uint32_t* a, const uint32_t* b) {
-  constexpr int N = P::N;
-  static uint32_t sm[COOP_SLOTS * N];
-  static volatile int flag;
-  simt::run_block(128, [&](int t) {
-    CoopMem<P> m{sm};
-    if (t < 4 * N) { sm[t] = a[t]; sm[4 * N + t] = b[t]; }
-    __syncthreads();
-    if (op == 0 || op == 2) COOP::dbl_n(m, &flag, count);
-    if (op == 1 || op == 2) COOP::add(m, &flag);
-    if (t < 4 * N) out[t] = sm[t];
-  });
-}
+// ---- the one-warp point arithmetic of the Horner kernels (onewarp.cuh), driven the way k_final drives it.
+// op 0: P <- 2^count P, op 1: P <- P + Q, op 2: P <- 2^count P + Q (what one Horner step does)
 // the same three operations on ONE emulated warp (onewarp.cuh): the point distributed over the lanes
 template <class P> static void onewarp_op(int op, int count, uint32_t* out, const uint32_t* a, const uint32_t* b) {
   typedef OneWarpWeierstrass<P> OW;
@@ -203,11 +189,6 @@ template <class P> static void quad_add(uint32_t* out, const uint32_t* a, const 
 }
 
 extern "C" {
-void emu_coop_w(int curve, int op, int count, uint32_t* out, const uint32_t* a, const uint32_t* b) {
-  if (curve == 0) coop_op<CoopWeierstrass<Fp377>, Fp377>(op, count, out, a, b);
-  else if (curve == 1) coop_op<CoopWeierstrass<FpPallas>, FpPallas>(op, count, out, a, b);
-  else coop_op<CoopWeierstrass<Fp381>, Fp381>(op, count, out, a, b);
-}
 void emu_onewarp_w(int curve, int op, int count, uint32_t* out, const uint32_t* a, const uint32_t* b) {
   if (curve == 0) onewarp_op<Fp377>(op, count, out, a, b);
   else if (curve == 1) onewarp_op<FpPallas>(op, count, out, a, b);
@@ -215,9 +196,6 @@ void emu_onewarp_w(int curve, int op, int count, uint32_t* out, const uint32_t* 
 }
 void emu_onewarp_te(int op, int count, uint32_t* out, const uint32_t* a, const uint32_t* b) {
   onewarp_te_op<Fr377, Ed377Consts>(op, count, out, a, b);
-}
-void emu_coop_te(int op, int count, uint32_t* out, const uint32_t* a, const uint32_t* b) {
-  coop_op<CoopTwistedEdwards<Fr377, Ed377Consts>, Fr377>(op, count, out, a, b);
 }
 void emu_quad_add(int curve, uint32_t* out, const uint32_t* a, const uint32_t* b) {
   if (curve == 0) quad_add<Fp377>(out, a, b);

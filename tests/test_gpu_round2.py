@@ -286,3 +286,26 @@ def test_affine_bucket_reduction_equals_default(label):
         assert eng.msm(sc, affine_reduction=True)[0] == eng.msm(sc)[0]
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("label", ["bls12-377", "ed-on-bls12-377"])
+def test_identical_points_and_scalars(label):
+    """Every pair is (s, P) with the same s and the same P: every addition of the bucket trees, of the leftover sums
+    (affine + affine with equal operands: the doubling branch of mmadd) and of the reduction is a doubling or meets
+    equal operands; the result is [n s] P."""
+    cv = CURVES[label]
+    O = OracleCurve(label)
+    n = 5000
+    eng = m.MsmEngine(cv, 0, n)
+    try:
+        eng.random_points(1, seed=70)
+        xy, z = eng.get_points(0, 1)
+        eng.set_points(np.tile(xy.reshape(-1), n), np.zeros(n, dtype=np.uint8) if cv.kind == "weierstrass" else None)
+        s = 0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF1234567890ABCD % cv.q
+        sc = scalars_to_bytes([s] * n)
+        P = O.scale(int(inputs.known_dlogs(70, 1)[0]), O.G)
+        exp = O.result_of(O.scale(n * s, P))
+        for c in (None, 8, 12):
+            assert eng.msm(sc, n=n, c=c)[0] == exp, (label, c)
+    finally:
+        eng.close()

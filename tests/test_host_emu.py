@@ -249,15 +249,12 @@ def test_warp_parallel_inverse(emu, fid):
         assert g == (pow(a * Ri, -1, p) * R % p if a else 0), (fid, hex(a))
 
 
-# ---- block-cooperative point arithmetic of the Horner kernels (csrc/coop.cuh: four warps share the products of a
-# formula level, the lanes of a warp share each product, runs of doublings are fused) on an emulated 128-thread block
+# ---- one-warp point arithmetic of the Horner kernels (csrc/onewarp.cuh) on an emulated warp
 
-@pytest.mark.parametrize("impl", ["block", "onewarp"])
 @pytest.mark.parametrize("cid,prm,n", [(0, BLS12_377, 12), (1, PALLAS, 8), (2, BLS12_381, 12)])
-def test_coop_weierstrass_horner_steps(emu, cid, prm, n, impl):
-    """impl = block: coop.cuh on a 128-thread block (what k_final runs); onewarp: onewarp.cuh, the whole point in one warp
-    (an experiment: no shared memory, no barriers)."""
-    run = emu.emu_coop_w if impl == "block" else emu.emu_onewarp_w
+def test_onewarp_weierstrass_horner_steps(emu, cid, prm, n):
+    """onewarp.cuh, what k_final / k_window_assemble run: the whole XYZZ point in one warp (no shared memory, no barriers)."""
+    run = emu.emu_onewarp_w
     p = prm.p
     R = 1 << (32 * n)
     Ri = pow(R, -1, p)
@@ -296,11 +293,10 @@ def test_coop_weierstrass_horner_steps(emu, cid, prm, n, impl):
     assert dec_x(I(out, n, 4)) == Q
 
 
-@pytest.mark.parametrize("impl", ["block", "onewarp"])
-def test_coop_twisted_edwards_horner_steps(emu, impl):
-    """impl = block: CoopTwistedEdwards on a 128-thread block (round 1); onewarp: OneWarpTwistedEdwards, the whole extended
-    point in one warp, dedicated doubling (what k_final runs since round 2)."""
-    run_te = emu.emu_coop_te if impl == "block" else emu.emu_onewarp_te
+def test_onewarp_twisted_edwards_horner_steps(emu):
+    """OneWarpTwistedEdwards: the whole extended point in one warp, dedicated doubling (what k_final runs for the
+    twisted-Edwards curve)."""
+    run_te = emu.emu_onewarp_te
     prm, n = ED_ON_BLS12_377, 8
     p = prm.p
     R = 1 << (32 * n)

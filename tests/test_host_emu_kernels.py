@@ -20,30 +20,20 @@ REF_NEG, REF_ENDO, REF_EMPTY = 0x80000000, 0x40000000, 0xFFFFFFFF
 U32 = ctypes.c_uint32
 
 
-# "product": the kernels as shipped (lane-parallel inversion of a tile's total, csrc/warp.cuh; Horner kernels of the Weierstrass
-# curves in one warp, csrc/onewarp.cuh); "lane0_inv": -DMGB_WARP_INV=0, the round-1 kernel whose lane 0 inverts alone;
-# "block_horner": -DMGB_ONEWARP_HORNER=0, the round-1 block-cooperative Horner -- same inputs, same expected sums
-@pytest.fixture(scope="module", params=["product", "lane0_inv", "block_horner"])
-def emu_k(request, tmp_path_factory):
+# the kernels as shipped (lane-parallel inversion of a tile's total, csrc/warp.cuh; Horner kernels in one warp, csrc/onewarp.cuh)
+@pytest.fixture(scope="module")
+def emu_k(tmp_path_factory):
     so = str(tmp_path_factory.mktemp("emu_k") / "emu_k.so")
-    flags = {"product": [], "lane0_inv": ["-DMGB_WARP_INV=0"], "block_horner": ["-DMGB_ONEWARP_HORNER=0"]}[request.param]
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-Wno-unknown-pragmas"] + flags +
-                          ["-o", so, os.path.join(ROOT, "tests", "host_emu", "emu_kernels.cpp")])
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-Wno-unknown-pragmas",
+                           "-o", so, os.path.join(ROOT, "tests", "host_emu", "emu_kernels.cpp")])
     lib = ctypes.CDLL(so)
-    lib.variant = request.param
+    lib.variant = "product"
     return lib
-
-
-def only(lib, *variants):
-    """an experiment build is exercised by the tests of the kernel it changes; the others would repeat the product run"""
-    if lib.variant not in variants:
-        pytest.skip("kernel not affected by the %s build" % lib.variant)
 
 
 @pytest.mark.parametrize("cid,prm,n,e_big", [(0, BLS12_377, 12, 2), (0, BLS12_377, 12, 8), (1, PALLAS, 8, 4)],
                          ids=["bls12-377-E2", "bls12-377-E8", "pallas-E4"])
 def test_batch_add_two_rounds(emu_k, cid, prm, n, e_big):
-    only(emu_k, "product", "lane0_inv")
     p = prm.p
     R = 1 << (32 * n)
     Ri = pow(R, -1, p)
@@ -144,7 +134,6 @@ def test_batch_add_two_rounds(emu_k, cid, prm, n, e_big):
 @pytest.mark.parametrize("cid,prm,n", [(0, BLS12_377, 12), (1, PALLAS, 8)], ids=["bls12-377", "pallas"])
 def test_final_horner_kernel(emu_k, cid, prm, n):
     """k_final: sum_w 2^(c w) S_w over K window sums given as XYZZ accumulators (one of them the neutral element)."""
-    only(emu_k, "product", "block_horner")
     p = prm.p
     R = 1 << (32 * n)
     Ri = pow(R, -1, p)
@@ -190,7 +179,6 @@ def test_final_horner_kernel(emu_k, cid, prm, n):
 
 
 def test_final_horner_kernel_twisted_edwards(emu_k):
-    only(emu_k, "product")
     prm, n = ED_ON_BLS12_377, 8
     p = prm.p
     R = 1 << (32 * n)
@@ -225,7 +213,6 @@ def test_final_horner_kernel_twisted_edwards(emu_k):
 def test_pair_add_two_rounds_twisted_edwards(emu_k):
     """k_pair_add (the accumulation kernel of the twisted-Edwards curve): buckets of 2..4 points laid out back to back
     as the scatter kernel does, negated references, P + P and P + (-P), two tree rounds, next round's pair list."""
-    only(emu_k, "product")
     prm, n = ED_ON_BLS12_377, 8
     p = prm.p
     R = 1 << (32 * n)
@@ -297,7 +284,6 @@ def test_pair_add_two_rounds_twisted_edwards(emu_k):
 def test_set_get_points_and_combine_weierstrass(emu_k, cid, prm, n):
     """k_set_points (canonical bytes -> Montgomery table entry x | y | beta x, infinity flag), k_get_points (back), and
     k_normalize summing three partial accumulators (the multi-GPU combine) into the canonical affine point."""
-    only(emu_k, "product")
     p = prm.p
     R = 1 << (32 * n)
     A = AffineCurve(prm)
