@@ -104,6 +104,7 @@ struct WeierstrassPolicy {
   MGB_DEV static acc dbl(const acc& a) { return G::dbl(a); }
   MGB_DEV static acc add_v(const acc& a, const vpoint& p) { return G::madd(a, p); }
   MGB_DEV static acc add_vv(const vpoint& p, const vpoint& q) { return G::mmadd(p, q); }   // two stored (affine) elements: 6 products, not 10
+  // (add_refs -- the sum of two table entries -- is only needed by the paths that add without inversion: see the other policies)
   MGB_DEV static acc ld_acc(const uint32_t* p) { acc r; r.X = ld_fe<FP>(p); r.Y = ld_fe<FP>(p + N); r.ZZ = ld_fe<FP>(p + 2 * N); r.ZZZ = ld_fe<FP>(p + 3 * N); return r; }
   MGB_DEV static void st_acc(uint32_t* p, const acc& a) { st_fe<FP>(p, a.X); st_fe<FP>(p + N, a.Y); st_fe<FP>(p + 2 * N, a.ZZ); st_fe<FP>(p + 3 * N, a.ZZZ); }
   MGB_DEV static acc generator() {
@@ -180,10 +181,30 @@ struct TwistedEdwardsPolicy {
   static constexpr int HALVES = 1;
   static constexpr int MAG_LIMBS = 8;
   static constexpr int MAG_BITS = CC::SCALAR_BITS + 1;
-  static constexpr int ENTRY_LIMBS = 3 * N;  // x | y | t = x*y
+  static constexpr int ENTRY_LIMBS = 4 * N;  // x | y | t = x*y | k*t (k = 2d: lets round 0 add two table entries with 7 products)
   static constexpr int V_LIMBS = 4 * N;
   static constexpr int ACC_LIMBS = 4 * N;
   static constexpr int COORD_BYTES = 4 * N;
+
+  // Sum of two TABLE entries (round 0 of the bucket trees): both have Z = 1 and the second one's k*T is stored, so
+  // add-2008-hwcd-3 needs A = (y1 - x1)(y2 - x2), B = (y1 + x1)(y2 + x2), C = t1 * (k t2), D = 2 and the four final
+  // products: 7 instead of the 9 of the general unified addition.  Negation of an entry: -x, -t, -kt.
+  MGB_DEV static vpoint add_refs(const uint32_t* table, uint32_t ra, uint32_t rb) {
+    const uint32_t* ea = table + (size_t)(ra & REF_IDX) * ENTRY_LIMBS;
+    const uint32_t* eb = table + (size_t)(rb & REF_IDX) * ENTRY_LIMBS;
+    Fe<FP> x1 = ldg_fe<FP>(ea), y1 = ldg_fe<FP>(ea + N), t1 = ldg_fe<FP>(ea + 2 * N);
+    Fe<FP> x2 = ldg_fe<FP>(eb), y2 = ldg_fe<FP>(eb + N), kt2 = ldg_fe<FP>(eb + 3 * N);
+    if (ra & REF_NEG) { x1 = F::neg(x1); t1 = F::neg(t1); }
+    if (rb & REF_NEG) { x2 = F::neg(x2); kt2 = F::neg(kt2); }
+    const Fe<FP> A = F::mul(F::sub(y1, x1), F::sub(y2, x2));
+    const Fe<FP> B = F::mul(F::add(y1, x1), F::add(y2, x2));
+    const Fe<FP> Cc = F::mul(t1, kt2);
+    const Fe<FP> D = F::dbl(F::one());
+    const Fe<FP> E = F::sub(B, A), Ff = F::sub(D, Cc), Gg = F::add(D, Cc), H = F::add(B, A);
+    vpoint r;
+    r.X = F::mul(E, Ff); r.Y = F::mul(Gg, H); r.T = F::mul(E, H); r.Z = F::mul(Ff, Gg);
+    return r;
+  }
 
   // table entry (x, y, t = x*y) -> extended point with Z = 1 (negation: -x, -t)
   MGB_DEV static vpoint load_entry(const uint32_t* table, uint32_t idx, bool /*endo*/, bool negate) {
@@ -208,7 +229,8 @@ struct TwistedEdwardsPolicy {
   MGB_DEV static void make_entry(uint32_t* e, const Fe<FP>& x_plain, const Fe<FP>& y_plain, bool inf) {
     Fe<FP> x = F::to_mont(x_plain), y = F::to_mont(y_plain);
     if (inf) { x = F::zero(); y = F::one(); }
-    st_fe<FP>(e, x); st_fe<FP>(e + N, y); st_fe<FP>(e + 2 * N, F::mul(x, y));
+    const Fe<FP> t = F::mul(x, y);
+    st_fe<FP>(e, x); st_fe<FP>(e + N, y); st_fe<FP>(e + 2 * N, t); st_fe<FP>(e + 3 * N, F::mul(t, G::k2d()));
   }
   MGB_DEV static void make_entry_from_acc(uint32_t* e, const acc& a) {
     Fe<FP> x, y; G::to_affine(a, x, y);
@@ -265,6 +287,10 @@ struct WeierstrassBasicPolicy : MAIN {
   MGB_DEV static void store_v(uint32_t* V, uint32_t slot, const vpoint& p) { MAIN::st_acc(V + (size_t)slot * V_LIMBS, p); }
   MGB_DEV static acc add_v(const acc& a, const vpoint& p) { return G::add(a, p); }
   MGB_DEV static acc add_vv(const vpoint& p, const vpoint& q) { return G::add(p, q); }
+  // two table entries are both affine: mmadd (6 products) instead of the general XYZZ addition (14)
+  MGB_DEV static vpoint add_refs(const uint32_t* table, uint32_t ra, uint32_t rb) {
+    return G::mmadd(MAIN::load_entry(table, ra & REF_IDX, false, (ra & REF_NEG) != 0), MAIN::load_entry(table, rb & REF_IDX, false, (rb & REF_NEG) != 0));
+  }
 };
 
 typedef WeierstrassPolicy<Fp377, Bls12377Consts, Glv377, 127> CurveBls377;     // |k| < 2^126 (gen_constants.py self-check; reference maxBits = 126)
@@ -985,8 +1011,7 @@ __global__ void __launch_bounds__(256) k_pair_add(uint32_t* __restrict__ V, cons
         const uint2 rr = recs[q0 + idx];
         ent.slot = 2u * (q0 + idx);
         ent.life = lifes[q0 + idx];
-        typename CV::vpoint A = load_ref<CV>(table, rr.x);
-        if (rr.y != REF_EMPTY) A = CV::add(A, load_ref<CV>(table, rr.y));
+        const typename CV::vpoint A = rr.y != REF_EMPTY ? CV::add_refs(table, rr.x, rr.y) : load_ref<CV>(table, rr.x);
         CV::store_v(V, ent.slot, A);
       } else {
         ent = pairs[idx];

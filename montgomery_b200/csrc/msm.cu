@@ -690,6 +690,15 @@ size_t entry_bytes(int curve) {
   }
 }
 
+size_t point_bytes(int curve) {   // x||y little-endian bytes of one point in the caller's format
+  switch (curve) {
+    case MGB_BLS12_377_G1: return 2 * CurveBls377::COORD_BYTES;
+    case MGB_PALLAS: return 2 * CurvePallas::COORD_BYTES;
+    case MGB_BLS12_381_G1: return 2 * CurveBls381::COORD_BYTES;
+    default: return 2 * CurveEd377::COORD_BYTES;
+  }
+}
+
 int msm_common(mgb_ctx* ctx, const void* scalars, bool dev, size_t n, const mgb_opts* opts, uint8_t* out_xy, int* out_is_zero, mgb_timing* tm) {
   if (!ctx || !out_xy || (!scalars && n)) return fail(ctx, MGB_E_INVALID, "mgb_msm: NULL argument");
   if (n > ctx->npoints) return fail(ctx, ctx->npoints ? MGB_E_INVALID : MGB_E_STATE, "mgb_msm: n exceeds the number of points set");
@@ -895,7 +904,7 @@ int mgb_multi_create(mgb_multi** out, int curve, const int* device_ids, int n_de
 int mgb_multi_set_points(mgb_multi* m, const uint8_t* xy_le, const uint8_t* is_zero, size_t n) {
   if (!m || (!xy_le && n)) return multi_fail(m, MGB_E_INVALID, "mgb_multi_set_points: NULL argument");
   multi_shards(m, n);
-  const size_t pb = entry_bytes(m->ctxs[0]->curve) / 3 * 2;      // x||y bytes of one point
+  const size_t pb = point_bytes(m->ctxs[0]->curve);              // x||y bytes of one point
   return multi_each(m, [&](size_t g) {
     return mgb_set_points(m->ctxs[g], xy_le + m->lo[g] * pb, is_zero ? is_zero + m->lo[g] : nullptr, m->hi[g] - m->lo[g]);
   });
@@ -911,7 +920,7 @@ int mgb_multi_random_points(mgb_multi* m, uint64_t seed, size_t n) {
 int mgb_multi_get_points(mgb_multi* m, size_t first, size_t n, uint8_t* xy_le, uint8_t* is_zero) {
   if (!m || (!xy_le && n)) return multi_fail(m, MGB_E_INVALID, "mgb_multi_get_points: NULL argument");
   if (first + n > m->npoints) return multi_fail(m, MGB_E_INVALID, "mgb_multi_get_points: range exceeds stored points");
-  const size_t pb = entry_bytes(m->ctxs[0]->curve) / 3 * 2;
+  const size_t pb = point_bytes(m->ctxs[0]->curve);
   for (size_t g = 0; g < m->ctxs.size(); g++) {
     const size_t a = std::max(first, m->lo[g]), b = std::min(first + n, m->hi[g]);
     if (a >= b) continue;

@@ -226,7 +226,7 @@ def test_pair_add_two_rounds_twisted_edwards(emu_k):
     table = []
     for P in pts:
         x, y = T.to_affine(P)
-        table += limbs(M(x)) + limbs(M(y)) + limbs(M(x * y % p))
+        table += limbs(M(x)) + limbs(M(y)) + limbs(M(x * y % p)) + limbs(M(2 * prm.d * x * y % p))      # x | y | t | k t
     ref_point = lambda ref: T.negate(pts[ref & 0x3FFFFFFF]) if ref & REF_NEG else pts[ref & 0x3FFFFFFF]
     rand_ref = lambda: rnd.randrange(npts) | rnd.choice([0, REF_NEG])
     buckets = []
