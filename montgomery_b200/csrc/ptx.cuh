@@ -33,6 +33,12 @@ inline uint32_t sub3(uint32_t a, uint32_t b, uint32_t bin, bool setcf) { uint64_
 inline uint32_t sub_cc(uint32_t a, uint32_t b) { return sub3(a, b, 0, true); }
 inline uint32_t subc_cc(uint32_t a, uint32_t b) { return sub3(a, b, CF, true); }
 inline uint32_t subc(uint32_t a, uint32_t b) { return sub3(a, b, CF, false); }
+// x + y (64 bit); `carries` is incremented by the carry out
+inline unsigned long long add64_count(unsigned long long x, unsigned long long y, uint32_t& carries) {
+  const unsigned long long r = x + y;
+  carries += r < x ? 1u : 0u;
+  return r;
+}
 }  // namespace ptx
 }  // namespace mgb
 #else
@@ -55,6 +61,16 @@ MGB_DEV uint32_t addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u
 MGB_DEV uint32_t sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 MGB_DEV uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 MGB_DEV uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+// x + y (64 bit); `carries` is incremented by the carry out.  One carry chain of three instructions (IADD3, IADD3.X,
+// IADD3.X) instead of the add + two-word compare + select the C idiom `r = x + y; carries += r < x` compiles to.
+MGB_DEV unsigned long long add64_count(unsigned long long x, unsigned long long y, uint32_t& carries) {
+  uint32_t lo, hi, c;
+  asm("add.cc.u32 %0,%3,%5;\n\taddc.cc.u32 %1,%4,%6;\n\taddc.u32 %2,%7,0;"
+      : "=r"(lo), "=r"(hi), "=r"(c)
+      : "r"((uint32_t)x), "r"((uint32_t)(x >> 32)), "r"((uint32_t)y), "r"((uint32_t)(y >> 32)), "r"(carries));
+  carries = c;
+  return ((unsigned long long)hi << 32) | lo;
+}
 }  // namespace ptx
 }  // namespace mgb
 #endif  // MGB_HOST_EMU
