@@ -1037,6 +1037,8 @@ struct ReduceGeom {
   int shift[6];     // bit position of each digit
   int NP;           // partial sums per group (power of two)
   int CH;           // buckets per partial sum
+  int VB;           // NV = 2^VB group slots per (window, digit): 32, or 16 / 8 when no digit is wider than 4 / 3 bits (small
+  int NV;           // windows: half of the groups -- and of the latency-bound tree work -- would be empty otherwise)
 };
 
 // Bucket sums after the last tree round: one thread per bucket adds whatever the bucket has left (the
@@ -1065,11 +1067,11 @@ __global__ void __launch_bounds__(128) k_group_partial(MsmParams pr, ReduceGeom 
                                                        const uint32_t* __restrict__ Bsum /* bucket sums of k_bucket_finish, or nullptr */, uint32_t* __restrict__ P) {
   // thread -> (window w, digit d, value v, chunk ch)
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t total = (uint32_t)Kg * gm.D * 32 * gm.NP;
+  uint32_t total = (uint32_t)Kg * gm.D * gm.NV * gm.NP;
   if (t >= total) return;
-  t += (uint32_t)w_begin * gm.D * 32 * gm.NP;          // global (window, digit, value, chunk) index
+  t += (uint32_t)w_begin * gm.D * gm.NV * gm.NP;       // global (window, digit, value, chunk) index
   uint32_t ch = t % gm.NP, g = t / gm.NP;
-  uint32_t v = g & 31, wd = g >> 5;
+  uint32_t v = g & (uint32_t)(gm.NV - 1), wd = g >> gm.VB;
   uint32_t d = wd % gm.D, w = wd / gm.D;
   typename CV::acc acc = CV::acc_zero();
   // digit d of the weight index idx = (bucket >> sub): bits [shift + sub, ...) of the bucket number
@@ -1115,7 +1117,7 @@ __global__ void __launch_bounds__(128) k_group_partial(MsmParams pr, ReduceGeom 
 // window is sparse and spread over sub-buckets, MsmParams::top_sub, so its groups can be larger).  Groups lie back to back.
 struct AffineRedGeom {
   int GS0, GS1;
-  uint32_t g_top;        // first group of the top window = (K - 1) * D * 32
+  uint32_t g_top;        // first group of the top window = (K - 1) * D * NV
   uint32_t n0;           // slots of the groups below it = g_top * GS0
   uint32_t total;        // all slots
 };
@@ -1132,7 +1134,7 @@ __global__ void __launch_bounds__(256) k_affine_gather(MsmParams pr, ReduceGeom 
   const int GS = top ? ag.GS1 : ag.GS0;
   const uint32_t tt = top ? t - ag.n0 : t;
   const uint32_t m = tt & (uint32_t)(GS - 1), g = (top ? ag.g_top : 0u) + tt / (uint32_t)GS;
-  const uint32_t v = g & 31, wd = g >> 5;
+  const uint32_t v = g & (uint32_t)(gm.NV - 1), wd = g >> gm.VB;
   const uint32_t d = wd % gm.D, w = wd / gm.D;
   const int sub = (w == (uint32_t)pr.K - 1) ? pr.top_sub : 0;
   const int nb = pr.c - 1;
@@ -1221,7 +1223,7 @@ __global__ void __launch_bounds__(192) k_window_sums(MsmParams pr, ReduceGeom gm
   const int lane = threadIdx.x & 31, d = threadIdx.x >> 5, w = w_begin + blockIdx.x;
   if (d < gm.D) {
     typename CV::acc G = CV::acc_zero();
-    if (lane < (1 << gm.width[d])) G = CV::ld_acc(P + ((size_t)((w * gm.D + d) * 32 + lane) * gm.NP) * CV::ACC_LIMBS);
+    if (lane < (1 << gm.width[d])) G = CV::ld_acc(P + ((size_t)((w * gm.D + d) * gm.NV + lane) * gm.NP) * CV::ACC_LIMBS);
     typename CV::acc S = G;
     _Pragma("unroll 1") for (int dl = 1; dl < 32; dl <<= 1) {
       typename CV::acc o = shfl_acc<CV>(S, lane + dl > 31 ? lane : lane + dl);
@@ -1290,17 +1292,17 @@ __global__ void __launch_bounds__(128) k_digit_sums(MsmParams pr, ReduceGeom gm,
   auto lds = [&](int vv) -> fe { fe r; _Pragma("unroll") for (int i = 0; i < N; i++) r.v[i] = sm[(vv * 4 + k) * N + i]; return r; };
   auto sts = [&](int vv, const fe& a) { _Pragma("unroll") for (int i = 0; i < N; i++) sm[(vv * 4 + k) * N + i] = a.v[i]; };
   fe S = Q::zero_coord(k);
-  if (v < (1 << gm.width[d])) S = ld_fe<FP>(P + ((size_t)((w * gm.D + d) * 32 + v) * gm.NP) * CV::ACC_LIMBS + k * N);
-  _Pragma("unroll 1") for (int dl = 1; dl < 32; dl <<= 1) {
+  if (v < (1 << gm.width[d])) S = ld_fe<FP>(P + ((size_t)((w * gm.D + d) * gm.NV + v) * gm.NP) * CV::ACC_LIMBS + k * N);
+  _Pragma("unroll 1") for (int dl = 1; dl < gm.NV; dl <<= 1) {        // values >= NV do not exist (zero): log2(NV) steps
     sts(v, S);
     __syncthreads();
-    const fe o = (v + dl <= 31) ? lds(v + dl) : Q::zero_coord(k);
+    const fe o = (v + dl <= gm.NV - 1) ? lds(v + dl) : Q::zero_coord(k);
     __syncthreads();
     S = Q::add(S, o);
   }
   if (v == 0 && d == 0) st_fe<FP>(out + ((size_t)pr.K * gm.D + w) * CV::ACC_LIMBS + k * N, S);
-  fe X = (v >= 1) ? S : Q::zero_coord(k);
-  _Pragma("unroll 1") for (int dl = 16; dl >= 1; dl >>= 1) {
+  fe X = (v >= 1 && v < gm.NV) ? S : Q::zero_coord(k);
+  _Pragma("unroll 1") for (int dl = gm.NV >> 1; dl >= 1; dl >>= 1) {
     sts(v, X);
     __syncthreads();
     const fe o = (v < dl) ? lds(v + dl) : Q::zero_coord(k);

@@ -241,8 +241,12 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
     if (const char* ev = getenv("MGB_DEBUG_CH")) gm.CH = std::max(1, atoi(ev));
     gm.NP = 1;
     while ((uint32_t)gm.NP * gm.CH < gmax) gm.NP <<= 1;
+    gm.VB = 3;
+    for (int d = 0; d < gm.D; d++) gm.VB = std::max(gm.VB, gm.width[d]);
+    if (const char* ev = getenv("MGB_DEBUG_NV32")) { if (atoi(ev)) gm.VB = 5; }
+    gm.NV = 1 << gm.VB;
   }
-  const uint32_t ngroups = (uint32_t)pr.K * gm.D * 32;
+  const uint32_t ngroups = (uint32_t)pr.K * gm.D * gm.NV;
   ENS(ctx, ctx->acc_out, CV::ACC_LIMBS * 4);
   CU(ctx, cudaEventRecord(ctx->ev[EV_START], st));
   // Host scalars travel in chunks on a second stream; the digit kernel of a chunk starts as soon as that chunk has
@@ -454,8 +458,8 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
     }
     if (g == 0) CU(ctx, cudaEventRecord(ctx->ev[EV_ACC], st));
     // bucket reduction of the group's windows (digit-decomposed weights, see engine.cuh)
-    const uint32_t ngroups_g = (uint32_t)Kg * gm.D * 32;
-    uint32_t* Pg = (uint32_t*)ctx->redU[0].p + (size_t)w_begin * gm.D * 32 * gm.NP * CV::ACC_LIMBS;
+    const uint32_t ngroups_g = (uint32_t)Kg * gm.D * gm.NV;
+    uint32_t* Pg = (uint32_t*)ctx->redU[0].p + (size_t)w_begin * gm.D * gm.NV * gm.NP * CV::ACC_LIMBS;
     const uint32_t* bsum = nullptr;
     bool reduced_affine = false;
     if constexpr (CV::BATCH_AFFINE) {
@@ -472,9 +476,9 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
         while ((uint32_t)ag.GS0 < (pr.L >> minw)) ag.GS0 <<= 1;               // slots per group (largest group, power of two)
         ag.GS1 = 2;
         while ((uint32_t)ag.GS1 < (pr.L >> minw_top)) ag.GS1 <<= 1;           // the same for the (possibly clipped) top window
-        ag.g_top = (uint32_t)(pr.K - 1) * gm.D * 32;
+        ag.g_top = (uint32_t)(pr.K - 1) * gm.D * gm.NV;
         ag.n0 = ag.g_top * (uint32_t)ag.GS0;
-        const size_t nslots = (size_t)ag.n0 + (size_t)gm.D * 32 * ag.GS1;
+        const size_t nslots = (size_t)ag.n0 + (size_t)gm.D * gm.NV * ag.GS1;
         if (nslots >= (1ull << 31)) return fail(ctx, MGB_E_INVALID, "affine_reduction: too many group slots for this window size");
         ag.total = (uint32_t)nslots;
         const int GSmax = std::max(ag.GS0, ag.GS1);
