@@ -688,7 +688,7 @@ MGB_DEV typename CV::vpoint load_ref(const uint32_t* table, uint32_t ref) {
 // recs[q]; operands come from the point table, V is only written, no pair list is read.
 template <class CV, int EMAX, int MINB, bool FIRST>
 __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ V, const PairEnt* __restrict__ pairs,
-                                                         const uint32_t* __restrict__ npairs_ptr, int r, int E_big, uint32_t n_big,
+                                                         const uint32_t* __restrict__ npairs_ptr, int r, int E_big, int E_small, uint32_t n_big,
                                                          PairEnt* __restrict__ pairs_out, uint32_t* __restrict__ npairs_out,
                                                          uint32_t* __restrict__ tile_counter,
                                                          const uint2* __restrict__ recs, const uint8_t* __restrict__ lifes,
@@ -714,9 +714,7 @@ __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ 
   const int lane = tid & 31;
   const uint32_t q0 = FIRST ? offs[b_begin] >> 1 : 0u;
   const uint32_t npairs = FIRST ? (offs[b_end] >> 1) - q0 : *npairs_ptr;
-  // Guided tile sizes: the first n_big tiles hold E_big pairs per lane (few inversions), the rest a
-  // quarter of that, so the end of the round is not one long tile per straggling warp.
-  const int E_small = E_big >= 16 ? E_big / 4 : E_big;
+  // Tile sizes: the first n_big tiles hold E_big pairs per lane, the rest E_small (chosen by the host, see msm_core).
   const uint32_t TILE_BIG = 32u * (uint32_t)E_big, TILE_SMALL = 32u * (uint32_t)E_small;
   const uint32_t nbig = min(n_big, npairs / TILE_BIG);
   const uint32_t rest = npairs - nbig * TILE_BIG;

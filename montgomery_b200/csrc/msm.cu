@@ -428,6 +428,7 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
           if (q && k == r && atoi(q) != 0) E = std::min(EMAX, std::abs(atoi(q)));
         }
         if (const char* ev = getenv("MGB_DEBUG_NBIG")) n_big = (uint32_t)(atof(ev) * warps);
+        int E_small = E >= 16 ? E / 4 : E;          // only used when n_big cuts the tile list (tuning knobs)
         // per-warp scratch for the prefix products of a tile (see k_batch_add)
         const size_t pre_bytes = (size_t)ctx->sm_count * MINB * 4 * EMAX * (CV::N / 4) * 32 * 16;
         ENS(ctx, ctx->prebuf, pre_bytes * 4);     // one area per window group (at most 4)
@@ -435,12 +436,12 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
         if (r == 0) {
           auto kern = k_batch_add<CV, EMAX, MINB, true>;
           cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, MINB > 4 ? 90 : 75);   // MINB blocks x 36 KB of staging
-          kern<<<ctx->sm_count * MINB, 128, 0, sg>>>((uint32_t*)ctx->V.p, nullptr, nullptr, r, E, n_big, pout, cnt + r + 1, tcnt + r,
+          kern<<<ctx->sm_count * MINB, 128, 0, sg>>>((uint32_t*)ctx->V.p, nullptr, nullptr, r, E, E_small, n_big, pout, cnt + r + 1, tcnt + r,
                                                     (const uint2*)recs, lifes, table, offs, b_begin, b_end, scratch);
         } else {
           auto kern = k_batch_add<CV, EMAX, MINB, false>;
           cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, MINB > 4 ? 90 : 75);
-          kern<<<ctx->sm_count * MINB, 128, 0, sg>>>((uint32_t*)ctx->V.p, pin, cnt + r, r, E, n_big, pout, cnt + r + 1, tcnt + r,
+          kern<<<ctx->sm_count * MINB, 128, 0, sg>>>((uint32_t*)ctx->V.p, pin, cnt + r, r, E, E_small, n_big, pout, cnt + r + 1, tcnt + r,
                                                     nullptr, nullptr, nullptr, nullptr, 0, 0, scratch);
         }
       } else {
@@ -500,7 +501,7 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
           const int E = (int)std::min<uint64_t>(EMAX, std::max<uint64_t>(4, (per_lane + kt - 1) / kt));
           auto kern = k_batch_add<CV, EMAX, MINB, false>;
           cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, MINB > 4 ? 90 : 75);
-          kern<<<ctx->sm_count * MINB, 128, 0, sg>>>((uint32_t*)ctx->W.p, apl[r & 1], acnt + r, r, E, 0xffffffffu, apl[(r & 1) ^ 1], acnt + r + 1, atcnt + r,
+          kern<<<ctx->sm_count * MINB, 128, 0, sg>>>((uint32_t*)ctx->W.p, apl[r & 1], acnt + r, r, E, E, 0xffffffffu, apl[(r & 1) ^ 1], acnt + r + 1, atcnt + r,
                                                     nullptr, nullptr, nullptr, nullptr, 0, 0, (uint4*)ctx->prebuf.p);
           launches++;
         }

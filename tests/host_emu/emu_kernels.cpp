@@ -13,7 +13,7 @@ static void batch_add(uint32_t* V, const PairEnt* pairs, const uint32_t* npairs_
                       uint32_t* npairs_out, uint32_t* tile_counter, const uint2* recs, const uint8_t* lifes, const uint32_t* table,
                       const uint32_t* offs, uint32_t b_begin, uint32_t b_end, uint4* scratch, int blocks) {
   simt::run_grid((unsigned)blocks, 128, [&] {
-    k_batch_add<CV, 8, 4, FIRST>(V, pairs, npairs_ptr, r, E_big, n_big, pairs_out, npairs_out, tile_counter, recs, lifes, table, offs, b_begin, b_end, scratch);
+    k_batch_add<CV, 8, 4, FIRST>(V, pairs, npairs_ptr, r, E_big, E_big >= 16 ? E_big / 4 : E_big, n_big, pairs_out, npairs_out, tile_counter, recs, lifes, table, offs, b_begin, b_end, scratch);
   });
 }
 
