@@ -21,6 +21,7 @@ src/curve-random.ts:24-92), result returned to the host as the canonical affine 
 The oracle (oracle/) is used here only for `cpu_baseline` and `--impl reference`.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -94,19 +95,29 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def wait_first_sample(self, timeout=3.0):
+        """nvidia-smi takes ~0.1 s to initialise NVML (and holds driver locks meanwhile): the sampler is started before
+        the warm-up steps and the timed region only begins once it is in its steady 100 ms polling loop."""
+        t_end = time.perf_counter() + timeout
+        while self.proc and not self.lines and time.perf_counter() < t_end:
+            time.sleep(0.005)
+
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples taken in [t0, t1] (perf_counter values bracketing the timed region)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        if t1 is not None and not any(t0 <= t <= t1 + 0.1 for t, _ in self.lines):
+            time.sleep(0.15)            # region shorter than one polling period: take the sample right after it
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        inside = [ln for t, ln in self.lines if t0 is None or t0 <= t <= t1 + 0.1]
+        for ln in inside or [ln for _, ln in self.lines[-1:]]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -274,11 +285,14 @@ def run_b200(args):
             return sharded.msm(host_sets[k] if e2e else dev_sets[k], n, on_device=not e2e, c=c)
 
         def timed(e2e, smp=None):
-            for i in range(warmup):
-                step(i, e2e)
-            barrier()
             if smp:
                 smp.start()
+                smp.wait_first_sample()
+            for i in range(warmup):
+                step(i, e2e)
+            gc.collect()
+            gc.disable()                # no collector pauses inside the timed region
+            barrier()
             t0 = time.perf_counter()
             phases, launches, res, tm = {}, 0, None, None
             for i in range(steps):
@@ -288,7 +302,8 @@ def run_b200(args):
                     phases[key] = phases.get(key, 0.0) + tm[key] / steps
             barrier()
             el = time.perf_counter() - t0
-            clocks = smp.stop() if smp else None
+            gc.enable()
+            clocks = smp.stop(t0, t0 + el) if smp else None
             t = torch.tensor([el, phases["total"]], dtype=torch.float64, device="cuda")
             if dist:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -3,7 +3,7 @@
 set -u
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/r2q_topo.txt 2>&1
-for n in 8 4; do
+for n in 8 4 2; do
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2961$n bench.py --gpus $n --steps 10 --warmup 3 > gpurun_out/r2q_bench$n.json 2> gpurun_out/r2q_bench$n.err
   tail -2 gpurun_out/r2q_bench$n.err
   python - $n <<'PY'
