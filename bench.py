@@ -280,23 +280,27 @@ def run_b200(args):
         dev_sets = [h.cuda(non_blocking=False) for h in host_sets]
         torch.cuda.synchronize()
 
-        def step(i, e2e):
+        def step(i, e2e, pipelined=False):
             k = i % nsets
+            if pipelined:       # the NEXT step's scalars start travelling before this step's MSM is launched
+                sharded.prefetch(host_sets[(i + 1) % nsets], n)
             return sharded.msm(host_sets[k] if e2e else dev_sets[k], n, on_device=not e2e, c=c)
 
-        def timed(e2e, smp=None):
+        def timed(e2e, smp=None, pipelined=False):
             if smp:
                 smp.start()
                 smp.wait_first_sample()
+            if pipelined:
+                sharded.prefetch(host_sets[0], n)
             for i in range(warmup):
-                step(i, e2e)
+                step(i, e2e, pipelined)
             gc.collect()
             gc.disable()                # no collector pauses inside the timed region
             barrier()
             t0 = time.perf_counter()
             phases, launches, res, tm = {}, 0, None, None
             for i in range(steps):
-                res, tm = step(warmup + i, e2e)
+                res, tm = step(warmup + i, e2e, pipelined)
                 launches += tm["n_launches"]
                 for key in ("h2d_scalars", "decompose_slice", "sort", "accumulate", "reduce", "final_sum", "total"):
                     phases[key] = phases.get(key, 0.0) + tm[key] / steps
@@ -304,6 +308,8 @@ def run_b200(args):
             el = time.perf_counter() - t0
             gc.enable()
             clocks = smp.stop(t0, t0 + el) if smp else None
+            if pipelined:       # the set uploaded during the last timed step: consume it, so that no prefetch slot stays occupied
+                step(warmup + steps, e2e, False)
             t = torch.tensor([el, phases["total"]], dtype=torch.float64, device="cuda")
             if dist:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -311,13 +317,16 @@ def run_b200(args):
 
         el, dev_ms_max, phases, launches, res, tm, clocks = timed(False, sampler)
         el_e2e, _, phases_e2e, _, res_e2e, _, _ = timed(True)
+        el_pipe, res_pipe, phases_pipe = None, None, None
+        if nsets >= 2:          # software-pipelined end to end: the upload of step i + 1 overlaps the MSM of step i
+            el_pipe, _, phases_pipe, _, res_pipe, _, _ = timed(True, pipelined=True)
         # parity: the closed form over every rank's shard, for the scalar set of the LAST step of each timed loop
         last = (warmup + steps - 1) % nsets
         ks = gather_ints(inputs.dot_known_dlogs(np_sets[last], inputs.known_dlogs(seed_points + rank, n)))
         O = OracleCurve(label)
         expect = O.result_of(O.scale(sum(ks) % O.q, O.G))
-        parity_ok = bool(res == expect and res_e2e == expect)
-        out = {"curve": curve, "n": n, "el": el, "el_e2e": el_e2e, "dev_ms_max": dev_ms_max, "phases": phases, "phases_e2e": phases_e2e,
+        parity_ok = bool(res == expect and res_e2e == expect and (res_pipe is None or res_pipe == expect))
+        out = {"curve": curve, "n": n, "el": el, "el_e2e": el_e2e, "el_pipe": el_pipe, "phases_pipe": phases_pipe, "dev_ms_max": dev_ms_max, "phases": phases, "phases_e2e": phases_e2e,
                "launches": launches, "res": res, "tm": tm, "clocks": clocks, "parity_ok": parity_ok, "sharded": sharded,
                "host_sets": host_sets}
         return out
@@ -356,6 +365,7 @@ def run_b200(args):
             blk = {"workload": "%s MSM, 2^%d points, 1 GPU" % (cfg["curve"], cfg["logn"]), "ms_device": dev_ms,
                    "ms_per_step": r["el"] / extra_steps * 1e3, "points_per_s": nn / (r["el"] / extra_steps),
                    "e2e_ms_per_step": r["el_e2e"] / extra_steps * 1e3, "e2e_points_per_s": nn / (r["el_e2e"] / extra_steps),
+                   "e2e_pipelined_ms_per_step": r["el_pipe"] and r["el_pipe"] / extra_steps * 1e3,
                    "roofline_frac": cfg["mults_per_point"] * cfg["mads_per_mult"] * nn / (dev_ms * 1e-3) / peak_mads,
                    "window_bits": r["tm"]["c"], "windows": r["tm"]["K"], "tree_rounds": r["tm"]["rounds"], "kernels_per_msm": r["tm"]["n_launches"],
                    "phases_ms": r["phases"], "parity_ok": r["parity_ok"]}
@@ -378,11 +388,12 @@ def run_b200(args):
             head_engine_closed = True
         ln = STRONG_LOGN - (world.bit_length() - 1)
         ssteps = max(2, min(args.steps, 5))
-        r = measure("bls12-377", ln, SEED_POINTS ^ 0x5A5A, 0x6D6F6E74 ^ 4, ssteps, 2, nsets=1)
+        r = measure("bls12-377", ln, SEED_POINTS ^ 0x5A5A, 0x6D6F6E74 ^ 4, ssteps, 2, nsets=2)
         tot = (1 << ln) * world
         strong = {"workload": "bls12-377 G1 MSM, 2^%d points in total = 2^%d per GPU on %d GPU(s) (BASELINE config 5)" % (STRONG_LOGN, ln, world),
                   "scaling": "strong", "n_gpus": world, "ms_per_step": r["el"] / ssteps * 1e3, "ms_device_max": r["dev_ms_max"],
                   "points_per_s": tot / (r["el"] / ssteps), "e2e_ms_per_step": r["el_e2e"] / ssteps * 1e3, "e2e_points_per_s": tot / (r["el_e2e"] / ssteps),
+                  "e2e_pipelined_ms_per_step": r["el_pipe"] and r["el_pipe"] / ssteps * 1e3,
                   "roofline_frac": STRONG_MULTS_PER_POINT * MADS_PER_FIELD_MULT * (1 << ln) / (r["dev_ms_max"] * 1e-3) / peak_mads,
                   "window_bits": r["tm"]["c"], "windows": r["tm"]["K"], "tree_rounds": r["tm"]["rounds"], "steps": ssteps, "parity_ok": r["parity_ok"]}
         r["sharded"].close()
@@ -432,7 +443,14 @@ def run_b200(args):
                                           "results of the last device-timed and the last end-to-end step of every configuration in this line",
         "msm_ms": ms_step, "msm_ms_device": phases["total"], "phases_ms": phases, "result_x": hex(head["res"]["x"]),
         "e2e": {"value": e2e_value, "unit": "points/s", "ms_per_step": head["el_e2e"] / args.steps * 1e3,
-                "h2d_bytes_per_step": n * 32 * world, "d2h_bytes_per_step": (2 * curve.coord_bytes + 4) * world, "phases_ms": head["phases_e2e"]},
+                "h2d_bytes_per_step": n * 32 * world, "d2h_bytes_per_step": (2 * curve.coord_bytes + 4) * world, "phases_ms": head["phases_e2e"],
+                "mode": "one blocking call per step: upload this step's scalars (pinned host memory, 4 chunks overlapped with the digit kernel), "
+                        "MSM, read the point back",
+                "pipelined": head["el_pipe"] and {
+                    "value": total_points / (head["el_pipe"] / args.steps), "unit": "points/s", "ms_per_step": head["el_pipe"] / args.steps * 1e3, "phases_ms": head["phases_pipe"],
+                    "note": "the same steps with mgb_msm_prefetch: every step still uploads its own scalar set and reads its own result back, but "
+                            "the upload of step i+1 is started before the MSM call of step i and overlaps it (what a prover committing to "
+                            "several polynomials does)"}},
         "gpu_launches": head["launches"], "clocks": head["clocks"], "roofline": roofline, "hbm_phases": hbm,
         "host_affinity": numa,
     }

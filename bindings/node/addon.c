@@ -126,6 +126,21 @@ static napi_value Msm(napi_env env, napi_callback_info info) {
   return promise;
 }
 
+/* prefetch(ctx, scalars, n): starts the upload of the scalars of the NEXT msm call (mgb_msm_prefetch).  The caller keeps the
+ * Uint8Array alive and unchanged until the msm(ctx, scalars, n) call that consumes it has resolved; a JS heap buffer is
+ * pageable, so the driver stages the copy (the call returns once the staging is done, the transfer itself still overlaps). */
+static napi_value Prefetch(napi_env env, napi_callback_info info) {
+  size_t argc = 3, len; napi_value argv[3], undef; void* data; int64_t n; napi_typedarray_type ty; mgb_ctx* ctx;
+  CHECK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+  if (!(ctx = ctx_of(env, argv[0]))) return NULL;
+  CHECK(napi_get_typedarray_info(env, argv[1], &ty, &len, &data, NULL, NULL));
+  CHECK(napi_get_value_int64(env, argv[2], &n));
+  if (ty != napi_uint8_array || n < 0 || len < 32 * (size_t)n) { napi_throw_type_error(env, NULL, "scalars: Uint8Array of n * 32 bytes, little-endian"); return NULL; }
+  if (mgb_msm_prefetch(ctx, (const uint8_t*)data, (size_t)n) != 0) { napi_throw_error(env, NULL, mgb_last_error(ctx)); return NULL; }
+  CHECK(napi_get_undefined(env, &undef));
+  return undef;
+}
+
 /* ---- one process, several GPUs: mgb_multi_* (contexts, shards and the NCCL all-gather live inside the library) */
 static mgb_multi* multi_of(napi_env env, napi_value v) {
   void* p = NULL;
@@ -200,6 +215,7 @@ static napi_value Init(napi_env env, napi_value exports) {
     {"setPoints", NULL, SetPoints, NULL, NULL, NULL, napi_default, NULL},
     {"randomPoints", NULL, RandomPoints, NULL, NULL, NULL, napi_default, NULL},
     {"msm", NULL, Msm, NULL, NULL, NULL, napi_default, NULL},
+    {"prefetch", NULL, Prefetch, NULL, NULL, NULL, napi_default, NULL},
     {"createMulti", NULL, CreateMulti, NULL, NULL, NULL, napi_default, NULL},
     {"setPointsMulti", NULL, SetPointsMulti, NULL, NULL, NULL, napi_default, NULL},
     {"randomPointsMulti", NULL, RandomPointsMulti, NULL, NULL, NULL, napi_default, NULL},

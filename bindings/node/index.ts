@@ -39,6 +39,9 @@ export function create(curve: Curve, { device = 0, maxPoints = 1 << 20 } = {}) {
     // every addition of the engine is complete, so the "unsafe" variant is the same call
     msmUnsafe: (scalars: Uint8Array, points: Points, N: number, _verbose = false, { c = 0 } = {}) => run(scalars, points, N, c),
     msmProjective: (scalars: Uint8Array, points: Points, N: number, { c = 0 } = {}) => run(scalars, points, N, c, 1),
+    // extension: start uploading the scalars of the NEXT msm call while the current one runs (mgb_msm_prefetch); pass the
+    // same Uint8Array and N to msm afterwards and keep it unchanged until that call resolves
+    prefetchScalars(scalars: Uint8Array, N: number): void { addon.prefetch(ctx, scalars, N); },
   };
   return { Parallel };
 }

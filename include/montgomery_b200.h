@@ -109,6 +109,17 @@ int mgb_get_points(mgb_ctx* ctx, size_t first, size_t n, uint8_t* xy_le, uint8_t
 int mgb_msm(mgb_ctx* ctx, const uint8_t* scalars_le32, size_t n, const mgb_opts* opts,
             uint8_t* out_xy_le, int* out_is_zero, mgb_timing* timing);
 
+/* Registers a host scalar set for upload AHEAD of its MSM and returns at once.  The copy is started by the next MSM call
+ * of this context, behind the launch of its first tree round, and runs on its own stream while that MSM computes (started
+ * any earlier it would slow the bandwidth-bound digit / sort phase down).  The following mgb_msm / mgb_msm_partial /
+ * mgb_msm_sharded call whose host pointer and n are the ones given here uses the uploaded copy instead of transferring
+ * again; if no MSM ran in between, that call simply uploads the set itself.  The reference has no counterpart (its
+ * scalars already live in the Wasm memory, src/msm-batched-affine.ts:69-75); a prover that calls `msm` for one polynomial
+ * after another calls mgb_msm_prefetch(set i + 1) before mgb_msm(set i).  The buffer must stay unchanged until the MSM
+ * call that consumes it returns (page-locked memory for a truly asynchronous copy); at most two sets wait at a time
+ * (MGB_E_INVALID beyond that); registering the same pointer again replaces the earlier registration. */
+int mgb_msm_prefetch(mgb_ctx* ctx, const uint8_t* scalars_le32, size_t n);
+
 /* Same with scalars already in device memory (device pointer), for kernel-only timing.
  * Contract for caller-owned device scalars (here and in mgb_msm_partial / mgb_msm_sharded with
  * scalars_on_device): the pointer must be 16-byte aligned (128-bit loads) and the data must be

@@ -31,7 +31,7 @@ class MgbTiming(ctypes.Structure):
 
 
 EXPORTS = [
-    "mgb_create", "mgb_set_points", "mgb_random_points", "mgb_get_points", "mgb_msm", "mgb_msm_device",
+    "mgb_create", "mgb_set_points", "mgb_random_points", "mgb_get_points", "mgb_msm", "mgb_msm_prefetch", "mgb_msm_device",
     "mgb_partial_bytes", "mgb_msm_partial", "mgb_combine_partials", "mgb_field_op", "mgb_microbench",
     "mgb_last_error", "mgb_destroy",
     "mgb_comm_unique_id", "mgb_comm_init", "mgb_comm_info", "mgb_msm_sharded",
@@ -55,6 +55,7 @@ def load():
     lib.mgb_get_points.argtypes = [vp, sz, sz, vp, vp]
     lib.mgb_msm.argtypes = [vp, vp, sz, ctypes.POINTER(MgbOpts), vp, ctypes.POINTER(ci), ctypes.POINTER(MgbTiming)]
     lib.mgb_msm_device.argtypes = lib.mgb_msm.argtypes
+    lib.mgb_msm_prefetch.argtypes = [vp, vp, sz]
     lib.mgb_partial_bytes.argtypes = [vp]
     lib.mgb_partial_bytes.restype = sz
     lib.mgb_msm_partial.argtypes = [vp, vp, ci, sz, ctypes.POINTER(MgbOpts), vp, ctypes.POINTER(MgbTiming)]

@@ -128,6 +128,25 @@ class MsmEngine:
         }
         return res, tm.as_dict()
 
+    def prefetch(self, scalars, n=None):
+        """Registers a host scalar set for upload ahead of its MSM (mgb_msm_prefetch): `scalars` is a C-contiguous uint8
+        numpy array or a raw host address (then n is required).  The next msm call of this engine starts the copy behind
+        its first tree round; the following msm / msm_sharded call with the SAME buffer and n uses the uploaded copy.
+        Keep the buffer alive and unchanged until that call has returned."""
+        if isinstance(scalars, np.ndarray):
+            if not scalars.flags["C_CONTIGUOUS"] or scalars.dtype != np.uint8:
+                raise ValueError("prefetch: a C-contiguous uint8 array is required (its address identifies the set)")
+            if n is None:
+                n = scalars.size // 32
+            if n * 32 > scalars.size:
+                raise ValueError("prefetch: n = %d exceeds the %d scalars in the buffer" % (n, scalars.size // 32))
+            ptr = scalars.ctypes.data
+        else:
+            if n is None:
+                raise ValueError("prefetch(address): n is required")
+            ptr = int(scalars)
+        self._check(self.lib.mgb_msm_prefetch(self._h, ctypes.c_void_p(ptr), n))
+
     def msm_partial(self, scalars_ptr, on_device, n, out_device_ptr, c=None):
         tm = _native.MgbTiming()
         opts = self._opts(c, False)

@@ -616,6 +616,16 @@ __global__ void __launch_bounds__(256) k_scatter(MsmParams pr, int w_begin, int 
   }
 }
 
+// Counters the host sizes the tree rounds from, written by the device into page-locked host memory:
+// host[64] padded slots, [65] largest bucket, [66] range flags of k_digits, [68 + r] additions of tree round r
+static __global__ void k_plan_to_host(const uint32_t* __restrict__ misc, const uint32_t* __restrict__ flags, uint32_t* host) {
+  const int t = threadIdx.x;
+  if (t < 2) host[64 + t] = misc[t];
+  if (t == 2) host[66] = *flags;
+  if (t < SCAN_ROUNDS) host[68 + t] = misc[512 + t];
+  __threadfence_system();
+}
+
 // ---------------------------------------------------------------- k_batch_add (Weierstrass)
 // Batched-affine additions with one field inversion per WARP tile of 32*E independent additions
 // (reference: batchAddNew / batchAddUnsafeNew, src/curve-affine.ts:376-522, and the Montgomery

@@ -77,5 +77,14 @@ class ShardedMsm:
             raise ValueError("msm: n_local = %d exceeds the %d scalars in the buffer" % (n_local, nbytes // 32))
         return self.engine.msm_sharded(ptr, on_device, n_local, c=c)
 
+    def prefetch(self, scalars, n_local: int):
+        """Starts the upload of this rank's NEXT host scalar set (pinned tensor or numpy array) while the current MSM
+        runs; the msm(...) call that passes the same buffer and n_local then finds it on the device."""
+        ptr = scalars.data_ptr() if isinstance(scalars, torch.Tensor) else scalars.ctypes.data
+        nbytes = scalars.numel() * scalars.element_size() if isinstance(scalars, torch.Tensor) else scalars.nbytes
+        if n_local * 32 > nbytes:
+            raise ValueError("prefetch: n_local = %d exceeds the %d scalars in the buffer" % (n_local, nbytes // 32))
+        self.engine.prefetch(ptr, n_local)
+
     def close(self):
         self.engine.close()

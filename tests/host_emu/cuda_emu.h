@@ -23,6 +23,7 @@ inline int __popc(uint32_t v) { return __builtin_popcount(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
 inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 inline void __threadfence_block() {}
+inline void __threadfence_system() {}
 inline uint32_t __ballot_sync(uint32_t, bool pred) { return simt::vote(pred); }
 inline uint32_t __shfl_up_sync(uint32_t, uint32_t v, unsigned d) { return simt::exchange(v, simt::t_lane < (int)d ? simt::t_lane : simt::t_lane - (int)d); }
 inline uint32_t __reduce_add_sync(uint32_t, uint32_t v) { uint32_t s = 0; for (int l = 0; l < 32; l++) s += simt::exchange(v, l); return s; }

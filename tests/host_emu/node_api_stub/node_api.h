@@ -42,6 +42,7 @@ napi_status napi_create_object(napi_env env, napi_value* result);
 napi_status napi_create_arraybuffer(napi_env env, size_t byte_length, void** data, napi_value* result);
 napi_status napi_create_typedarray(napi_env env, napi_typedarray_type type, size_t length, napi_value arraybuffer, size_t byte_offset, napi_value* result);
 napi_status napi_get_boolean(napi_env env, bool value, napi_value* result);
+napi_status napi_get_undefined(napi_env env, napi_value* result);
 napi_status napi_delete_reference(napi_env env, napi_ref ref);
 napi_status napi_delete_async_work(napi_env env, napi_async_work work);
 napi_status napi_create_reference(napi_env env, napi_value value, uint32_t initial_refcount, napi_ref* result);

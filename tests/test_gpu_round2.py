@@ -309,3 +309,48 @@ def test_identical_points_and_scalars(label):
             assert eng.msm(sc, n=n, c=c)[0] == exp, (label, c)
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("label", ["bls12-377", "ed-on-bls12-377"])
+def test_prefetched_scalars(label):
+    """mgb_msm_prefetch: scalar sets uploaded ahead of their MSM give the same point as the plain call; a set that was
+    prefetched but is not the one passed is simply not used; at most two sets wait; the sharded entry point consumes
+    them too (include/montgomery_b200.h)."""
+    cv = CURVES[label]
+    n = 3000
+    eng = m.MsmEngine(cv, 0, 4096)
+    try:
+        eng.random_points(4096, seed=21)
+        sets = [torch.from_numpy(inputs.random_scalars(cv.q, n, 30 + i)).pin_memory() for i in range(4)]
+        plain = [eng.msm(s.numpy())[0] for s in sets]
+        assert plain[0] == closed_form(label, [(21, sets[0].numpy())])
+        # the pipeline of bench.py: the next set travels while the current MSM runs
+        eng.prefetch(sets[0].numpy())
+        got = []
+        for i in range(4):
+            if i + 1 < 4:
+                eng.prefetch(sets[i + 1].numpy())
+            got.append(eng.msm(sets[i].numpy())[0])
+        assert got == plain
+        # a prefetched set that is not the one passed (other pointer, or other n) stays put; the call uploads its own
+        eng.prefetch(sets[0].numpy())
+        assert eng.msm(sets[1].numpy())[0] == plain[1]
+        assert eng.msm(sets[0].numpy(), n=n - 1)[0] == eng.msm(sets[0].numpy()[: n - 1].copy())[0]
+        assert eng.msm(sets[0].numpy())[0] == plain[0]                     # ... and is still there for its own call
+        # the same buffer again with new contents: uploaded again
+        buf = sets[3].numpy()
+        eng.prefetch(buf)
+        buf[:] = sets[2].numpy()
+        eng.prefetch(buf)
+        assert eng.msm(buf)[0] == plain[2]
+        # two sets may wait, a third is refused
+        eng.prefetch(sets[0].numpy())
+        eng.prefetch(sets[1].numpy())
+        with pytest.raises(MsmError):
+            eng.prefetch(sets[2].numpy())
+        assert eng.msm(sets[1].numpy())[0] == plain[1]
+        assert eng.msm_sharded(sets[0].data_ptr(), False, n)[0] == plain[0]
+        with pytest.raises(MsmError):
+            eng.prefetch(sets[0].data_ptr(), n=4097)                       # more than the context holds (raw address: the library checks)
+    finally:
+        eng.close()
