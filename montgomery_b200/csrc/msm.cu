@@ -384,8 +384,8 @@ int msm_core(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const 
   if (opts && opts->verbose > 1) rounds = r_full;
   // affine bucket reduction (opt-in): the bucket trees run to completion, every bucket sum is one affine point
   const bool affine_red = CV::BATCH_AFFINE && opts && opts->affine_reduction && G == 1;
-  if (affine_red) rounds = r_full;
   if (const char* ev = getenv("MGB_DEBUG_NROUNDS")) rounds = std::max(0, std::min(r_full, atoi(ev)));   // tuning aid
+  if (affine_red) rounds = r_full;               // (after the tuning knob: the group trees need complete bucket sums)
   // Elements a bucket has left after the last round are summed once by k_bucket_finish when there are many of them
   // (otherwise k_group_partial adds the single leftover directly as a mixed addition, which is cheaper).
   uint64_t left = 0;

@@ -26,7 +26,7 @@ struct Barrier {   // generation barrier on atomics: the threads outnumber the c
     }
   }
 };
-constexpr int MAX_WARPS = 4;
+constexpr int MAX_WARPS = 32;   // blocks of up to 1024 threads (the scan kernels)
 static Barrier g_warp_bar[MAX_WARPS];
 static Barrier g_block_bar;
 static uint32_t g_slot[MAX_WARPS][32];

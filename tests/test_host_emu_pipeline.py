@@ -1,0 +1,234 @@
+"""CPU test of the WHOLE path behind the C ABI: montgomery_b200/csrc/msm.cu -- context and buffer management, window /
+reduction-geometry choice, round planning, every kernel launch in its shipped order, error paths -- compiled with g++
+against a stand-in CUDA runtime (tests/host_emu/cuda_rt_emu.h: "device" memory is host memory, a launch runs the grid
+block after block as lockstep host threads, tests/host_emu/cuda_emu.h) and driven exactly as a C host drives the
+product: mgb_create -> mgb_set_points / mgb_random_points -> mgb_msm, results bit-exact against the oracle.
+
+The only edit to the shipped source is mechanical and done here at build time (tests/host_emu/make_emu_host.py): each
+`kernel<<<grid, block, 0, stream>>>(args)` becomes `emu_launch(grid, block, [&] { kernel(args); })`.  The emulated device
+has 2 "SMs", so persistent grids are 8 blocks; inputs are a few hundred points (one MSM takes seconds).  This library is
+test infrastructure: it is built into a temporary directory, bound here with ctypes, and never loaded by the package --
+the product has no CPU path (montgomery_b200/_native.py fails loudly without the CUDA library).  The GPU versions of
+these checks are tests/test_gpu_*.py."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from montgomery_b200 import _native, curves, inputs
+from tests.helpers import OracleCurve, points_to_bytes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.timeout(900)
+E_INVALID, E_STATE = -1, -4
+
+
+class EmuHost:
+    """The calls of include/montgomery_b200.h that the tests use, bound on the emulated build."""
+
+    def __init__(self, path):
+        lib = ctypes.CDLL(path)
+        vp, sz, ci = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+        po, pt = ctypes.POINTER(_native.MgbOpts), ctypes.POINTER(_native.MgbTiming)
+        lib.mgb_create.argtypes = [ctypes.POINTER(vp), ci, ci, sz]
+        lib.mgb_set_points.argtypes = [vp, vp, vp, sz]
+        lib.mgb_random_points.argtypes = [vp, ctypes.c_uint64, sz]
+        lib.mgb_get_points.argtypes = [vp, sz, sz, vp, vp]
+        lib.mgb_msm.argtypes = [vp, vp, sz, po, vp, ctypes.POINTER(ci), pt]
+        lib.mgb_msm_prefetch.argtypes = [vp, vp, sz]
+        lib.mgb_partial_bytes.argtypes = [vp]
+        lib.mgb_partial_bytes.restype = sz
+        lib.mgb_msm_partial.argtypes = [vp, vp, ci, sz, po, vp, pt]
+        lib.mgb_combine_partials.argtypes = [vp, vp, ci, vp, ctypes.POINTER(ci)]
+        lib.mgb_msm_sharded.argtypes = [vp, vp, ci, sz, po, vp, ctypes.POINTER(ci), pt]
+        lib.mgb_last_error.argtypes = [vp]
+        lib.mgb_last_error.restype = ctypes.c_char_p
+        lib.mgb_destroy.argtypes = [vp]
+        lib.mgb_destroy.restype = None
+        self.lib = lib
+
+    def create(self, label, max_points):
+        cv = curves.BY_LABEL[label]
+        h = ctypes.c_void_p()
+        rc = self.lib.mgb_create(ctypes.byref(h), cv.curve_id, 0, max_points)
+        assert rc == 0, self.lib.mgb_last_error(None)
+        return Ctx(self.lib, h, cv, label)
+
+
+class Ctx:
+    def __init__(self, lib, h, cv, label):
+        self.lib, self.h, self.cv, self.label = lib, h, cv, label
+
+    def error(self):
+        return (self.lib.mgb_last_error(self.h) or b"").decode()
+
+    def random_points(self, n, seed):
+        assert self.lib.mgb_random_points(self.h, seed, n) == 0, self.error()
+        return self.get_points(n)
+
+    def set_points(self, pts):
+        xy, z = points_to_bytes(pts, self.cv.coord_bytes)
+        assert self.lib.mgb_set_points(self.h, xy.ctypes.data, z.ctypes.data, len(pts)) == 0, self.error()
+
+    def get_points(self, n):
+        cb = self.cv.coord_bytes
+        xy = np.zeros(n * 2 * cb, np.uint8)
+        z = np.zeros(n, np.uint8)
+        assert self.lib.mgb_get_points(self.h, 0, n, xy.ctypes.data, z.ctypes.data) == 0, self.error()
+        rows = xy.reshape(n, 2 * cb)
+        return [None if f else (int.from_bytes(r[:cb].tobytes(), "little"), int.from_bytes(r[cb:].tobytes(), "little")) for r, f in zip(rows, z)]
+
+    def _point(self, out, flag):
+        cb = self.cv.coord_bytes
+        return {"x": int.from_bytes(out[:cb].tobytes(), "little"), "y": int.from_bytes(out[cb:].tobytes(), "little"), "isZero": bool(flag.value)}
+
+    def msm(self, sc, n=None, expect_rc=0, **o):
+        n = sc.shape[0] if n is None else n
+        out = np.zeros(2 * self.cv.coord_bytes, np.uint8)
+        flag = ctypes.c_int(0)
+        tm = _native.MgbTiming()
+        opts = _native.MgbOpts(o.get("c", 0), 0, 0, o.get("projective", 0), o.get("affine_reduction", 0))
+        rc = self.lib.mgb_msm(self.h, sc.ctypes.data, n, ctypes.byref(opts), out.ctypes.data, ctypes.byref(flag), ctypes.byref(tm))
+        assert rc == expect_rc, (rc, self.error())
+        return (self._point(out, flag), tm.as_dict()) if rc == 0 else (None, None)
+
+    def close(self):
+        self.lib.mgb_destroy(self.h)
+
+
+@pytest.fixture(scope="module")
+def host(tmp_path_factory):
+    d = tmp_path_factory.mktemp("emu_host")
+    src, so = str(d / "msm_emu.cpp"), str(d / "libmgb_emu.so")
+    emu = os.path.join(ROOT, "tests", "host_emu")
+    subprocess.check_call([sys.executable, os.path.join(emu, "make_emu_host.py"), os.path.join(ROOT, "montgomery_b200", "csrc", "msm.cu"), src])
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-DMGB_HOST_EMU", "-I", emu,
+                           "-I", os.path.join(ROOT, "montgomery_b200", "csrc"), "-I", os.path.join(ROOT, "include"),
+                           "-include", "cuda_rt_emu.h", src, "-o", so, "-ldl"])
+    return EmuHost(so)
+
+
+def oracle_msm(label, sc, pts):
+    return OracleCurve(label).msm(inputs.scalars_to_ints(sc), pts)
+
+
+@pytest.mark.parametrize("label", ["bls12-377", "pallas", "ed-on-bls12-377", "bls12-381"])
+def test_whole_msm_default_plan(host, label):
+    """random points made on the (emulated) device, read back, one MSM with the engine's own window and round choice"""
+    ctx = host.create(label, 128)
+    try:
+        pts = ctx.random_points(96, seed=11)
+        sc = inputs.random_scalars(ctx.cv.q, 96, 12)
+        res, tm = ctx.msm(sc)
+        assert res == oracle_msm(label, sc, pts), tm
+        assert tm["n_launches"] >= 10 and tm["K"] * tm["c"] >= 126
+        # fewer scalars than points held: the first n pairs; n = 0: the neutral element
+        assert ctx.msm(sc, n=17)[0] == oracle_msm(label, sc[:17], pts[:17])
+        assert ctx.msm(sc, n=0)[0] == OracleCurve(label).result_of(None if label != "ed-on-bls12-377" else (0, 1))
+    finally:
+        ctx.close()
+
+
+def test_deep_trees_and_both_reductions(host, monkeypatch):
+    """three tree rounds of batched-affine additions (pair lists handed from round to round), bucket finish, then the default
+    (XYZZ, digit-decomposed) and the affine bucket reduction; points uploaded as bytes, with a point at infinity, a repeated
+    point and a pair P, -P among them"""
+    label = "bls12-377"
+    ctx = host.create(label, 320)
+    try:
+        O = OracleCurve(label)
+        pts = [O.scale(3 + 5 * i, O.G) for i in range(300)]
+        pts[7] = None
+        pts[20] = pts[21] = pts[22]
+        pts[31] = (pts[30][0], (-pts[30][1]) % O.prm.p)
+        ctx.set_points(pts)
+        assert ctx.get_points(300) == pts
+        sc = inputs.random_scalars(ctx.cv.q, 300, 5)
+        sc[20] = sc[21] = sc[22]                              # same point, same scalar: doublings inside a bucket
+        sc[31] = sc[30]
+        exp = oracle_msm(label, sc, pts)
+        monkeypatch.setenv("MGB_DEBUG_NROUNDS", "3")
+        res, tm = ctx.msm(sc, c=6)
+        assert res == exp and tm["rounds"] == 3, tm
+        res, tm = ctx.msm(sc, c=6, affine_reduction=1)         # trees run to completion, group trees through k_batch_add
+        assert res == exp, tm
+        monkeypatch.delenv("MGB_DEBUG_NROUNDS")
+        assert ctx.msm(sc, c=9)[0] == exp                      # another window size: two digits of the bucket index
+        assert ctx.msm(sc, projective=1)[0] == exp             # msmProjective: no GLV, no batched-affine rounds
+    finally:
+        ctx.close()
+
+
+def test_error_paths_and_state(host):
+    ctx = host.create("ed-on-bls12-377", 64)
+    try:
+        sc = inputs.random_scalars(ctx.cv.q, 64, 3)
+        ctx.msm(sc, expect_rc=E_STATE)                         # no points yet
+        pts = ctx.random_points(64, seed=2)
+        ctx.msm(sc, c=30, expect_rc=E_INVALID)                 # window out of range
+        assert "window" in ctx.error()
+        big = sc.copy()
+        big[5, 31] = 0xFF                                      # >= 2^251 on the path without decomposition
+        ctx.msm(big, expect_rc=E_INVALID)
+        assert "out of range" in ctx.error()
+        assert ctx.msm(sc)[0] == oracle_msm("ed-on-bls12-377", sc, pts)    # the context is still usable
+        h2 = ctypes.c_void_p()
+        assert host.lib.mgb_create(ctypes.byref(h2), 17, 0, 8) == E_INVALID   # unknown curve
+    finally:
+        ctx.close()
+
+
+def test_partials_combine_and_sharded_entry(host):
+    """the multi-GPU building blocks on one emulated device: two shards -> partial accumulators -> combine = the whole MSM;
+    the sharded entry point without a communicator is a one-rank job"""
+    label = "pallas"
+    a, b = host.create(label, 64), host.create(label, 64)
+    try:
+        O = OracleCurve(label)
+        pts = [O.scale(7 + 3 * i, O.G) for i in range(100)]
+        a.set_points(pts[:50])
+        b.set_points(pts[50:])
+        sc = inputs.random_scalars(a.cv.q, 100, 9)
+        pb = host.lib.mgb_partial_bytes(a.h)
+        parts = np.zeros(2 * pb, np.uint8)
+        opts = _native.MgbOpts(0, 0, 0, 0, 0)
+        for k, (cx, lo) in enumerate(((a, 0), (b, 50))):
+            rc = host.lib.mgb_msm_partial(cx.h, sc[lo:lo + 50].ctypes.data, 0, 50, ctypes.byref(opts), parts.ctypes.data + k * pb, None)
+            assert rc == 0, cx.error()
+        out = np.zeros(2 * a.cv.coord_bytes, np.uint8)
+        flag = ctypes.c_int(0)
+        assert host.lib.mgb_combine_partials(a.h, parts.ctypes.data, 2, out.ctypes.data, ctypes.byref(flag)) == 0, a.error()
+        assert a._point(out, flag) == oracle_msm(label, sc, pts)
+        flag = ctypes.c_int(0)
+        rc = host.lib.mgb_msm_sharded(a.h, sc[:50].ctypes.data, 0, 50, ctypes.byref(opts), out.ctypes.data, ctypes.byref(flag), None)
+        assert rc == 0 and a._point(out, flag) == oracle_msm(label, sc[:50], pts[:50])
+    finally:
+        a.close()
+        b.close()
+
+
+def test_prefetch_bookkeeping(host):
+    """mgb_msm_prefetch: registered sets are uploaded behind the next MSM's first round and consumed by the call that passes
+    the same pointer and n; anything else falls back to a plain upload; a third waiting set is refused"""
+    label = "bls12-377"
+    ctx = host.create(label, 64)
+    try:
+        pts = ctx.random_points(64, seed=4)
+        sets = [inputs.random_scalars(ctx.cv.q, 64, 40 + i) for i in range(3)]
+        exp = [oracle_msm(label, s, pts) for s in sets]
+        pf = lambda s, n=64: host.lib.mgb_msm_prefetch(ctx.h, s.ctypes.data, n)
+        assert pf(sets[0]) == 0 and pf(sets[1]) == 0
+        assert pf(sets[2]) == E_INVALID and "waiting" in ctx.error()
+        assert ctx.msm(sets[0])[0] == exp[0]                   # never uploaded ahead (no MSM ran since): plain upload; starts set 1
+        sets[2][:] = sets[0]                                   # a buffer that is NOT registered may change freely
+        assert ctx.msm(sets[1])[0] == exp[1]                   # consumed from the prefetched copy
+        assert pf(sets[1]) == 0
+        assert ctx.msm(sets[2])[0] == exp[0]                   # other pointer: own upload; set 1 is uploaded meanwhile
+        assert ctx.msm(sets[1], n=63)[0] == oracle_msm(label, sets[1][:63], pts[:63])   # other n: not the registered set
+        assert ctx.msm(sets[1])[0] == exp[1]
+        assert pf(sets[0], 65) == E_INVALID                    # more than the context holds
+    finally:
+        ctx.close()
