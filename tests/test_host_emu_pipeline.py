@@ -232,3 +232,18 @@ def test_prefetch_bookkeeping(host):
         assert pf(sets[0], 65) == E_INVALID                    # more than the context holds
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("label,c", [("pallas", 2), ("pallas", 4), ("pallas", 8), ("pallas", 11), ("ed-on-bls12-377", 3), ("ed-on-bls12-377", 9)])
+def test_window_sizes(host, label, c):
+    """one, two and three reduction digits, a clipped top window (c = 11: 128 = 11 * 11 + 7 bits), the smallest windows"""
+    ctx = host.create(label, 64)
+    try:
+        pts = ctx.random_points(48, seed=100 + c)
+        sc = inputs.random_scalars(ctx.cv.q, 48, 200 + c)
+        sc[3] = 0                                              # a zero scalar contributes to no bucket
+        sc[4] = np.frombuffer(int(ctx.cv.q - 1).to_bytes(32, "little"), dtype=np.uint8)
+        res, tm = ctx.msm(sc, c=c)
+        assert res == oracle_msm(label, sc, pts) and tm["c"] == c, tm
+    finally:
+        ctx.close()
