@@ -8,6 +8,7 @@
 #include "cuda_emu.h"
 #include <chrono>
 #include <cstdlib>
+#include <mutex>
 
 typedef int cudaError_t;
 enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2 };
@@ -23,7 +24,7 @@ struct dim3 { unsigned x, y, z; dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned 
 #define MGB_EMU_SM_COUNT 2        // "SMs" of the emulated device: persistent grids are sm_count x blocks-per-SM
 #endif
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
-inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaGetDeviceCount(int* n) { *n = 4; return cudaSuccess; }   // four "devices" (all the same host memory) for the mgb_multi_* tests
 inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { p->multiProcessorCount = MGB_EMU_SM_COUNT; return cudaSuccess; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline const char* cudaGetErrorString(cudaError_t) { return "emulated runtime"; }
@@ -50,7 +51,7 @@ inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(b->ms - a->ms); return cudaSuccess; }
 template <class K> inline cudaError_t cudaFuncSetAttribute(K, int, int) { return cudaSuccess; }
 
-// the NCCL types msm.cu names (the library itself is bound with dlopen at run time and never called by these tests)
+// the NCCL types msm.cu names (the library itself is bound with dlopen at run time; the tests hand it tests/host_emu/fake_nccl.cpp)
 typedef int ncclResult_t;
 enum { ncclSuccess = 0 };
 typedef struct ncclComm* ncclComm_t;
@@ -58,9 +59,13 @@ struct ncclUniqueId { char internal[128]; };
 typedef int ncclDataType_t;
 enum { ncclUint8 = 1 };
 
-// kernel launch: the blocks of a (one- or two-dimensional) grid one after the other, each as `threads` lockstep host threads
+// kernel launch: the blocks of a (one- or two-dimensional) grid one after the other, each as `threads` lockstep host threads.
+// One launch at a time in the process: the block state of the emulation (blockIdx, the barriers, __shared__ statics) is
+// global, and mgb_multi_* / the sharded tests drive several contexts from several host threads.
+inline std::mutex& emu_launch_mutex() { static std::mutex mu; return mu; }   // (not a static of the template below: one per process)
 template <class F>
 inline void emu_launch(dim3 grid, unsigned threads, F body) {
+  std::lock_guard<std::mutex> lk(emu_launch_mutex());
   gridDim.x = grid.x; gridDim.y = grid.y; blockDim.x = threads;
   for (unsigned by = 0; by < grid.y; by++)
     for (unsigned bx = 0; bx < grid.x; bx++) {

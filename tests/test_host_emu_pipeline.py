@@ -48,6 +48,19 @@ class EmuHost:
         lib.mgb_last_error.restype = ctypes.c_char_p
         lib.mgb_destroy.argtypes = [vp]
         lib.mgb_destroy.restype = None
+        pi = ctypes.POINTER(ci)
+        lib.mgb_comm_unique_id.argtypes = [vp]
+        lib.mgb_comm_init.argtypes = [vp, vp, ci, ci]
+        lib.mgb_comm_info.argtypes = [vp, pi, pi, pi]
+        lib.mgb_multi_create.argtypes = [ctypes.POINTER(vp), ci, pi, ci, sz]
+        lib.mgb_multi_set_points.argtypes = [vp, vp, vp, sz]
+        lib.mgb_multi_random_points.argtypes = [vp, ctypes.c_uint64, sz]
+        lib.mgb_multi_get_points.argtypes = [vp, sz, sz, vp, vp]
+        lib.mgb_multi_msm.argtypes = [vp, vp, sz, po, vp, pi, pt]
+        lib.mgb_multi_last_error.argtypes = [vp]
+        lib.mgb_multi_last_error.restype = ctypes.c_char_p
+        lib.mgb_multi_destroy.argtypes = [vp]
+        lib.mgb_multi_destroy.restype = None
         self.lib = lib
 
     def create(self, label, max_points):
@@ -108,7 +121,13 @@ def host(tmp_path_factory):
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-DMGB_HOST_EMU", "-I", emu,
                            "-I", os.path.join(ROOT, "montgomery_b200", "csrc"), "-I", os.path.join(ROOT, "include"),
                            "-include", "cuda_rt_emu.h", src, "-o", so, "-ldl"])
-    return EmuHost(so)
+    # the collective of the multi-GPU entry points: msm.cu binds NCCL with dlopen; the emulated build gets an in-process
+    # stand-in (ranks = host threads) through the same MGB_NCCL_LIB override a host with an unusual NCCL path would use
+    nccl = str(d / "libfake_nccl.so")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-pthread", os.path.join(emu, "fake_nccl.cpp"), "-o", nccl])
+    os.environ["MGB_NCCL_LIB"] = nccl
+    yield EmuHost(so)
+    os.environ.pop("MGB_NCCL_LIB", None)
 
 
 def oracle_msm(label, sc, pts):
@@ -247,3 +266,109 @@ def test_window_sizes(host, label, c):
         assert res == oracle_msm(label, sc, pts) and tm["c"] == c, tm
     finally:
         ctx.close()
+
+
+def _read_point(cv, out, flag):
+    cb = cv.coord_bytes
+    return {"x": int.from_bytes(out[:cb].tobytes(), "little"), "y": int.from_bytes(out[cb:].tobytes(), "little"), "isZero": bool(flag.value)}
+
+
+def test_one_process_several_devices(host):
+    """mgb_multi_*: three (emulated) devices behind one handle, one host thread per device, the all-gather of the partial
+    accumulators through the stand-in NCCL: contiguous shards, reads across shard borders, n below the point count (a
+    partly used and an empty shard), n = 0, device-made points"""
+    label = "pallas"
+    cv = curves.BY_LABEL[label]
+    lib = host.lib
+    devs = (ctypes.c_int * 3)(0, 1, 2)
+    m = ctypes.c_void_p()
+    assert lib.mgb_multi_create(ctypes.byref(m), cv.curve_id, devs, 3, 40) == 0, lib.mgb_multi_last_error(None)
+    try:
+        O = OracleCurve(label)
+        pts = [O.scale(11 + 7 * i, O.G) for i in range(100)]
+        pts[35] = None                                         # a point at infinity in the second shard
+        xy, z = points_to_bytes(pts, cv.coord_bytes)
+        assert lib.mgb_multi_set_points(m, xy.ctypes.data, z.ctypes.data, 100) == 0, lib.mgb_multi_last_error(m)
+
+        def get(first, n):
+            cb = cv.coord_bytes
+            o, f = np.zeros(n * 2 * cb, np.uint8), np.zeros(n, np.uint8)
+            assert lib.mgb_multi_get_points(m, first, n, o.ctypes.data, f.ctypes.data) == 0, lib.mgb_multi_last_error(m)
+            rows = o.reshape(n, 2 * cb)
+            return [None if fl else (int.from_bytes(r[:cb].tobytes(), "little"), int.from_bytes(r[cb:].tobytes(), "little")) for r, fl in zip(rows, f)]
+
+        assert get(0, 100) == pts and get(30, 45) == pts[30:75]   # shards of 34 / 34 / 32 points
+
+        def msm(sc, n, expect_rc=0):
+            out, flag, tm = np.zeros(2 * cv.coord_bytes, np.uint8), ctypes.c_int(0), _native.MgbTiming()
+            rc = lib.mgb_multi_msm(m, sc.ctypes.data, n, None, out.ctypes.data, ctypes.byref(flag), ctypes.byref(tm))
+            assert rc == expect_rc, (rc, lib.mgb_multi_last_error(m))
+            return _read_point(cv, out, flag) if rc == 0 else None
+
+        sc = inputs.random_scalars(cv.q, 100, 21)
+        assert msm(sc, 100) == oracle_msm(label, sc, pts)
+        assert msm(sc, 40) == oracle_msm(label, sc[:40], pts[:40])     # device 1 uses 6 of its points, device 2 none
+        assert msm(sc, 0) == O.result_of(None)
+        msm(sc, 101, expect_rc=E_INVALID)
+        assert lib.mgb_multi_set_points(m, xy.ctypes.data, z.ctypes.data, 121) == E_INVALID   # 41 per device > 40
+        assert b"device" in lib.mgb_multi_last_error(m)
+        # points made on the devices: shard g is the known-dlog set of seed + g
+        assert lib.mgb_multi_random_points(m, 77, 60) == 0, lib.mgb_multi_last_error(m)
+        rp = get(0, 60)
+        assert all(O.A.is_on_curve(p) for p in rp) and len(set(rp)) == 60
+        assert msm(sc, 60) == oracle_msm(label, sc[:60], rp)
+    finally:
+        lib.mgb_multi_destroy(m)
+
+
+def test_one_context_per_rank_with_communicator(host, monkeypatch):
+    """mgb_comm_unique_id / mgb_comm_init / mgb_msm_sharded as an SPMD host uses them (here: one thread per rank): every
+    rank ends with the same canonical sum; an empty shard; state errors; an asynchronous NCCL failure is reported"""
+    import threading
+    label = "bls12-377"
+    lib = host.lib
+    ranks = [host.create(label, 64) for _ in range(2)]
+    try:
+        O = OracleCurve(label)
+        pts = [O.scale(5 + 9 * i, O.G) for i in range(80)]
+        ranks[0].set_points(pts[:48])
+        ranks[1].set_points(pts[48:])
+        sc = inputs.random_scalars(ranks[0].cv.q, 80, 33)
+        opts = _native.MgbOpts(0, 0, 0, 0, 0)
+        out = np.zeros(2 * ranks[0].cv.coord_bytes, np.uint8)
+        flag = ctypes.c_int(0)
+        # before mgb_comm_init the context is a one-rank job
+        rk, wd, ver = ctypes.c_int(-1), ctypes.c_int(-1), ctypes.c_int(-1)
+        assert lib.mgb_comm_info(ranks[0].h, ctypes.byref(rk), ctypes.byref(wd), ctypes.byref(ver)) == 0
+        assert (rk.value, wd.value, ver.value) == (0, 1, 99999)      # the version the stand-in reports: it is the library bound
+        uid = np.zeros(_native.COMM_ID_BYTES, np.uint8)
+        assert lib.mgb_comm_unique_id(uid.ctypes.data) == 0
+        assert lib.mgb_comm_init(ranks[0].h, uid.ctypes.data, 2, 2) == E_INVALID   # rank out of range
+
+        def on_ranks(fn):
+            res = [None, None]
+            th = [threading.Thread(target=lambda r=r: res.__setitem__(r, fn(r))) for r in range(2)]
+            [t.start() for t in th]
+            [t.join(600) for t in th]
+            assert not any(t.is_alive() for t in th), "a rank hangs in the collective"
+            return res
+
+        assert on_ranks(lambda r: lib.mgb_comm_init(ranks[r].h, uid.ctypes.data, r, 2)) == [0, 0]
+        assert lib.mgb_comm_init(ranks[0].h, uid.ctypes.data, 0, 2) == E_STATE     # already has a communicator
+        assert lib.mgb_comm_info(ranks[1].h, ctypes.byref(rk), ctypes.byref(wd), None) == 0 and (rk.value, wd.value) == (1, 2)
+
+        def sharded(r, lo, hi):
+            o, f = np.zeros_like(out), ctypes.c_int(0)
+            rc = lib.mgb_msm_sharded(ranks[r].h, sc[lo:hi].ctypes.data if hi > lo else None, 0, hi - lo, ctypes.byref(opts), o.ctypes.data, ctypes.byref(f), None)
+            return rc, (ranks[r]._point(o, f) if rc == 0 else ranks[r].error())
+
+        exp = oracle_msm(label, sc, pts)
+        assert on_ranks(lambda r: sharded(r, *((0, 48), (48, 80))[r])) == [(0, exp), (0, exp)]
+        exp0 = oracle_msm(label, sc[:48], pts[:48])
+        assert on_ranks(lambda r: sharded(r, *((0, 48), (48, 48))[r])) == [(0, exp0), (0, exp0)]    # rank 1's shard is empty
+        monkeypatch.setenv("MGB_FAKE_NCCL_ASYNC_ERROR", "1")
+        res = on_ranks(lambda r: sharded(r, *((0, 48), (48, 80))[r]))
+        assert [rc for rc, _ in res] == [_native.E_COMM] * 2 and "asynchronous" in res[0][1]
+    finally:
+        for cx in ranks:
+            cx.close()
