@@ -43,8 +43,9 @@ enum mgb_error {
   MGB_E_NOMEM = -3,     /* device memory exhausted (the reference's "memory overflow" error,
                            src/wasm/memory-helpers.ts:225-236)                                         */
   MGB_E_STATE = -4,     /* msm called before points were set / sharded msm without a communicator     */
-  MGB_E_COMM = -5       /* NCCL: library not found, communicator set-up or collective failed, or an
-                           asynchronous error reported by ncclCommGetAsyncError                        */
+  MGB_E_COMM = -5       /* NCCL: library not found, communicator set-up or collective failed, an asynchronous
+                           error reported by ncclCommGetAsyncError, or (mgb_msm_sharded) ANOTHER rank could not
+                           compute its shard -- that rank returns its own error code                    */
 };
 
 /* Per-call options; mirrors `{c?, useSafeAdditions?}` of msm-batched-affine.ts:74-77 and
@@ -152,7 +153,14 @@ int mgb_combine_partials(mgb_ctx* ctx, const void* d_partials, int count,
  * ncclAllGather of the un-normalised partial accumulators and one kernel that adds them and
  * normalises.  Every rank receives the same canonical result.  NCCL is bound at run time
  * (dlopen of libnccl.so.2, or the path in MGB_NCCL_LIB): single-GPU hosts do not need it.
- * A context with no communicator (world 1) computes the plain MSM. */
+ * A context with no communicator (world 1) computes the plain MSM.
+ * Failure of one rank (a scalar out of range, a window size that does not fit, device memory): the
+ * status travels with the data -- the failing rank still joins the all-gather (neutral element,
+ * flagged) and returns its own error; every other rank returns MGB_E_COMM and no result.  Nobody
+ * is left waiting in the collective, and nobody gets a sum that misses a shard.  (Argument errors
+ * detected before any work -- NULL pointers, n_local above the points set -- return at once: they
+ * are the caller's to make collectively.)  The reference's workers share one exception through the
+ * barrier timeout of src/threads/threads.ts:319-330. */
 #define MGB_COMM_ID_BYTES 128
 int mgb_comm_unique_id(uint8_t* id_out /* MGB_COMM_ID_BYTES */);
 int mgb_comm_init(mgb_ctx* ctx, const uint8_t* id /* MGB_COMM_ID_BYTES */, int rank, int world);
@@ -183,7 +191,7 @@ void mgb_multi_destroy(mgb_multi* m);
  * op: 0 mul, 1 add, 2 sub, 3 inverse (Fermat), 4 square, 5 inverse (binary gcd), 6 negate,
  * 7 inverse (division steps, the one the MSM uses), 8 mul by the warp-cooperative routine (one limb per
  * lane, csrc/warp.cuh; b is the second factor), 9 inverse by the lane-parallel division-step routine of
- * csrc/warp.cuh (an experiment, not used by the MSM yet). */
+ * csrc/warp.cuh (the one every tile of the accumulation and the final normalisation use). */
 int mgb_field_op(int device, int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n);
 
 /* Integer-pipe microbenchmarks (roofline denominator).  mode: 0 = mad.lo.u32 (IMAD), 1 = mad.hi.u32,

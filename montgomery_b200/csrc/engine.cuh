@@ -140,12 +140,12 @@ struct WeierstrassPolicy {
   // Sum of `count` accumulators (the multi-GPU combine) by ONE warp; every lane returns the sum.  Quad q adds up the
   // partials q, q + 8, ..., then three levels of 4-lane additions (coop.cuh) combine the eight quads: 3 + count / 8
   // addition latencies of ~5 us instead of count - 1 serial 14-product additions (7 x 17 us at eight GPUs).
-  MGB_DEV static acc sum_partials_warp(const uint32_t* accs, int count) {
+  MGB_DEV static acc sum_partials_warp(const uint32_t* accs, int count, int stride = ACC_LIMBS) {
     const int lane = threadIdx.x & 31, k = lane & 3, q = lane >> 2;
     Fe<FP> v = Quad::zero_coord(k);
     for (int base = 0; base < count; base += 8) {          // warp-uniform trip count
       Fe<FP> o = Quad::zero_coord(k);
-      if (base + q < count) o = ld_fe<FP>(accs + (size_t)(base + q) * ACC_LIMBS + k * N);
+      if (base + q < count) o = ld_fe<FP>(accs + (size_t)(base + q) * stride + k * N);
       v = Quad::add(v, o);
     }
     _Pragma("unroll 1") for (int dl = 4; dl >= 1; dl >>= 1) {
@@ -248,9 +248,9 @@ struct TwistedEdwardsPolicy {
     inf = F::is_zero(x) && F::eq(y, o);
   }
   // sum of `count` accumulators on every lane (unified additions, 9 products each; no quad form for this curve)
-  MGB_DEV static acc sum_partials_warp(const uint32_t* accs, int count) {
+  MGB_DEV static acc sum_partials_warp(const uint32_t* accs, int count, int stride = ACC_LIMBS) {
     acc res = ld_acc(accs);
-    for (int i = 1; i < count; i++) res = add(res, ld_acc(accs + (size_t)i * ACC_LIMBS));
+    for (int i = 1; i < count; i++) res = add(res, ld_acc(accs + (size_t)i * stride));
     return res;
   }
   // called by all 32 lanes of a warp with the same accumulator (lane-parallel inversion, see WeierstrassPolicy)
@@ -1368,17 +1368,23 @@ __global__ void __launch_bounds__(32) k_final(int K, int c, const uint32_t* __re
 }
 
 // sum `count` partial accumulators (multi-GPU combine) and/or normalise: out = canonical x||y + flag.  One warp: every
-// lane forms the same sum, the inversion of the normalisation is lane-parallel.
+// lane forms the same sum, the inversion of the normalisation is lane-parallel.  The partials lie `stride` limbs apart;
+// with stride > ACC_LIMBS each is followed by the status word of the rank that sent it (mgb_msm_sharded: non-zero = that
+// rank could not compute its shard), and out_flag[1] tells the host whether any rank reported one.
 template <class CV>
-__global__ void __launch_bounds__(32) k_normalize(const uint32_t* __restrict__ accs, int count, uint32_t* __restrict__ out_xy, uint32_t* __restrict__ out_flag) {
+__global__ void __launch_bounds__(32) k_normalize(const uint32_t* __restrict__ accs, int count, int stride, uint32_t* __restrict__ out_xy, uint32_t* __restrict__ out_flag) {
   if (blockIdx.x != 0) return;
-  const typename CV::acc res = count == 1 ? CV::ld_acc(accs) : CV::sum_partials_warp(accs, count);
+  const typename CV::acc res = count == 1 ? CV::ld_acc(accs) : CV::sum_partials_warp(accs, count, stride);
   Fe<typename CV::P> x, y;
   bool inf;
   CV::acc_to_plain_warp(res, x, y, inf);
   if (threadIdx.x == 0) {
     _Pragma("unroll") for (int i = 0; i < CV::N; i++) { out_xy[i] = x.v[i]; out_xy[CV::N + i] = y.v[i]; }
-    *out_flag = inf ? 1u : 0u;
+    out_flag[0] = inf ? 1u : 0u;
+    uint32_t failed = 0;
+    if (stride > CV::ACC_LIMBS)
+      for (int i = 0; i < count; i++) failed |= accs[(size_t)i * stride + CV::ACC_LIMBS];
+    out_flag[1] = failed;
   }
 }
 

@@ -615,20 +615,24 @@ int finish_timing(mgb_ctx* ctx, mgb_timing* tm) {
   return 0;
 }
 
-// d_accs == nullptr: k_final has normalised already (msm_core with normalize = true), only the read-back is left
+// d_accs == nullptr: k_final has normalised already (msm_core with normalize = true), only the read-back is left.
+// stride_limbs > ACC_LIMBS: the partials are the gathered records of mgb_msm_sharded, each followed by its rank's status
+// word; *peer_failed then tells whether any rank reported that it could not compute its shard.
 template <class CV>
-int normalize_out(mgb_ctx* ctx, const void* d_accs, int count, uint8_t* out_xy, int* out_is_zero) {
+int normalize_out(mgb_ctx* ctx, const void* d_accs, int count, uint8_t* out_xy, int* out_is_zero, int stride_limbs = CV::ACC_LIMBS, bool* peer_failed = nullptr) {
   ENS(ctx, ctx->out_xy, 64 * 4);
   uint32_t* d = (uint32_t*)ctx->out_xy.p;
+  const bool with_status = d_accs && stride_limbs > CV::ACC_LIMBS;
   if (d_accs) {
-    k_normalize<CV><<<1, 32, 0, ctx->stream>>>((const uint32_t*)d_accs, count, d, d + 2 * CV::N);
+    k_normalize<CV><<<1, 32, 0, ctx->stream>>>((const uint32_t*)d_accs, count, stride_limbs, d, d + 2 * CV::N);
     CU(ctx, cudaGetLastError());
   }
-  CU(ctx, cudaMemcpyAsync(ctx->h_pinned, d, (2 * CV::N + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaMemcpyAsync(ctx->h_pinned, d, (2 * CV::N + (with_status ? 2 : 1)) * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CU(ctx, cudaEventRecord(ctx->ev[EV_FINAL], ctx->stream));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
   if (out_xy) memcpy(out_xy, ctx->h_pinned, 2 * CV::COORD_BYTES);
   if (out_is_zero) *out_is_zero = (int)ctx->h_pinned[2 * CV::N];
+  if (peer_failed) *peer_failed = with_status && ctx->h_pinned[2 * CV::N + 1] != 0;
   return 0;
 }
 
@@ -675,28 +679,45 @@ int msm_partial_impl(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n
 // One rank of the sharded MSM: partial sum of the local shard, ONE ncclAllGather of the un-normalised
 // partial accumulators on the engine's own stream straight behind k_final, sum + normalisation of the comm_world
 // partials in one kernel, one device->host copy, one synchronisation.  An empty shard contributes the neutral element.
+// A rank whose shard fails (a scalar out of range, a window size that does not fit, no memory) must not leave its peers
+// waiting in the collective: every rank sends its accumulator followed by a status word, the failing rank joins the
+// all-gather with the neutral element and a non-zero status, returns its own error, and the others return MGB_E_COMM
+// instead of a sum that misses a shard.  (The reference's workers share one address space and one exception,
+// src/threads/threads.ts:319-330; ranks in different processes need the status to travel with the data.)
 template <class CV>
 int msm_sharded_impl(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const mgb_opts* opts, uint8_t* out_xy, int* out_is_zero, mgb_timing* tm) {
   if (tm) memset(tm, 0, sizeof(*tm));
-  const size_t acc_bytes = CV::ACC_LIMBS * 4;
-  ENS(ctx, ctx->acc_out, acc_bytes);
+  constexpr int REC_LIMBS = CV::ACC_LIMBS + 4;              // accumulator + status word, padded to 16 bytes
+  const size_t acc_bytes = CV::ACC_LIMBS * 4, rec_bytes = REC_LIMBS * 4;
+  const bool collective = ctx->comm_world > 1;
+  ENS(ctx, ctx->acc_out, rec_bytes);
+  int local_rc = 0;
+  std::string local_err;
   if (n == 0) {
     k_acc_neutral<CV><<<1, 32, 0, ctx->stream>>>((uint32_t*)ctx->acc_out.p);
     CU(ctx, cudaGetLastError());
   } else {
-    int r = msm_core<CV>(ctx, scalars, on_device, n, opts, tm, ctx->comm_world == 1);
-    if (r) return r;
+    local_rc = msm_core<CV>(ctx, scalars, on_device, n, opts, tm, !collective);
+    if (local_rc && !collective) return local_rc;
   }
-  const void* partials = (ctx->comm_world == 1 && n) ? nullptr : ctx->acc_out.p;
-  if (ctx->comm_world > 1) {
+  const void* partials = (!collective && n) ? nullptr : ctx->acc_out.p;
+  bool peer_failed = false;
+  if (collective) {
     NcclApi* api = nccl_api();
     if (!api || !ctx->comm) return fail(ctx, MGB_E_STATE, "sharded msm: the context has no communicator (mgb_comm_init)");
-    ENS(ctx, ctx->gathered, acc_bytes * ctx->comm_world);
-    NC(ctx, api, api->AllGather(ctx->acc_out.p, ctx->gathered.p, acc_bytes, ncclUint8, ctx->comm, ctx->stream));
+    if (local_rc) {                                         // join the collective all the same, flagged
+      local_err = ctx->err;
+      ENS(ctx, ctx->acc_out, rec_bytes);                    // (msm_core may have failed before it got that far)
+      k_acc_neutral<CV><<<1, 32, 0, ctx->stream>>>((uint32_t*)ctx->acc_out.p);
+      CU(ctx, cudaGetLastError());
+    }
+    CU(ctx, cudaMemsetAsync((char*)ctx->acc_out.p + acc_bytes, local_rc ? 0xff : 0, rec_bytes - acc_bytes, ctx->stream));
+    ENS(ctx, ctx->gathered, rec_bytes * ctx->comm_world);
+    NC(ctx, api, api->AllGather(ctx->acc_out.p, ctx->gathered.p, rec_bytes, ncclUint8, ctx->comm, ctx->stream));
     partials = ctx->gathered.p;
     if (tm) tm->n_launches += 1;
   }
-  int r = normalize_out<CV>(ctx, partials, ctx->comm_world, out_xy, out_is_zero);
+  int r = normalize_out<CV>(ctx, partials, ctx->comm_world, out_xy, out_is_zero, collective ? REC_LIMBS : CV::ACC_LIMBS, &peer_failed);
   if (r) return r;
   if (tm && partials) tm->n_launches += 1;
   if (ctx->comm) {     // asynchronous NCCL failures (a peer died, a transport error) surface here, not as a hang later
@@ -705,6 +726,8 @@ int msm_sharded_impl(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n
     NC(ctx, api, api->CommGetAsyncError(ctx->comm, &async));
     if (async != ncclSuccess) return fail(ctx, MGB_E_COMM, std::string("NCCL asynchronous error: ") + api->GetErrorString(async));
   }
+  if (local_rc) return fail(ctx, local_rc, local_err);
+  if (peer_failed) return fail(ctx, MGB_E_COMM, "sharded msm: another rank could not compute its shard (its own error says why); no result");
   return n ? finish_timing(ctx, tm) : 0;
 }
 
@@ -770,8 +793,10 @@ int multi_each(mgb_multi* m, Fn fn) {
   for (size_t g = 1; g < G; g++) th.emplace_back([&, g] { rc[g] = fn(g); });
   rc[0] = fn(0);
   for (auto& t : th) t.join();
-  for (size_t g = 0; g < G; g++)
-    if (rc[g]) return multi_fail(m, rc[g], "device " + std::to_string(m->ctxs[g]->device) + ": " + m->ctxs[g]->err);
+  // the root cause first: when one device fails its shard the others report MGB_E_COMM ("another rank could not ...")
+  for (int pass = 0; pass < 2; pass++)
+    for (size_t g = 0; g < G; g++)
+      if (rc[g] && (pass == 1 || rc[g] != MGB_E_COMM)) return multi_fail(m, rc[g], "device " + std::to_string(m->ctxs[g]->device) + ": " + m->ctxs[g]->err);
   return 0;
 }
 

@@ -69,11 +69,11 @@ extern "C" void emu_set_get_points(int curve, uint32_t n, const uint32_t* xy, co
   else if (curve == 2) set_get<CurveBls381>(n, xy, is_zero, table, xy_back, zero_back);
   else set_get<CurveEd377>(n, xy, is_zero, table, xy_back, zero_back);
 }
-extern "C" void emu_normalize(int curve, const uint32_t* accs, int count, uint32_t* out_xy, uint32_t* out_flag) {
+extern "C" void emu_normalize(int curve, const uint32_t* accs, int count, int stride, uint32_t* out_xy, uint32_t* out_flag /* 2 words */) {
   simt::run_grid(1, 32, [&] {
-    if (curve == 0) k_normalize<CurveBls377>(accs, count, out_xy, out_flag);
-    else if (curve == 1) k_normalize<CurvePallas>(accs, count, out_xy, out_flag);
-    else if (curve == 2) k_normalize<CurveBls381>(accs, count, out_xy, out_flag);
-    else k_normalize<CurveEd377>(accs, count, out_xy, out_flag);
+    if (curve == 0) k_normalize<CurveBls377>(accs, count, stride, out_xy, out_flag);
+    else if (curve == 1) k_normalize<CurvePallas>(accs, count, stride, out_xy, out_flag);
+    else if (curve == 2) k_normalize<CurveBls381>(accs, count, stride, out_xy, out_flag);
+    else k_normalize<CurveEd377>(accs, count, stride, out_xy, out_flag);
   });
 }

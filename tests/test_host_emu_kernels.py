@@ -314,14 +314,21 @@ def test_set_get_points_and_combine_weierstrass(emu_k, cid, prm, n):
         coords = [0, R % p, 0, 0] if P is None else [P[0] * z * z * R % p, P[1] * z * z * z * R % p, z * z * R % p, z * z * z * R % p]
         for v in coords:
             words += limbs(v)
-    out, flag = (U32 * (2 * n))(), U32(7)
-    emu_k.emu_normalize(cid, (U32 * len(words))(*words), 3, out, ctypes.byref(flag))
-    assert (val(out[:n]), val(out[n:]), flag.value) == (*A.add(pts[0], pts[1]), 0)
+    out, flag = (U32 * (2 * n))(), (U32 * 2)(7, 7)          # flag[0]: the sum is the neutral element, flag[1]: a rank reported a failure
+    emu_k.emu_normalize(cid, (U32 * len(words))(*words), 3, 4 * n, out, flag)
+    assert (val(out[:n]), val(out[n:]), flag[0], flag[1]) == (*A.add(pts[0], pts[1]), 0, 0)
+    # the records mgb_msm_sharded gathers: accumulator + status word (padded to four limbs); any non-zero status is reported
+    for bad in (None, 1):
+        rec = []
+        for k in range(3):
+            rec += words[k * 4 * n:(k + 1) * 4 * n] + [0xFFFFFFFF if k == bad else 0, 9, 9, 9]
+        emu_k.emu_normalize(cid, (U32 * len(rec))(*rec), 3, 4 * n + 4, out, flag)
+        assert (val(out[:n]), val(out[n:]), flag[0]) == (*A.add(pts[0], pts[1]), 0) and (flag[1] != 0) == (bad is not None)
     words2 = words[:4 * n] + [w for w in words[:4 * n]]
     neg = A.negate(pts[0])
     words2[4 * n:] = sum((limbs(v) for v in (neg[0] * R % p, neg[1] * R % p, R % p, R % p)), [])
-    emu_k.emu_normalize(cid, (U32 * len(words2))(*words2), 2, out, ctypes.byref(flag))         # P + (-P): the neutral element
-    assert flag.value == 1 and val(out[:]) == 0
+    emu_k.emu_normalize(cid, (U32 * len(words2))(*words2), 2, 4 * n, out, flag)                # P + (-P): the neutral element
+    assert flag[0] == 1 and val(out[:]) == 0
     # the eight-GPU shape and beyond: 8, 11 and 17 partials (quad q sums q, q + 8, ..., then a tree over the eight quads),
     # with a duplicate (doubling inside the tree) and neutral elements among them
     for count in (8, 11, 17):
@@ -337,5 +344,5 @@ def test_set_get_points_and_combine_weierstrass(emu_k, cid, prm, n):
         exp = None
         for P in sel:
             exp = A.add(exp, P)
-        emu_k.emu_normalize(cid, (U32 * len(words3))(*words3), count, out, ctypes.byref(flag))
-        assert (val(out[:n]), val(out[n:]), flag.value) == ((*exp, 0) if exp is not None else (0, 0, 1)), count
+        emu_k.emu_normalize(cid, (U32 * len(words3))(*words3), count, 4 * n, out, flag)
+        assert (val(out[:n]), val(out[n:]), flag[0]) == ((*exp, 0) if exp is not None else (0, 0, 1)), count

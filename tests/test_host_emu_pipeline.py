@@ -372,3 +372,58 @@ def test_one_context_per_rank_with_communicator(host, monkeypatch):
     finally:
         for cx in ranks:
             cx.close()
+
+
+def test_failed_shard_does_not_hang_the_collective(host):
+    """a rank that cannot compute its shard (here: a scalar out of range on the path without decomposition) still joins the
+    all-gather, flagged: it returns its own error, its peers return MGB_E_COMM instead of waiting forever or of returning a
+    sum that misses a shard; the contexts stay usable.  Same through mgb_multi_msm, which reports the root cause."""
+    import threading
+    label = "ed-on-bls12-377"
+    cv = curves.BY_LABEL[label]
+    lib = host.lib
+    ranks = [host.create(label, 32) for _ in range(2)]
+    m = ctypes.c_void_p()
+    try:
+        pts = ranks[0].random_points(24, seed=8) + ranks[1].random_points(24, seed=9)
+        sc = inputs.random_scalars(cv.q, 48, 44)
+        bad = sc.copy()
+        bad[30, 31] = 0xFF                                     # in rank 1's shard
+        uid = np.zeros(_native.COMM_ID_BYTES, np.uint8)
+        assert lib.mgb_comm_unique_id(uid.ctypes.data) == 0
+        opts = _native.MgbOpts(0, 0, 0, 0, 0)
+
+        def on_ranks(fn):
+            res = [None, None]
+            th = [threading.Thread(target=lambda r=r: res.__setitem__(r, fn(r)), daemon=True) for r in range(2)]
+            [t.start() for t in th]
+            [t.join(300) for t in th]
+            assert not any(t.is_alive() for t in th), "a rank hangs in the collective"
+            return res
+
+        def sharded(r, s):
+            o, f = np.zeros(2 * cv.coord_bytes, np.uint8), ctypes.c_int(0)
+            rc = lib.mgb_msm_sharded(ranks[r].h, s[24 * r:24 * r + 24].ctypes.data, 0, 24, ctypes.byref(opts), o.ctypes.data, ctypes.byref(f), None)
+            return rc, (ranks[r]._point(o, f) if rc == 0 else ranks[r].error())
+
+        assert on_ranks(lambda r: lib.mgb_comm_init(ranks[r].h, uid.ctypes.data, r, 2)) == [0, 0]
+        res = on_ranks(lambda r: sharded(r, bad))
+        assert res[0][0] == _native.E_COMM and "another rank" in res[0][1]
+        assert res[1][0] == E_INVALID and "out of range" in res[1][1]
+        exp = oracle_msm(label, sc, pts)
+        assert on_ranks(lambda r: sharded(r, sc)) == [(0, exp), (0, exp)]
+
+        devs = (ctypes.c_int * 2)(0, 1)
+        assert lib.mgb_multi_create(ctypes.byref(m), cv.curve_id, devs, 2, 32) == 0, lib.mgb_multi_last_error(None)
+        xy, z = points_to_bytes(pts, cv.coord_bytes)
+        assert lib.mgb_multi_set_points(m, xy.ctypes.data, z.ctypes.data, 48) == 0
+        out, flag = np.zeros(2 * cv.coord_bytes, np.uint8), ctypes.c_int(0)
+        assert lib.mgb_multi_msm(m, bad.ctypes.data, 48, None, out.ctypes.data, ctypes.byref(flag), None) == E_INVALID
+        err = lib.mgb_multi_last_error(m).decode()
+        assert "device 1" in err and "out of range" in err
+        assert lib.mgb_multi_msm(m, sc.ctypes.data, 48, None, out.ctypes.data, ctypes.byref(flag), None) == 0
+        assert _read_point(cv, out, flag) == exp
+    finally:
+        for cx in ranks:
+            cx.close()
+        lib.mgb_multi_destroy(m)
