@@ -165,18 +165,51 @@ int default_window(bool glv, size_t n) {
 
 inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
+// Byte ingestion (`pointsFromBytes` + `toMontgomery` as a device kernel overlapped with the host->device
+// copies).  Large point sets travel in chunks through two staging halves: the copy of chunk k + 1 runs on the copy
+// stream while k_set_points converts chunk k, and the staging memory stays bounded (2 x 2^18 points) instead of a second
+// copy of the whole input.  Small sets are one copy and one launch.
 template <class CV>
 int set_points_impl(mgb_ctx* ctx, const uint8_t* xy, const uint8_t* is_zero, size_t n) {
   const size_t pbytes = 2 * CV::COORD_BYTES;
-  ENS(ctx, ctx->stage, n * pbytes + n);
-  CU(ctx, cudaMemcpyAsync(ctx->stage.p, xy, n * pbytes, cudaMemcpyHostToDevice, ctx->stream));
-  uint8_t* dz = nullptr;
-  if (is_zero) {
-    dz = (uint8_t*)ctx->stage.p + n * pbytes;
-    CU(ctx, cudaMemcpyAsync(dz, is_zero, n, cudaMemcpyHostToDevice, ctx->stream));
+  size_t chunk = (size_t)1 << 18;
+  if (const char* ev = getenv("MGB_DEBUG_INGEST_CHUNK")) chunk = std::max(1, atoi(ev));   // (tests: several chunks of a small set)
+  uint32_t* table = (uint32_t*)ctx->table.p;
+  if (n <= chunk) {
+    ENS(ctx, ctx->stage, n * pbytes + n);
+    CU(ctx, cudaMemcpyAsync(ctx->stage.p, xy, n * pbytes, cudaMemcpyHostToDevice, ctx->stream));
+    uint8_t* dz = nullptr;
+    if (is_zero) {
+      dz = (uint8_t*)ctx->stage.p + n * pbytes;
+      CU(ctx, cudaMemcpyAsync(dz, is_zero, n, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    k_set_points<CV><<<cdiv(n, 128), 128, 0, ctx->stream>>>((uint32_t)n, (const uint32_t*)ctx->stage.p, dz, table);
+    CU(ctx, cudaGetLastError());
+  } else {
+    const size_t half = (chunk * (pbytes + 1) + 255) / 256 * 256;     // one staging half: the chunk's x||y bytes, then its flags
+    ENS(ctx, ctx->stage, 2 * half);
+    cudaStream_t cs = ctx->aux[2];
+    cudaEvent_t* landed = ctx->ev_chunk;                              // [h]: the copy into half h has finished
+    cudaEvent_t* drained = ctx->ev_join;                              // [h]: the kernel reading half h has finished
+    size_t k = 0;
+    for (size_t b = 0; b < n; b += chunk, k++) {
+      const size_t cnt = std::min(chunk, n - b);
+      const int h = (int)(k & 1);
+      char* sp = (char*)ctx->stage.p + h * half;
+      if (k >= 2) CU(ctx, cudaStreamWaitEvent(cs, drained[h], 0));
+      CU(ctx, cudaMemcpyAsync(sp, xy + b * pbytes, cnt * pbytes, cudaMemcpyHostToDevice, cs));
+      uint8_t* dz = nullptr;
+      if (is_zero) {
+        dz = (uint8_t*)sp + chunk * pbytes;
+        CU(ctx, cudaMemcpyAsync(dz, is_zero + b, cnt, cudaMemcpyHostToDevice, cs));
+      }
+      CU(ctx, cudaEventRecord(landed[h], cs));
+      CU(ctx, cudaStreamWaitEvent(ctx->stream, landed[h], 0));
+      k_set_points<CV><<<cdiv(cnt, 128), 128, 0, ctx->stream>>>((uint32_t)cnt, (const uint32_t*)sp, dz, table + b * CV::ENTRY_LIMBS);
+      CU(ctx, cudaGetLastError());
+      CU(ctx, cudaEventRecord(drained[h], ctx->stream));
+    }
   }
-  k_set_points<CV><<<cdiv(n, 128), 128, 0, ctx->stream>>>((uint32_t)n, (const uint32_t*)ctx->stage.p, dz, (uint32_t*)ctx->table.p);
-  CU(ctx, cudaGetLastError());
   CU(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->npoints = n;
   return 0;

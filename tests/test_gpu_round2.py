@@ -217,6 +217,59 @@ def test_one_process_multi_device_api(label):
             mg.close()
 
 
+def test_failed_shard_is_reported_not_hung():
+    """mgb_msm_sharded / mgb_multi_msm: a device whose shard holds an out-of-range scalar joins the all-gather flagged; the
+    call returns that device's error (not a hang, not a sum without the shard) and the handle stays usable.  Needs two
+    GPUs for the collective; the CPU suite runs the same scenario on the emulated host (tests/test_host_emu_pipeline.py)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    label = "ed-on-bls12-377"
+    cv = CURVES[label]
+    n = 4096
+    mg = m.MultiGpuMsm(cv, [0, 1], n)
+    try:
+        mg.random_points(n, seed=60)
+        sc = inputs.random_scalars(cv.q, n, 61)
+        bad = sc.copy()
+        bad[n - 5, 31] = 0xFF                                                    # in device 1's shard
+        with pytest.raises(MsmError) as ei:
+            mg.msm(bad)
+        assert ei.value.code == _native.E_INVALID and "device 1" in str(ei.value) and "out of range" in str(ei.value)
+        per = n // 2
+        assert mg.msm(sc)[0] == closed_form(label, [(60, sc[:per]), (61, sc[per:])])
+    finally:
+        mg.close()
+
+
+@pytest.mark.parametrize("label", ["bls12-377", "ed-on-bls12-377"])
+def test_chunked_point_ingestion(label, monkeypatch):
+    """mgb_set_points above 2^18 points: chunks through two staging halves, the copy of the next chunk overlapping the
+    conversion of the current one.  Points made on the device are read back as bytes, fed to a second
+    context, and must give the same table (byte-identical read-back) and the same, closed-form-checked, MSM -- with the
+    default chunk (two chunks, the last one partial) and with 27 small ones."""
+    cv = CURVES[label]
+    n = (1 << 18) + 4097
+    a = m.MsmEngine(cv, 0, n)
+    b = m.MsmEngine(cv, 0, n)
+    try:
+        a.random_points(n, seed=70)
+        xy, z = a.get_points(0, n)
+        sc = inputs.random_scalars(cv.q, n, 71)
+        exp = closed_form(label, [(70, sc)])
+        assert a.msm(sc)[0] == exp
+        for chunk in (None, "10007"):
+            if chunk:
+                monkeypatch.setenv("MGB_DEBUG_INGEST_CHUNK", chunk)
+            assert b.set_points(xy.reshape(-1), z if cv.kind == "weierstrass" else None) == n
+            back, bz = b.get_points(0, n)
+            assert np.array_equal(back, xy) and np.array_equal(bz, z)
+            assert b.msm(sc)[0] == exp
+            b.random_points(16, seed=1)                                          # scribble over the head of the table between the passes
+    finally:
+        a.close()
+        b.close()
+
+
 def test_multi_gpu_one_process_per_gpu():
     """The bench's multi-GPU path: torchrun, one process per GPU, communicator owned by the context (mgb_comm_init),
     mgb_msm_sharded; closed form over all ranks' shards on three curves, plus ranks with empty shards."""

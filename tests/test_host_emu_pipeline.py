@@ -181,6 +181,30 @@ def test_deep_trees_and_both_reductions(host, monkeypatch):
         ctx.close()
 
 
+@pytest.mark.parametrize("label", ["bls12-381", "ed-on-bls12-377"])
+def test_chunked_ingestion(host, label, monkeypatch):
+    """mgb_set_points in several chunks through the two staging halves (the path of point sets above 2^18, forced here with
+    7 points per chunk): every point and every infinity flag lands at its own index; chunk borders, a last partial chunk,
+    flags absent; then an MSM over the table"""
+    ctx = host.create(label, 64)
+    try:
+        O = OracleCurve(label)
+        pts = [O.scale(2 + 3 * i, O.G) for i in range(52)]
+        if O.kind == "weierstrass":
+            pts[6] = pts[7] = pts[51] = None                   # the last point of a chunk, the first of the next, the very last
+        monkeypatch.setenv("MGB_DEBUG_INGEST_CHUNK", "7")
+        ctx.set_points(pts)
+        assert ctx.get_points(52) == pts
+        xy, _ = points_to_bytes(pts[8:50], ctx.cv.coord_bytes)
+        assert ctx.lib.mgb_set_points(ctx.h, xy.ctypes.data, None, 42) == 0, ctx.error()      # no flags: 6 whole chunks
+        assert ctx.get_points(42) == pts[8:50]
+        monkeypatch.delenv("MGB_DEBUG_INGEST_CHUNK")
+        sc = inputs.random_scalars(ctx.cv.q, 42, 6)
+        assert ctx.msm(sc)[0] == oracle_msm(label, sc, pts[8:50])
+    finally:
+        ctx.close()
+
+
 def test_error_paths_and_state(host):
     ctx = host.create("ed-on-bls12-377", 64)
     try:
