@@ -205,6 +205,29 @@ def test_chunked_ingestion(host, label, monkeypatch):
         ctx.close()
 
 
+def test_skewed_buckets_and_tuning_paths(host, monkeypatch):
+    """one scalar value for most of the input: a single bucket per window holds nearly every point, so the trees get their
+    forced depth (at most 16 leftovers per bucket) and every round hands a long pair list on; then the same input through
+    the mechanisms that stay in the library for tuning -- window groups on separate streams, the reduction with and
+    without the bucket-finish kernel, another chunking of the group sums -- all the same canonical point"""
+    label = "pallas"
+    ctx = host.create(label, 160)
+    try:
+        pts = ctx.random_points(150, seed=31)
+        sc = inputs.random_scalars(ctx.cv.q, 150, 32)
+        sc[10:140] = sc[9]                                     # 131 points share every digit
+        exp = oracle_msm(label, sc, pts)
+        res, tm = ctx.msm(sc, c=7)
+        assert res == exp and tm["max_bucket"] >= 131 and tm["rounds"] >= 4, tm
+        for knob, val in (("MGB_DEBUG_GROUPS", "3"), ("MGB_DEBUG_FINISH", "0"), ("MGB_DEBUG_FINISH", "1"), ("MGB_DEBUG_CH", "4")):
+            monkeypatch.setenv(knob, val)
+            res, tm = ctx.msm(sc, c=7)
+            assert res == exp, (knob, val, tm)
+            monkeypatch.delenv(knob)
+    finally:
+        ctx.close()
+
+
 def test_error_paths_and_state(host):
     ctx = host.create("ed-on-bls12-377", 64)
     try:
