@@ -352,24 +352,26 @@ def run_b200(args):
     lib.mgb_microbench(local, 6, 4, 256, 2000, ctypes.byref(ops), ctypes.byref(msb))     # Fp377 Montgomery products, 8 warps per scheduler
     peak_fp377_mults = ops.value
 
-    # ---- the other BASELINE configs (single-GPU sizes: measured at N = 1 only) and config 5 (2^24 in total, every N)
+    # ---- the other BASELINE configs (the named size on every GPU of the run, like the headline: weak scaling; the CPU port
+    # beside them at N = 1) and config 5 (2^24 in total, every N)
     extra_steps, extra_warm = max(3, min(args.steps, 10)), 3
     configs = {}
     cpu_host_threads = os.cpu_count() or 1
-    if world == 1 and args.logn == LOGN_DEFAULT and args.curve == "bls12-377" and not args.no_extras:
+    if args.logn == LOGN_DEFAULT and args.curve == "bls12-377" and not args.no_extras:
         sharded.close()
         for name, cfg in EXTRA_CONFIGS.items():
             r = measure(cfg["curve"], cfg["logn"], SEED_POINTS ^ (cfg["seed_index"] + 1), 0x6D6F6E74 ^ cfg["seed_index"], extra_steps, extra_warm)
             nn = r["n"]
-            dev_ms = r["phases"]["total"]
-            blk = {"workload": "%s MSM, 2^%d points, 1 GPU" % (cfg["curve"], cfg["logn"]), "ms_device": dev_ms,
-                   "ms_per_step": r["el"] / extra_steps * 1e3, "points_per_s": nn / (r["el"] / extra_steps),
-                   "e2e_ms_per_step": r["el_e2e"] / extra_steps * 1e3, "e2e_points_per_s": nn / (r["el_e2e"] / extra_steps),
+            dev_ms = r["dev_ms_max"]            # slowest rank (= this rank's phases["total"] at N = 1)
+            where = "1 GPU" if world == 1 else "per GPU on %d GPUs (weak: %d x 2^%d pairs in total, one all-gather of the partial sums)" % (world, world, cfg["logn"])
+            blk = {"workload": "%s MSM, 2^%d points, %s" % (cfg["curve"], cfg["logn"], where), "n_gpus": world, "ms_device": dev_ms,
+                   "ms_per_step": r["el"] / extra_steps * 1e3, "points_per_s": nn * world / (r["el"] / extra_steps),
+                   "e2e_ms_per_step": r["el_e2e"] / extra_steps * 1e3, "e2e_points_per_s": nn * world / (r["el_e2e"] / extra_steps),
                    "e2e_pipelined_ms_per_step": r["el_pipe"] and r["el_pipe"] / extra_steps * 1e3,
                    "roofline_frac": cfg["mults_per_point"] * cfg["mads_per_mult"] * nn / (dev_ms * 1e-3) / peak_mads,
                    "window_bits": r["tm"]["c"], "windows": r["tm"]["K"], "tree_rounds": r["tm"]["rounds"], "kernels_per_msm": r["tm"]["n_launches"],
                    "phases_ms": r["phases"], "parity_ok": r["parity_ok"]}
-            if not args.no_cpu_baseline:
+            if world == 1 and not args.no_cpu_baseline:
                 pts, _ = r["sharded"].engine.get_points(0, nn)
                 cres, cms = cpu_reference_msm(cfg["curve"], pts, r["host_sets"][0].numpy(), nn, cpu_host_threads)
                 gres, _ = r["sharded"].engine.msm(r["host_sets"][0].numpy(), n=nn)

@@ -3,13 +3,15 @@
 //
 // Pipeline (reference phases in brackets, src/msm-batched-affine.ts):
 //   k_digits      GLV split + signed c-bit digits + bucket histogram         [:350-421, :175-205]
-//   scan          exclusive scan of the histogram -> bucket offsets          [:423-447]
+//   k_scan_*      exclusive scan of the histogram -> bucket offsets, exact size of every tree round [:423-447]
 //   k_scatter     counting-sort scatter of point references (not points)     [:456-502]
-//   k_plan/k_batch_add  log-depth in-place tree per bucket, batched-affine additions with a
-//                 block-wide Montgomery batch inversion over a shared-memory product tree [:243-283,
-//                 src/curve-affine.ts:376-522, src/wasm/inverse.ts:220-271]
-//   k_reduce_*    bucket running sums per window chunk, then segment combination [:556-583]
-//   k_final       Horner over windows + affine normalisation                 [:311-334, curve-projective.ts:335-349]
+//   k_batch_add   log-depth in-place tree per bucket: batched-affine additions, one lane-parallel inversion per
+//                 warp tile of 32 * E additions (k_pair_add on the curves that add without inversion)
+//                 [:243-283, src/curve-affine.ts:376-522, src/wasm/inverse.ts:220-271]
+//   k_bucket_finish, k_group_partial, k_tree_*, k_digit_sums, k_window_assemble
+//                 bucket reduction with the weight split into digits          [:504-583]
+//   k_final       Horner over windows + affine normalisation, one warp       [:311-334, curve-projective.ts:335-349]
+//   k_normalize   sum of the gathered partial accumulators (multi-GPU) + normalisation
 #pragma once
 #ifdef MGB_HOST_EMU
 // host emulation (tests only): tests/host_emu/cuda_emu.h, included first, stands in for the CUDA built-ins used below
@@ -635,8 +637,8 @@ static __global__ void k_plan_to_host(const uint32_t* __restrict__ misc, const u
 //      also counts the pairs whose sum goes on to the next round: one atomicAdd per TILE then
 //      reserves their range in the next round's pair list;
 //   2. warp-wide inclusive prefix and suffix products of the 32 lane totals by shuffles;
-//   3. lane 0 inverts the grand total with the division-step inverse (the other warps of the
-//      SM keep the multiplier pipe busy meanwhile);
+//   3. the warp inverts the grand total with the lane-parallel division-step inverse (warp.cuh; round 1 left it to
+//      lane 0 while the other warps of the SM kept the multiplier pipe busy);
 //   4. every lane gets the inverse of its own total (2 multiplications), then walks its pairs
 //      backwards: recompute the denominator, peel off its inverse, finish the addition, store.
 //      Continuing sums are appended to the reserved range (ballot + running offset, no atomic).
@@ -712,10 +714,11 @@ __global__ void __launch_bounds__(128, MINB) k_batch_add(uint32_t* __restrict__ 
   constexpr int N = CV::N;
   constexpr int CW = N / 4;             // 16-byte chunks per coordinate
   // staging slots, in chunks: A.x | B.x | A.y | B.y | prefix product | 3 pair entries: 18 chunks = 36 KB per block for a
-  // 12-limb field, so that FIVE blocks are resident per SM (20 warps; registers capped at 96).  The multiplier pipe is
-  // at 63 / 90 / 97 % of its rate with 1 / 2 / 3 warps of a scheduler inside a product at the same time (measured,
-  // profiles/r02_microbench_mul_vs_warps.jsonl) and a warp spends two thirds of its time there, so a fifth warp per
-  // scheduler is worth more than the second x buffer the round-1 kernel kept (48 KB, 4 blocks).
+  // 12-limb field (round 1 kept a second x buffer: 48 KB), four blocks per SM at 128 registers.  The multiplier pipe is
+  // at 63 / 90 / 97 / 98 % of its rate with 1 / 2 / 3 / 4 warps of a scheduler inside a product at the same time
+  // (profiles/r02_microbench_mul_vs_warps.jsonl) and a warp spends two thirds of its time there; the shared memory would
+  // allow a fifth and sixth block, but at 96 / 80 registers those builds spill and were slower (MGB_MINB = 5, 6:
+  // profiles/r02_ab_blocks_per_sm.txt).
   constexpr int ST_A = 0, ST_PRE = 4 * CW, ST_ENT = 5 * CW;
   constexpr int ST_TOTAL = ST_ENT + 3;
   __shared__ uint4 stage[ST_TOTAL][128];   // [chunk][thread]: conflict-free 16-byte accesses
@@ -1337,7 +1340,6 @@ __global__ void __launch_bounds__(32) k_window_assemble(MsmParams pr, ReduceGeom
 }
 
 // result = sum_w 2^(c*w) S_w by Horner (msm-batched-affine.ts:322-334): (K-1)*c dependent doublings.
-// One 128-thread block; the four warps share the multiplications of each formula level (coop.cuh).
 // out_xy != nullptr (single-GPU msm): the same warp also normalises -- canonical x || y and the is-zero flag, as
 // k_normalize would -- so the result needs no further launch.
 // One warp: the point is spread over the lanes (onewarp.cuh: 8-lane group g = coordinate g, one 64-bit digit per lane, the
