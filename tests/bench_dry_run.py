@@ -6,6 +6,9 @@ Sizes are shrunk (2^7 / 2^6 / 2^10 points), torch's CUDA calls are stubbed ("dev
 emulation), the microbenchmarks return a constant.  Timings mean nothing; `parity_ok` and the structure do.
 
     python tests/bench_dry_run.py            # prints the JSON line; exit code 0 = the whole script ran and parity held
+    python tests/bench_dry_run.py --ranks 2  # the multi-GPU shape: one process per rank as torchrun starts them,
+                                             # torch.distributed on gloo, the engine's own collective over the
+                                             # file rendezvous of tests/host_emu/fake_nccl.cpp (~15 minutes)
 """
 import os
 import subprocess
@@ -26,7 +29,7 @@ extern "C" int mgb_microbench(int, int, int, int, int, double* ops, float* ms) {
 
 def build(d):
     src, stub, so = os.path.join(d, "msm_emu.cpp"), os.path.join(d, "stub.cpp"), os.path.join(d, "libmgb_emu.so")
-    subprocess.check_call([sys.executable, os.path.join(EMU, "make_emu_host.py"), os.path.join(ROOT, "montgomery_b200", "csrc", "msm.cu"), src])
+    subprocess.check_call([sys.executable, os.path.join(EMU, "make_emu_host.py"), os.path.join(ROOT, "montgomery_b200", "csrc", "msm.cu"), src], stdout=sys.stderr)
     open(stub, "w").write(STUB)
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-DMGB_HOST_EMU", "-I", EMU,
                            "-I", os.path.join(ROOT, "montgomery_b200", "csrc"), "-I", os.path.join(ROOT, "include"),
@@ -34,9 +37,30 @@ def build(d):
     return so
 
 
-if __name__ == "__main__":
+def run_ranks(world):
+    """parent of a multi-rank dry run: builds once, starts one child per rank, relays rank 0's JSON line"""
     with tempfile.TemporaryDirectory() as d:
-        os.environ["MGB_LIB"] = build(d)          # read by montgomery_b200/_native.py at import
+        so = build(d)
+        nccl = os.path.join(d, "libfake_nccl.so")
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-pthread", os.path.join(EMU, "fake_nccl.cpp"), "-o", nccl])
+        os.makedirs(os.path.join(d, "rendezvous"))
+        procs = []
+        for r in range(world):
+            env = dict(os.environ, MGB_LIB=so, MGB_NCCL_LIB=nccl, MGB_FAKE_NCCL_DIR=os.path.join(d, "rendezvous"), RANK=str(r), LOCAL_RANK=str(r),
+                       WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(29400 + os.getpid() % 500), MGB_DRY_RUN_CHILD="1")
+            procs.append(subprocess.Popen([sys.executable, os.path.abspath(__file__)], env=env, stdout=subprocess.PIPE, text=True))
+        outs = [p.communicate()[0] for p in procs]
+        print(outs[0].strip())
+        return max(p.returncode for p in procs)
+
+
+if __name__ == "__main__":
+    if "--ranks" in sys.argv:
+        sys.exit(run_ranks(int(sys.argv[sys.argv.index("--ranks") + 1])))
+    with tempfile.TemporaryDirectory() as d:
+        child = bool(os.environ.get("MGB_DRY_RUN_CHILD"))
+        if not child:
+            os.environ["MGB_LIB"] = build(d)      # read by montgomery_b200/_native.py at import
         import torch
         torch.cuda.set_device = lambda *a, **k: None
         torch.cuda.synchronize = lambda *a, **k: None
@@ -44,10 +68,15 @@ if __name__ == "__main__":
         torch.Tensor.pin_memory = lambda self, *a, **k: self
         _tensor = torch.tensor
         torch.tensor = lambda *a, device=None, **k: _tensor(*a, **k)
+        world = int(os.environ.get("WORLD_SIZE", "1")) if child else 1
+        if world > 1:
+            import torch.distributed as dist
+            _init = dist.init_process_group
+            dist.init_process_group = lambda backend=None, **k: _init("gloo")      # no device_id: CPU tensors
         import bench
         bench.LOGN_DEFAULT = 7
-        bench.STRONG_LOGN = 10                    # the strong block runs when 2^STRONG_LOGN / world >= 2^10
+        bench.STRONG_LOGN = 10 + (world.bit_length() - 1)      # the strong block runs when 2^STRONG_LOGN / world >= 2^10
         for cfg in bench.EXTRA_CONFIGS.values():
             cfg["logn"] = 6
-        sys.argv = ["bench.py", "--steps", "1", "--warmup", "0", "--logn", "7"]
+        sys.argv = ["bench.py", "--gpus", str(world), "--steps", "1", "--warmup", "0", "--logn", "7"]
         bench.main()

@@ -3,6 +3,9 @@
 // memory is host memory (cuda_rt_emu.h), so the all-gather is a rendezvous of the ranks' threads and a memcpy.  The test
 // points MGB_NCCL_LIB at the library built from this file; nothing in the product links or loads it.
 // Fault injection: MGB_FAKE_NCCL_ASYNC_ERROR=1 makes ncclCommGetAsyncError report a failure.
+// Ranks in DIFFERENT processes (tests/bench_dry_run.py --ranks 2): with MGB_FAKE_NCCL_DIR set, ncclCommInitRank builds a
+// communicator whose all-gather goes through files in that directory (<id>.<sequence>.<rank>, written under a temporary
+// name and renamed, so a reader never sees a partial record).
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -11,6 +14,7 @@
 #include <mutex>
 #include <string>
 #include <vector>
+#include <unistd.h>
 
 typedef int ncclResult_t;
 enum { ncclSuccess = 0, ncclInternalError = 3, ncclInvalidArgument = 4, ncclRemoteError = 6 };
@@ -33,7 +37,7 @@ std::map<std::string, Group*> g_groups;
 int g_next_id = 1;
 }  // namespace
 
-struct ncclComm { Group* grp; int rank; };
+struct ncclComm { Group* grp; int rank; std::string dir, id; int world = 0; long seq = 0; };
 typedef ncclComm* ncclComm_t;
 
 extern "C" {
@@ -49,6 +53,12 @@ ncclResult_t ncclGetUniqueId(ncclUniqueId* id) {
 
 ncclResult_t ncclCommInitRank(ncclComm_t* comm, int world, ncclUniqueId id, int rank) {
   if (!comm || world < 1 || rank < 0 || rank >= world) return ncclInvalidArgument;
+  if (const char* dir = getenv("MGB_FAKE_NCCL_DIR")) {       // one process per rank: file rendezvous
+    ncclComm* c = new ncclComm{nullptr, rank};
+    c->dir = dir; c->id = id.internal; c->world = world;
+    *comm = c;
+    return ncclSuccess;
+  }
   Group* grp;
   {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -75,6 +85,26 @@ ncclResult_t ncclCommInitAll(ncclComm_t* comms, int n, const int*) {
 }
 
 ncclResult_t ncclAllGather(const void* send, void* recv, size_t count, int /*dtype: bytes*/, ncclComm_t comm, void* /*stream*/) {
+  if (!comm->grp) {                                          // file rendezvous between processes
+    const std::string base = comm->dir + "/" + comm->id + "." + std::to_string(comm->seq++) + ".";
+    const std::string mine = base + std::to_string(comm->rank), tmp = mine + ".tmp";
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f || fwrite(send, 1, count, f) != count) return ncclInternalError;
+    fclose(f);
+    if (rename(tmp.c_str(), mine.c_str()) != 0) return ncclInternalError;
+    for (int r = 0; r < comm->world; r++) {
+      const std::string peer = base + std::to_string(r);
+      FILE* g = nullptr;
+      for (long spins = 0; !(g = fopen(peer.c_str(), "rb")); spins++) {
+        if (spins > 3600L * 100) return ncclRemoteError;     // an hour: the peer is gone
+        usleep(10000);
+      }
+      const size_t got = fread((char*)recv + (size_t)r * count, 1, count, g);
+      fclose(g);
+      if (got != count) return ncclInternalError;
+    }
+    return ncclSuccess;
+  }
   Group* grp = comm->grp;
   std::unique_lock<std::mutex> lk(grp->mu);
   grp->send[comm->rank] = send;
@@ -92,6 +122,7 @@ ncclResult_t ncclCommGetAsyncError(ncclComm_t, ncclResult_t* async) {
 
 ncclResult_t ncclCommDestroy(ncclComm_t comm) {
   if (!comm) return ncclSuccess;
+  if (!comm->grp) { delete comm; return ncclSuccess; }
   Group* grp = comm->grp;
   bool last;
   { std::lock_guard<std::mutex> lk(grp->mu); last = --grp->alive == 0; }
