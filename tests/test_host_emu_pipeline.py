@@ -118,7 +118,11 @@ def host(tmp_path_factory):
     src, so = str(d / "msm_emu.cpp"), str(d / "libmgb_emu.so")
     emu = os.path.join(ROOT, "tests", "host_emu")
     subprocess.check_call([sys.executable, os.path.join(emu, "make_emu_host.py"), os.path.join(ROOT, "montgomery_b200", "csrc", "msm.cu"), src])
-    subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-DMGB_HOST_EMU", "-I", emu,
+    # MGB_EMU_CXXFLAGS: e.g. "-O1 -g -fsanitize=address -fno-omit-frame-pointer" (run pytest under LD_PRELOAD=libasan.so with
+    # ASAN_OPTIONS=detect_leaks=0): "device" buffers are heap blocks in the emulation, so AddressSanitizer checks every
+    # kernel's global-memory accesses against the sizes msm.cu allocated -- a memcheck of the whole path without a GPU
+    flags = os.environ.get("MGB_EMU_CXXFLAGS", "-O2").split()
+    subprocess.check_call(["g++", "-std=c++17", *flags, "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-DMGB_HOST_EMU", "-I", emu,
                            "-I", os.path.join(ROOT, "montgomery_b200", "csrc"), "-I", os.path.join(ROOT, "include"),
                            "-include", "cuda_rt_emu.h", src, "-o", so, "-ldl"])
     # the collective of the multi-GPU entry points: msm.cu binds NCCL with dlopen; the emulated build gets an in-process
@@ -357,7 +361,8 @@ def test_one_process_several_devices(host):
         assert msm(sc, 40) == oracle_msm(label, sc[:40], pts[:40])     # device 1 uses 6 of its points, device 2 none
         assert msm(sc, 0) == O.result_of(None)
         msm(sc, 101, expect_rc=E_INVALID)
-        assert lib.mgb_multi_set_points(m, xy.ctypes.data, z.ctypes.data, 121) == E_INVALID   # 41 per device > 40
+        big_xy, big_z = np.zeros(121 * 2 * cv.coord_bytes, np.uint8), np.ones(121, np.uint8)
+        assert lib.mgb_multi_set_points(m, big_xy.ctypes.data, big_z.ctypes.data, 121) == E_INVALID   # 41 per device > 40
         assert b"device" in lib.mgb_multi_last_error(m)
         # points made on the devices: shard g is the known-dlog set of seed + g
         assert lib.mgb_multi_random_points(m, 77, 60) == 0, lib.mgb_multi_last_error(m)
