@@ -4,6 +4,9 @@
 # blocks there, so every global-memory access of every kernel is checked against the size msm.cu allocated for it, and
 # every host-side copy against the caller's buffers.  ~20 minutes on 8 cores; reports land in /tmp/mgb_asan.log.*.
 # Round 2: 20 / 20 tests, no report from the product (the first run caught a test that passed a too short host buffer).
+# The same with UndefinedBehaviorSanitizer (shifts by >= 32 bits and the like mean different things on the host and in
+# PTX, so undefined behaviour in a kernel is a portability bug of the emulation AND a smell on the GPU): no report either --
+#   MGB_EMU_CXXFLAGS="-O1 -g -fsanitize=undefined -fno-sanitize=alignment" python -m pytest tests/test_host_emu_pipeline.py -q
 set -u
 cd "$(dirname "$0")/.."
 rm -f /tmp/mgb_asan.log.*
