@@ -14,5 +14,11 @@ LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:log_pa
   MGB_EMU_CXXFLAGS="-O1 -g -fsanitize=address -fno-omit-frame-pointer" \
   python -m pytest tests/test_host_emu_pipeline.py -q -p no:cacheprovider "$@"
 rc=$?
+# the production geometries (window 16: 2.6e5 buckets, 256 partial sums per group; tile sizes 56 / 28 / 14 / 64) on the same build
+d=$(mktemp -d)
+python tests/host_emu/make_emu_host.py montgomery_b200/csrc/msm.cu $d/msm_emu.cpp > /dev/null
+g++ -std=c++17 -O1 -g -fsanitize=address -fno-omit-frame-pointer -fPIC -shared -pthread -Wno-unknown-pragmas -DMGB_HOST_EMU -I tests/host_emu \
+    -I montgomery_b200/csrc -I include -include cuda_rt_emu.h $d/msm_emu.cpp -o $d/libmgb_emu_asan.so -ldl
+LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:log_path=/tmp/mgb_asan.log python tests/host_emu/geometry_checks.py $d/libmgb_emu_asan.so || rc=1
 ls /tmp/mgb_asan.log.* 2>/dev/null && head -40 /tmp/mgb_asan.log.*
 exit $rc
