@@ -3,7 +3,7 @@ AddressSanitizer build -- small inputs, but the bucket counts, reduction geometr
 so that every buffer size in msm.cu is checked against the kernels' accesses at the shapes the GPU runs:
 
   * window sizes 16 (2^18 .. 2^21 points: three 5-bit digits, 256 partial sums per group, 2.6e5 buckets) and, with
-    --c18, 18 (2^22 points and more: four digits, 2048 partial sums per group, 1e6 buckets; about an hour under ASan);
+    --c18, 18 (2^22 points and more: four digits, 2048 partial sums per group, 1e6 buckets; 26 minutes under ASan);
   * tile sizes of the accumulation as the 2^20 plan picks them (E = 56 / 28 / 14 pairs per lane) and the maximum (64).
 
     python tests/host_emu/geometry_checks.py path/to/libmgb_emu.so [--c18]
