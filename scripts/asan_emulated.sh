@@ -11,7 +11,7 @@ set -u
 cd "$(dirname "$0")/.."
 rm -f /tmp/mgb_asan.log.*
 LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:log_path=/tmp/mgb_asan.log \
-  MGB_EMU_CXXFLAGS="-O1 -g -fsanitize=address -fno-omit-frame-pointer" \
+  MGB_EMU_CXXFLAGS="-O1 -g -fsanitize=address -fno-omit-frame-pointer" MGB_TEST_FULL=1 \
   python -m pytest tests/test_host_emu_pipeline.py -q -p no:cacheprovider "$@"
 rc=$?
 # the production geometries (window 16: 2.6e5 buckets, 256 partial sums per group; tile sizes 56 / 28 / 14 / 64) on the same build

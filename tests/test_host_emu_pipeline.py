@@ -24,6 +24,9 @@ from tests.helpers import OracleCurve, points_to_bytes
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.timeout(900)
 E_INVALID, E_STATE = -1, -4
+# The default run keeps the CPU suite at a few minutes; MGB_TEST_FULL=1 (set by scripts/asan_emulated.sh) adds the cases
+# that repeat a path with other parameters (more window sizes, the tuning mechanisms on a skewed input).
+full_only = pytest.mark.skipif(not os.environ.get("MGB_TEST_FULL"), reason="repeats covered paths with other parameters; MGB_TEST_FULL=1 runs it")
 
 
 class EmuHost:
@@ -209,6 +212,7 @@ def test_chunked_ingestion(host, label, monkeypatch):
         ctx.close()
 
 
+@full_only
 def test_skewed_buckets_and_tuning_paths(host, monkeypatch):
     """one scalar value for most of the input: a single bucket per window holds nearly every point, so the trees get their
     forced depth (at most 16 leftovers per bucket) and every round hands a long pair list on; then the same input through
@@ -304,7 +308,8 @@ def test_prefetch_bookkeeping(host):
         ctx.close()
 
 
-@pytest.mark.parametrize("label,c", [("pallas", 2), ("pallas", 4), ("pallas", 8), ("pallas", 11), ("ed-on-bls12-377", 3), ("ed-on-bls12-377", 9)])
+@pytest.mark.parametrize("label,c", [("pallas", 2), pytest.param("pallas", 4, marks=full_only), pytest.param("pallas", 8, marks=full_only), ("pallas", 11),
+                                     pytest.param("ed-on-bls12-377", 3, marks=full_only), ("ed-on-bls12-377", 9)])
 def test_window_sizes(host, label, c):
     """one, two and three reduction digits, a clipped top window (c = 11: 128 = 11 * 11 + 7 bits), the smallest windows"""
     ctx = host.create(label, 64)
