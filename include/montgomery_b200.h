@@ -157,9 +157,9 @@ int mgb_combine_partials(mgb_ctx* ctx, const void* d_partials, int count,
  * Failure of one rank (a scalar out of range, a window size that does not fit, device memory): the
  * status travels with the data -- the failing rank still joins the all-gather (neutral element,
  * flagged) and returns its own error; every other rank returns MGB_E_COMM and no result.  Nobody
- * is left waiting in the collective, and nobody gets a sum that misses a shard.  (Argument errors
- * detected before any work -- NULL pointers, n_local above the points set -- return at once: they
- * are the caller's to make collectively.)  The reference's workers share one exception through the
+ * is left waiting in the collective, and nobody gets a sum that misses a shard.  The same holds for
+ * the argument errors a single rank can make (n_local above the points it holds, a misaligned device
+ * buffer); only NULL pointers and the `projective` option -- identical on all ranks -- return at once.  The reference's workers share one exception through the
  * barrier timeout of src/threads/threads.ts:319-330. */
 #define MGB_COMM_ID_BYTES 128
 int mgb_comm_unique_id(uint8_t* id_out /* MGB_COMM_ID_BYTES */);

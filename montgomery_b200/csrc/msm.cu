@@ -718,21 +718,24 @@ int msm_partial_impl(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n
 // instead of a sum that misses a shard.  (The reference's workers share one address space and one exception,
 // src/threads/threads.ts:319-330; ranks in different processes need the status to travel with the data.)
 template <class CV>
-int msm_sharded_impl(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const mgb_opts* opts, uint8_t* out_xy, int* out_is_zero, mgb_timing* tm) {
+int msm_sharded_impl(mgb_ctx* ctx, const void* scalars, bool on_device, size_t n, const mgb_opts* opts, uint8_t* out_xy, int* out_is_zero, mgb_timing* tm,
+                     int pre_rc /* a rank-local argument error found by mgb_msm_sharded (message in ctx->err): join flagged, compute nothing */) {
   if (tm) memset(tm, 0, sizeof(*tm));
   constexpr int REC_LIMBS = CV::ACC_LIMBS + 4;              // accumulator + status word, padded to 16 bytes
   const size_t acc_bytes = CV::ACC_LIMBS * 4, rec_bytes = REC_LIMBS * 4;
   const bool collective = ctx->comm_world > 1;
   ENS(ctx, ctx->acc_out, rec_bytes);
-  int local_rc = 0;
+  int local_rc = pre_rc;
   std::string local_err;
-  if (n == 0) {
+  if (local_rc) {
+    // nothing to compute
+  } else if (n == 0) {
     k_acc_neutral<CV><<<1, 32, 0, ctx->stream>>>((uint32_t*)ctx->acc_out.p);
     CU(ctx, cudaGetLastError());
   } else {
     local_rc = msm_core<CV>(ctx, scalars, on_device, n, opts, tm, !collective);
-    if (local_rc && !collective) return local_rc;
   }
+  if (local_rc && !collective) return local_rc;
   const void* partials = (!collective && n) ? nullptr : ctx->acc_out.p;
   bool peer_failed = false;
   if (collective) {
@@ -988,11 +991,15 @@ int mgb_msm_prefetch(mgb_ctx* ctx, const uint8_t* scalars_le32, size_t n) {
 int mgb_msm_sharded(mgb_ctx* ctx, const void* scalars, int scalars_on_device, size_t n_local, const mgb_opts* opts,
                     uint8_t* out_xy_le, int* out_is_zero, mgb_timing* timing) {
   if (!ctx || !out_xy_le || (!scalars && n_local)) return fail(ctx, MGB_E_INVALID, "mgb_msm_sharded: NULL argument");
-  if (n_local > ctx->npoints) return fail(ctx, ctx->npoints ? MGB_E_INVALID : MGB_E_STATE, "mgb_msm_sharded: n_local exceeds the number of points set");
-  if (opts && opts->projective) return fail(ctx, MGB_E_INVALID, "mgb_msm_sharded: the projective cross-check path is single-GPU only");
-  if (scalars_on_device && ((uintptr_t)scalars & 15)) return fail(ctx, MGB_E_INVALID, "mgb_msm_sharded: the device scalar buffer must be 16-byte aligned");
+  if (opts && opts->projective) return fail(ctx, MGB_E_INVALID, "mgb_msm_sharded: the projective cross-check path is single-GPU only");   // (the same on every rank)
+  // argument errors that only THIS rank may have: with a communicator the rank still joins the collective, flagged, so
+  // that its peers return MGB_E_COMM instead of waiting for it (msm_sharded_impl)
+  int pre = 0;
+  if (n_local > ctx->npoints) pre = fail(ctx, ctx->npoints ? MGB_E_INVALID : MGB_E_STATE, "mgb_msm_sharded: n_local exceeds the number of points set");
+  else if (scalars_on_device && ((uintptr_t)scalars & 15)) pre = fail(ctx, MGB_E_INVALID, "mgb_msm_sharded: the device scalar buffer must be 16-byte aligned");
+  if (pre && ctx->comm_world == 1) return pre;
   CU(ctx, cudaSetDevice(ctx->device));
-  DISPATCH(ctx, msm_sharded_impl, ctx, scalars, scalars_on_device != 0, n_local, opts, out_xy_le, out_is_zero, timing);
+  DISPATCH(ctx, msm_sharded_impl, ctx, scalars, scalars_on_device != 0, n_local, opts, out_xy_le, out_is_zero, timing, pre);
 }
 
 /* ---- one host process driving several GPUs (`device_ids, n_devices`) ---- */

@@ -458,15 +458,19 @@ def test_failed_shard_does_not_hang_the_collective(host):
             assert not any(t.is_alive() for t in th), "a rank hangs in the collective"
             return res
 
-        def sharded(r, s):
+        def sharded(r, s, n=24):
             o, f = np.zeros(2 * cv.coord_bytes, np.uint8), ctypes.c_int(0)
-            rc = lib.mgb_msm_sharded(ranks[r].h, s[24 * r:24 * r + 24].ctypes.data, 0, 24, ctypes.byref(opts), o.ctypes.data, ctypes.byref(f), None)
+            rc = lib.mgb_msm_sharded(ranks[r].h, s[24 * r:24 * r + 24].ctypes.data, 0, n, ctypes.byref(opts), o.ctypes.data, ctypes.byref(f), None)
             return rc, (ranks[r]._point(o, f) if rc == 0 else ranks[r].error())
 
         assert on_ranks(lambda r: lib.mgb_comm_init(ranks[r].h, uid.ctypes.data, r, 2)) == [0, 0]
         res = on_ranks(lambda r: sharded(r, bad))
         assert res[0][0] == _native.E_COMM and "another rank" in res[0][1]
         assert res[1][0] == E_INVALID and "out of range" in res[1][1]
+        # an argument error only one rank makes (more pairs than it holds points): rejected before any work, and the rank
+        # still joins, flagged
+        res = on_ranks(lambda r: sharded(r, sc, n=(24, 25)[r]))
+        assert res[0][0] == _native.E_COMM and res[1][0] == E_INVALID and "exceeds" in res[1][1]
         exp = oracle_msm(label, sc, pts)
         assert on_ranks(lambda r: sharded(r, sc)) == [(0, exp), (0, exp)]
 
