@@ -141,7 +141,7 @@ def oracle_msm(label, sc, pts):
     return OracleCurve(label).msm(inputs.scalars_to_ints(sc), pts)
 
 
-@pytest.mark.parametrize("label", ["bls12-377", "pallas", "ed-on-bls12-377", "bls12-381"])
+@pytest.mark.parametrize("label", ["bls12-377", "pallas", "ed-on-bls12-377", pytest.param("bls12-381", marks=full_only)])
 def test_whole_msm_default_plan(host, label):
     """random points made on the (emulated) device, read back, one MSM with the engine's own window and round choice"""
     ctx = host.create(label, 128)
@@ -287,7 +287,7 @@ def test_partials_combine_and_sharded_entry(host):
 def test_prefetch_bookkeeping(host):
     """mgb_msm_prefetch: registered sets are uploaded behind the next MSM's first round and consumed by the call that passes
     the same pointer and n; anything else falls back to a plain upload; a third waiting set is refused"""
-    label = "bls12-377"
+    label = "pallas"
     ctx = host.create(label, 64)
     try:
         pts = ctx.random_points(64, seed=4)
@@ -382,7 +382,7 @@ def test_one_context_per_rank_with_communicator(host, monkeypatch):
     """mgb_comm_unique_id / mgb_comm_init / mgb_msm_sharded as an SPMD host uses them (here: one thread per rank): every
     rank ends with the same canonical sum; an empty shard; state errors; an asynchronous NCCL failure is reported"""
     import threading
-    label = "bls12-377"
+    label = "pallas"
     lib = host.lib
     ranks = [host.create(label, 64) for _ in range(2)]
     try:
